@@ -1,0 +1,118 @@
+"""Loader for the C-ABI CUDA library (``include/farkle_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` (plain ``nvcc
+-shared``; no torch headers are involved).  There is no CPU fallback: if the
+shared object is missing or no CUDA device can be bound, every entry point
+raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import shutil
+import subprocess
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+LIB_PATH = PKG_DIR / "libfarkle_b200.so"
+HEADER = PKG_DIR.parent / "include" / "farkle_b200.h"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+]
+
+# every symbol include/farkle_b200.h declares
+SYMBOLS = (
+    "fb_abi_version", "fb_last_error", "fb_init", "fb_device_info", "fb_row_stride",
+    "fb_workspace_bytes", "fb_seedseq_generate", "fb_coordinate_seeds", "fb_seed_streams",
+    "fb_roll_dice", "fb_default_score", "fb_permute_shuffles", "fb_play_tournament",
+    "fb_play_h2h", "fb_h2h_resolve", "fb_play_games", "fb_run_tournament_host",
+    "fb_last_play_kernel_ms", "fb_kernel_launch_count",
+)
+
+
+class NativeError(RuntimeError):
+    """A C-ABI call failed; the message is ``fb_last_error()``."""
+
+
+def sources() -> list[Path]:
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [HEADER]
+
+
+def is_stale() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    built = LIB_PATH.stat().st_mtime
+    return any(src.stat().st_mtime > built for src in sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile ``csrc/capi.cu`` for sm_100a with nvcc (cross-compiles without a GPU)."""
+    if not force and not is_stale():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), str(CSRC / "capi.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{proc.stdout}\n{proc.stderr}")
+    if verbose:
+        print(proc.stderr)
+    return LIB_PATH
+
+
+_lib: C.CDLL | None = None
+
+_u64, _u32, _i32, _int, _vp, _sz = (C.c_uint64, C.c_uint32, C.c_int32, C.c_int, C.c_void_p,
+                                    C.c_size_t)
+
+
+def _declare(L: C.CDLL) -> None:
+    L.fb_abi_version.restype = _int
+    L.fb_last_error.restype = C.c_char_p
+    L.fb_init.argtypes = [_int]
+    L.fb_device_info.argtypes = [C.POINTER(_int)] * 4
+    L.fb_row_stride.restype = _sz
+    L.fb_row_stride.argtypes = [_int]
+    L.fb_workspace_bytes.restype = _sz
+    L.fb_workspace_bytes.argtypes = [_int, _u64]
+    L.fb_seedseq_generate.argtypes = [_vp, _int, _u64, _int, _vp, _vp]
+    L.fb_coordinate_seeds.argtypes = [_u32, _u64, _u64, _u64, _u64, _u64, _u64, _int, _u64, _u64,
+                                      _int, _vp, _vp]
+    L.fb_seed_streams.argtypes = [_vp, _u64, _vp, _vp]
+    L.fb_roll_dice.argtypes = [_vp, _vp, _u64, _vp, _int, _vp, _vp]
+    L.fb_default_score.argtypes = [_vp, _vp, _vp, _u64, _vp, _vp]
+    L.fb_permute_shuffles.argtypes = [_u64, _int, _u64, _int, _int, _vp, _vp]
+    L.fb_play_tournament.argtypes = [_u64, _int, _u64, _int, _vp, _vp, _int, _int, _i32, _i32,
+                                     _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _int, _vp, _sz, _vp]
+    L.fb_play_h2h.argtypes = [_u64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _i32, _i32, _vp,
+                              _vp, _vp, _vp, _sz, _vp]
+    L.fb_h2h_resolve.argtypes = [_int, _vp, _vp, _vp, _vp, _vp]
+    L.fb_play_games.argtypes = [_vp, _u64, _int, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp,
+                                _sz, _vp]
+    L.fb_run_tournament_host.argtypes = [_u64, _int, _u64, _int, _vp, _vp, _int, _int, _i32, _i32,
+                                         _int, _vp, _vp, _vp, _int]
+    L.fb_last_play_kernel_ms.restype = C.c_float
+    L.fb_kernel_launch_count.restype = _u64
+
+
+def lib() -> C.CDLL:
+    """Return the loaded library; raise if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise NativeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`."
+                " farkle_ii_b200 has no CPU fallback.")
+        L = C.CDLL(str(LIB_PATH))
+        _declare(L)
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise NativeError(f"farkle_b200 error {rc}: {lib().fb_last_error().decode()}")

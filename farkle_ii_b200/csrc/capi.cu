@@ -1,0 +1,799 @@
+// capi.cu — C ABI of include/farkle_b200.h plus the prepare / building-block kernels.
+//
+// Kernel inventory (all sm_100a, integer-issue bound, no tensor-core work):
+//   seed_tournament_kernel  coordinate_rng for every (game, seat) of a run of shuffles
+//   seed_h2h_kernel         same for H2H attempts
+//   seed_explicit_kernel    same for explicit coordinates
+//   permute_kernel          Generator.permutation per shuffle
+//   play_kernel             (play.cuh) the game state machine, rows and tallies
+//   h2h_resolve_kernel      early-stop prefix rule over attempt outcomes
+//   test kernels            seedseq / coordinate_seed / roll_dice / default_score
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/farkle_b200.h"
+#include "play.cuh"
+#include "rng.cuh"
+#include "scoring.cuh"
+
+using namespace fb;
+
+// ---------------------------------------------------------------------------
+// host state
+// ---------------------------------------------------------------------------
+namespace {
+
+struct Ctx {
+    int device = -1;
+    int sm_count = 0, clock_khz = 0, cc_major = 0, cc_minor = 0;
+    int max_smem_optin = 0;
+    ScoreLut* lut_dev = nullptr;
+    // cached buffers of fb_run_tournament_host
+    void* host_ws = nullptr;
+    size_t host_ws_bytes = 0;
+};
+Ctx g_ctx;
+std::mutex g_mu;
+std::atomic<uint64_t> g_launches{0};
+
+thread_local std::string t_err;
+thread_local cudaEvent_t t_ev0 = nullptr, t_ev1 = nullptr;
+thread_local bool t_ev_valid = false;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_err = buf;
+    return code;
+}
+
+#define FB_CUDA(call)                                                                     \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(FB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                              \
+    } while (0)
+
+#define FB_REQUIRE_INIT()                                                        \
+    do {                                                                         \
+        if (g_ctx.device < 0)                                                    \
+            return fail(FB_ERR_NO_DEVICE, "fb_init has not succeeded: no CUDA device bound"); \
+    } while (0)
+
+inline int launch_check(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(FB_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return FB_OK;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+    uint32_t* seat_state;
+    int32_t* seat_strat;
+    uint64_t* game_seed;
+    int32_t* limits;
+    unsigned int* counter;
+    uint8_t* extra;  // mode specific tail (perm / h2h tables)
+    size_t extra_bytes;
+};
+
+size_t ws_core_bytes(int k, uint64_t n) {
+    return align_up(n * (uint64_t)k * 32, 256) + align_up(n * (uint64_t)k * 4, 256) +
+           align_up(n * 8, 256) + align_up(n * 8, 256) + 256;
+}
+
+bool carve(void* base, size_t bytes, int k, uint64_t n, Workspace& w) {
+    uint8_t* p = static_cast<uint8_t*>(base);
+    const size_t core = ws_core_bytes(k, n);
+    if (bytes < core) return false;
+    w.seat_state = reinterpret_cast<uint32_t*>(p);
+    p += align_up(n * (uint64_t)k * 32, 256);
+    w.seat_strat = reinterpret_cast<int32_t*>(p);
+    p += align_up(n * (uint64_t)k * 4, 256);
+    w.game_seed = reinterpret_cast<uint64_t*>(p);
+    p += align_up(n * 8, 256);
+    w.limits = reinterpret_cast<int32_t*>(p);
+    p += align_up(n * 8, 256);
+    w.counter = reinterpret_cast<unsigned int*>(p);
+    p += 256;
+    w.extra = p;
+    w.extra_bytes = bytes - core;
+    return true;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// device helpers / kernels
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void store_state(uint32_t* dst, const Pcg& g) {
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    d[0] = make_uint4((uint32_t)g.lo, (uint32_t)(g.lo >> 32), (uint32_t)g.hi, (uint32_t)(g.hi >> 32));
+    d[1] = make_uint4((uint32_t)g.ilo, (uint32_t)(g.ilo >> 32), (uint32_t)g.ihi, (uint32_t)(g.ihi >> 32));
+}
+
+__device__ __forceinline__ uint64_t coord_fingerprint(const Coord& c, bool as_u32) {
+    uint32_t pool[4], w[2];
+    ss_pool_coord(c, pool);
+    ss_generate<2>(pool, w);
+    return as_u32 ? (uint64_t)w[0] : ((uint64_t)w[0] | ((uint64_t)w[1] << 32));
+}
+
+// One thread per (game, seat) of shuffles shuffle0.. (run_tournament.py:336-364).
+__global__ void __launch_bounds__(256) seed_tournament_kernel(
+    uint64_t root, int k, uint64_t shuffle0, uint32_t gps, uint64_t n_games, const int32_t* perm,
+    int n_strategies, int32_t target, int32_t max_rounds, const uint64_t* ov_shuffle,
+    const uint32_t* ov_game, const int32_t* ov_rounds, int n_ov, int want_seeds,
+    uint32_t* seat_state, int32_t* seat_strat, uint64_t* game_seed, int32_t* limits) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_games * (uint64_t)k) return;
+    const uint64_t g = t / (uint64_t)k;
+    const uint32_t s = (uint32_t)(t - g * (uint64_t)k);
+    const uint64_t sl = g / gps;
+    const uint32_t gi = (uint32_t)(g - sl * gps);
+    Coord c{FB_PURPOSE_TOURNAMENT_PLAYER, root, (uint64_t)k, shuffle0 + sl, 0, 0, gi, s, 0};
+    Pcg pg;
+    pcg_seed_coord(pg, c);
+    store_state(seat_state + t * 8, pg);
+    seat_strat[t] = perm[sl * (uint64_t)n_strategies + (uint64_t)gi * k + s];
+    if (s == 0) {
+        if (want_seeds) {
+            Coord gc = c;
+            gc.purpose = FB_PURPOSE_TOURNAMENT_GAME;
+            gc.seat_index = 0;
+            game_seed[g] = coord_fingerprint(gc, true);
+        }
+        if (limits) {
+            int32_t mr = max_rounds;
+            for (int o = 0; o < n_ov; o++)
+                if (ov_shuffle[o] == shuffle0 + sl && ov_game[o] == gi) {
+                    mr = ov_rounds[o];
+                    break;
+                }
+            limits[2 * g] = target;
+            limits[2 * g + 1] = mr;
+        }
+    }
+}
+
+// Exclusive prefix sum of n_attempts (single block; n_blocks is at most ~1e5).
+__global__ void h2h_offsets_kernel(const uint32_t* n_attempts, int n_blocks, uint64_t* offsets) {
+    __shared__ uint64_t carry;
+    __shared__ uint64_t part[1024];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_blocks; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        uint64_t v = i < n_blocks ? n_attempts[i] : 0;
+        part[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < blockDim.x; o <<= 1) {
+            uint64_t add = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+            __syncthreads();
+            part[threadIdx.x] += add;
+            __syncthreads();
+        }
+        if (i < n_blocks) offsets[i] = carry + part[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry += part[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[n_blocks] = carry;
+}
+
+// One thread per (attempt, seat) (h2h_schedule.py:1169-1202).
+__global__ void __launch_bounds__(256) seed_h2h_kernel(
+    uint64_t root, int n_blocks, const uint64_t* pair_id, const uint8_t* order,
+    const fb_strategy_t* seat1, const fb_strategy_t* seat2, const uint32_t* attempt0,
+    const uint64_t* offsets, uint64_t total, int want_seeds, uint32_t* seat_state,
+    int32_t* seat_strat, uint64_t* game_seed, fb_strategy_t* table) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total * 2) return;
+    const uint64_t g = t >> 1;
+    const uint32_t s = (uint32_t)(t & 1);
+    int lo = 0, hi = n_blocks - 1;  // last block with offsets[b] <= g
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (offsets[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    const int b = lo;
+    const uint64_t a = (uint64_t)attempt0[b] + (g - offsets[b]);
+    Coord c{FB_PURPOSE_H2H_PLAYER, root, 2, 0, pair_id[b], order[b], a, s, 0};
+    Pcg pg;
+    pcg_seed_coord(pg, c);
+    store_state(seat_state + t * 8, pg);
+    seat_strat[t] = b * 2 + (int)s;
+    if (g == offsets[b]) table[b * 2 + s] = s ? seat2[b] : seat1[b];
+    if (s == 0 && want_seeds) {
+        Coord gc = c;
+        gc.purpose = FB_PURPOSE_H2H_GAME;
+        game_seed[g] = coord_fingerprint(gc, false);
+    }
+}
+
+__global__ void __launch_bounds__(256) seed_explicit_kernel(const uint64_t* coords, uint64_t n_games,
+                                                            int k, uint32_t* seat_state) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_games * (uint64_t)k) return;
+    const uint64_t g = t / (uint64_t)k;
+    const uint64_t* cc = coords + g * 7;
+    Coord c{(uint32_t)cc[0], cc[1], cc[2], cc[3], cc[4], cc[5], cc[6], t - g * (uint64_t)k, 0};
+    Pcg pg;
+    pcg_seed_coord(pg, c);
+    store_state(seat_state + t * 8, pg);
+}
+
+__global__ void pack_limits_kernel(const int32_t* tv, int32_t t0, const int32_t* mv, int32_t m0,
+                                   uint64_t n, int32_t* limits) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    limits[2 * i] = tv ? tv[i] : t0;
+    limits[2 * i + 1] = mv ? mv[i] : m0;
+}
+
+// Generator.permutation(n) per shuffle: Fisher-Yates from the top with masked
+// rejection on buffered 32-bit draws (run_tournament.py:312-318).
+__global__ void __launch_bounds__(128) permute_kernel(uint64_t root, int k, uint64_t shuffle0,
+                                                      int n_shuffles, int n, int32_t* out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_shuffles) return;
+    Coord c{FB_PURPOSE_SHUFFLE_PERMUTATION, root, (uint64_t)k, shuffle0 + (uint64_t)j, 0, 0, 0, 0, 0};
+    PcgStream s;
+    pcg_seed_coord(s.g, c);
+    s.saved = 0;
+    s.has32 = false;
+    int32_t* a = out + (size_t)j * n;
+    for (int i = 0; i < n; i++) a[i] = i;
+    for (int i = n - 1; i >= 1; i--) {
+        const uint32_t mask = 0xffffffffu >> __clz(i);
+        const uint32_t v = s.interval((uint32_t)i, mask);
+        const int32_t t = a[i];
+        a[i] = a[v];
+        a[v] = t;
+    }
+}
+
+// Early-stop rule of _simulate_block_from_manifest (h2h_schedule.py:1167-1235):
+// one warp per block walks the outcome bytes in order.
+__global__ void h2h_resolve_kernel(int n_blocks, const uint32_t* n_attempts, const uint64_t* offsets,
+                                   const uint8_t* outcome, const int32_t* required, int32_t* progress) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= n_blocks) return;
+    int attempted = progress[b * 5 + 0], completed = progress[b * 5 + 1], safety = progress[b * 5 + 2];
+    int w1 = progress[b * 5 + 3], w2 = progress[b * 5 + 4];
+    const int target = required[b];
+    const uint8_t* oc = outcome + offsets[b];
+    const uint32_t n = n_attempts[b];
+    for (uint32_t base = 0; base < n && completed < target; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t o = i < n ? (oc[i] & 0x7fu) : 0xffu;
+        const uint32_t mc = __ballot_sync(FULL, o == 1u || o == 2u);
+        const uint32_t valid = __ballot_sync(FULL, i < n);
+        // take the shortest prefix of this 32-attempt window that reaches the target
+        int take = __popc(valid);
+        const int room = target - completed;
+        if (__popc(mc) >= room) {
+            // position of the room-th completed attempt
+            uint32_t m = mc;
+            for (int r = 1; r < room; r++) m &= m - 1;
+            take = __ffs(m);
+        }
+        const uint32_t tm = take >= 32 ? FULL : ((1u << take) - 1u);
+        attempted += take;
+        completed += __popc(mc & tm);
+        safety += __popc(__ballot_sync(FULL, o == 0u) & tm);
+        w1 += __popc(__ballot_sync(FULL, o == 1u) & tm);
+        w2 += __popc(__ballot_sync(FULL, o == 2u) & tm);
+    }
+    if (lane == 0) {
+        progress[b * 5 + 0] = attempted; progress[b * 5 + 1] = completed; progress[b * 5 + 2] = safety;
+        progress[b * 5 + 3] = w1; progress[b * 5 + 4] = w2;
+    }
+}
+
+// ---- building-block / test kernels -----------------------------------------
+__global__ void seedseq_kernel(const uint32_t* entropy, int n_entropy, uint64_t n_streams,
+                               int n_words, uint32_t* out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_streams) return;
+    uint32_t pool[4];
+    ss_pool_generic(entropy + i * n_entropy, n_entropy, pool);
+    uint32_t hc = SS_INIT_B;
+    for (int w = 0; w < n_words; w++) {
+        uint32_t v = pool[w & 3] ^ hc;
+        hc *= SS_MULT_B;
+        v *= hc;
+        v ^= v >> 16;
+        out[i * n_words + w] = v;
+    }
+}
+
+__global__ void coord_seeds_kernel(Coord c, int vary, uint64_t base, uint64_t n, int as_u32,
+                                   uint64_t* out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (vary == 0) c.shuffle_index = base + i;
+    else if (vary == 1) c.game_index = base + i;
+    else c.pair_id = base + i;
+    out[i] = coord_fingerprint(c, as_u32 != 0);
+}
+
+__global__ void seed_streams_kernel(const uint64_t* coords, uint64_t n, uint64_t* out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t* cc = coords + i * 9;
+    Coord c{(uint32_t)cc[0], cc[1], cc[2], cc[3], cc[4], cc[5], cc[6], cc[7], cc[8]};
+    Pcg g;
+    pcg_seed_coord(g, c);
+    out[i * 4 + 0] = g.hi; out[i * 4 + 1] = g.lo; out[i * 4 + 2] = g.ihi; out[i * 4 + 3] = g.ilo;
+}
+
+// Same half-buffer roll code path as play_kernel's P phase, one stream per thread.
+__global__ void roll_dice_kernel(const uint64_t* state_inc, const uint32_t* half_buffer, uint64_t n,
+                                 const int32_t* n_dice, int n_rolls, uint8_t* faces) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Pcg rng{state_inc[i * 4], state_inc[i * 4 + 1], state_inc[i * 4 + 2], state_inc[i * 4 + 3]};
+    uint32_t saved = half_buffer ? half_buffer[i * 2 + 1] : 0u;
+    bool has32 = half_buffer ? half_buffer[i * 2] != 0u : false;
+    for (int r = 0; r < n_rolls; r++) {
+        const int nd = n_dice[r];
+        const uint32_t p = has32 ? 0u : 1u;
+        const int nw = (nd + (int)p) >> 1;
+        uint64_t shi = rng.hi, slo = rng.lo;
+        uint32_t H[7] = {saved, 0, 0, 0, 0, 0, 0};
+        for (int w = 0; w < nw; w++) {
+            const uint64_t o = pcg_output(shi, slo);
+            pcg_step(shi, slo, rng.ihi, rng.ilo);
+            H[1 + 2 * w] = (uint32_t)o;
+            H[2 + 2 * w] = (uint32_t)(o >> 32);
+        }
+        uint8_t f[6] = {0, 0, 0, 0, 0, 0};
+        bool rej = false;
+        for (int d = 0; d < nd; d++) {
+            const uint64_t m = (uint64_t)H[d + p] * 6u;
+            rej |= (uint32_t)m < 4u;
+            f[d] = (uint8_t)(1u + (uint32_t)(m >> 32));
+        }
+        const uint32_t q = p + (uint32_t)nd;
+        bool nhas = (q & 1u) == 0u;
+        uint32_t nsaved = H[q <= 6 ? q : 6];
+        if (rej) {
+            PcgStream s{rng, saved, has32};
+            uint32_t words = 0;
+            for (int d = 0; d < nd; d++) f[d] = (uint8_t)(1u + s.die0(words));
+            shi = s.g.hi; slo = s.g.lo; nhas = s.has32; nsaved = s.saved;
+        }
+        rng.hi = shi; rng.lo = slo; has32 = nhas; saved = nsaved;
+        for (int d = 0; d < 6; d++) faces[(i * n_rolls + r) * 6 + d] = f[d];
+    }
+}
+
+__global__ void default_score_kernel(const ScoreLut* lut, const uint8_t* faces, const int32_t* ts_pre,
+                                     const fb_strategy_t* strat, uint64_t n, int32_t* out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t hist = 0;
+    int nd = 0;
+    for (int d = 0; d < 6; d++) {
+        const uint32_t f = faces[i * 6 + d];
+        if (f) { hist += 1u << (3u * (f - 1u)); nd++; }
+    }
+    const uint32_t e = lut_lookup(lut, hist);
+    const int rscore = (int)(e & 127u) * 50;
+    int used = (int)((e >> 7) & 7u);
+    const int sf = (int)((e >> 10) & 3u), so = (int)((e >> 12) & 3u);
+    const uint2 sv = reinterpret_cast<const uint2*>(strat)[i];
+    const uint32_t dd = rscore ? smart_discards(rscore, used, sf, so, nd, ts_pre[i], (int)sv.x, sv.y) : 0u;
+    const int d5 = (int)(dd & 0xffu), d1 = (int)(dd >> 8);
+    used -= d5 + d1;
+    out[i * 5 + 0] = rscore - 50 * d5 - 100 * d1;
+    out[i * 5 + 1] = used;
+    out[i * 5 + 2] = nd - used;
+    out[i * 5 + 3] = d5;
+    out[i * 5 + 4] = d1;
+}
+
+// ---------------------------------------------------------------------------
+// play launch
+// ---------------------------------------------------------------------------
+namespace {
+
+int launch_play(const PlayParams& P, cudaStream_t stream) {
+    const int k = P.k;
+    const size_t lut_bytes = (LUT_BYTES + 15) & ~15;
+    const size_t per_warp = (size_t)k * SEAT_WORDS * STORE_STRIDE * 4;
+    const size_t budget = (size_t)g_ctx.max_smem_optin - 1024;  // static smem + slack
+    int warps = (int)((budget - lut_bytes) / per_warp);
+    if (warps < 1) return fail(FB_ERR_BAD_ARG, "k=%d does not fit the shared-memory seat store", k);
+    if (warps > 32) warps = 32;
+    const uint64_t lanes_needed = P.n_games;
+    int grid = g_ctx.sm_count;
+    const uint64_t per_cta = (uint64_t)warps * 32;
+    if ((uint64_t)grid * per_cta > lanes_needed) {
+        // small launch: fewer CTAs, then fewer warps
+        grid = (int)((lanes_needed + per_cta - 1) / per_cta);
+        if (grid < 1) grid = 1;
+        if (grid == 1) {
+            warps = (int)((lanes_needed + 31) / 32);
+            if (warps < 1) warps = 1;
+        }
+    }
+    const size_t smem = lut_bytes + per_warp * (size_t)warps;
+    FB_CUDA(cudaMemsetAsync(P.counter, 0, sizeof(unsigned int), stream));
+    if (!t_ev0) {
+        FB_CUDA(cudaEventCreate(&t_ev0));
+        FB_CUDA(cudaEventCreate(&t_ev1));
+    }
+    if (warps > 16) {
+        FB_CUDA(cudaFuncSetAttribute(play_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)budget));
+        FB_CUDA(cudaEventRecord(t_ev0, stream));
+        play_kernel<1024><<<grid, warps * 32, smem, stream>>>(P, g_ctx.lut_dev);
+    } else {
+        FB_CUDA(cudaFuncSetAttribute(play_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)budget));
+        FB_CUDA(cudaEventRecord(t_ev0, stream));
+        play_kernel<512><<<grid, warps * 32, smem, stream>>>(P, g_ctx.lut_dev);
+    }
+    int rc = launch_check("play_kernel");
+    if (rc) return rc;
+    FB_CUDA(cudaEventRecord(t_ev1, stream));
+    t_ev_valid = true;
+    return FB_OK;
+}
+
+inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int fb_abi_version(void) { return FB_ABI_VERSION; }
+const char* fb_last_error(void) { return t_err.c_str(); }
+uint64_t fb_kernel_launch_count(void) { return g_launches.load(); }
+
+int fb_init(int device) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(FB_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(FB_ERR_BAD_ARG, "device %d out of range [0,%d)", device, count);
+    FB_CUDA(cudaSetDevice(device));
+    if (g_ctx.device == device && g_ctx.lut_dev) return FB_OK;
+    cudaDeviceProp prop;
+    FB_CUDA(cudaGetDeviceProperties(&prop, device));
+    g_ctx.sm_count = prop.multiProcessorCount;
+    g_ctx.cc_major = prop.major;
+    g_ctx.cc_minor = prop.minor;
+    FB_CUDA(cudaDeviceGetAttribute(&g_ctx.clock_khz, cudaDevAttrClockRate, device));
+    FB_CUDA(cudaDeviceGetAttribute(&g_ctx.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    ScoreLut* host_lut = new ScoreLut;
+    host_build_lut(*host_lut);
+    if (g_ctx.lut_dev) cudaFree(g_ctx.lut_dev);
+    FB_CUDA(cudaMalloc(&g_ctx.lut_dev, sizeof(ScoreLut)));
+    FB_CUDA(cudaMemcpy(g_ctx.lut_dev, host_lut, sizeof(ScoreLut), cudaMemcpyHostToDevice));
+    delete host_lut;
+    g_ctx.device = device;
+    return FB_OK;
+}
+
+int fb_device_info(int* sm_count, int* clock_khz, int* cc_major, int* cc_minor) {
+    FB_REQUIRE_INIT();
+    if (sm_count) *sm_count = g_ctx.sm_count;
+    if (clock_khz) *clock_khz = g_ctx.clock_khz;
+    if (cc_major) *cc_major = g_ctx.cc_major;
+    if (cc_minor) *cc_minor = g_ctx.cc_minor;
+    return FB_OK;
+}
+
+size_t fb_row_stride(int k) {
+    return (sizeof(fb_row_header_t) + (size_t)k * sizeof(fb_row_seat_t) + 15u) & ~(size_t)15u;
+}
+
+size_t fb_workspace_bytes(int k, uint64_t n_games) {
+    if (k < 1 || k > FB_MAX_PLAYERS) return 0;
+    // core + H2H block table / offsets tail allowance (callers add the perm buffer)
+    return ws_core_bytes(k, n_games) + 4096;
+}
+
+int fb_seedseq_generate(const uint32_t* entropy_dev, int n_entropy, uint64_t n_streams, int n_words,
+                        uint32_t* out_dev, void* stream) {
+    FB_REQUIRE_INIT();
+    if (n_entropy < 1 || n_words < 1) return fail(FB_ERR_BAD_ARG, "n_entropy and n_words must be >= 1");
+    if (n_streams == 0) return FB_OK;
+    seedseq_kernel<<<blocks_for(n_streams, 128), 128, 0, (cudaStream_t)stream>>>(entropy_dev, n_entropy,
+                                                                                 n_streams, n_words, out_dev);
+    return launch_check("seedseq_kernel");
+}
+
+int fb_coordinate_seeds(uint32_t purpose, uint64_t root_seed, uint64_t k, uint64_t shuffle_index,
+                        uint64_t pair_id, uint64_t order, uint64_t game_index, int vary, uint64_t base,
+                        uint64_t n, int as_u32, uint64_t* out_dev, void* stream) {
+    FB_REQUIRE_INIT();
+    if (vary < 0 || vary > 2) return fail(FB_ERR_BAD_ARG, "vary must be 0, 1 or 2");
+    if (n == 0) return FB_OK;
+    Coord c{purpose, root_seed, k, shuffle_index, pair_id, order, game_index, 0, 0};
+    coord_seeds_kernel<<<blocks_for(n, 128), 128, 0, (cudaStream_t)stream>>>(c, vary, base, n, as_u32, out_dev);
+    return launch_check("coord_seeds_kernel");
+}
+
+int fb_seed_streams(const uint64_t* coords_dev, uint64_t n, uint64_t* state_inc_out_dev, void* stream) {
+    FB_REQUIRE_INIT();
+    if (n == 0) return FB_OK;
+    seed_streams_kernel<<<blocks_for(n, 128), 128, 0, (cudaStream_t)stream>>>(coords_dev, n, state_inc_out_dev);
+    return launch_check("seed_streams_kernel");
+}
+
+int fb_roll_dice(const uint64_t* state_inc_dev, const uint32_t* half_buffer_dev, uint64_t n,
+                 const int32_t* n_dice_dev, int n_rolls, uint8_t* faces_out_dev, void* stream) {
+    FB_REQUIRE_INIT();
+    if (n == 0 || n_rolls == 0) return FB_OK;
+    roll_dice_kernel<<<blocks_for(n, 128), 128, 0, (cudaStream_t)stream>>>(
+        state_inc_dev, half_buffer_dev, n, n_dice_dev, n_rolls, faces_out_dev);
+    return launch_check("roll_dice_kernel");
+}
+
+int fb_default_score(const uint8_t* faces_dev, const int32_t* turn_score_pre_dev,
+                     const fb_strategy_t* strategy_dev, uint64_t n, int32_t* out_dev, void* stream) {
+    FB_REQUIRE_INIT();
+    if (n == 0) return FB_OK;
+    default_score_kernel<<<blocks_for(n, 128), 128, 0, (cudaStream_t)stream>>>(
+        g_ctx.lut_dev, faces_dev, turn_score_pre_dev, strategy_dev, n, out_dev);
+    return launch_check("default_score_kernel");
+}
+
+int fb_permute_shuffles(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles, int n_strategies,
+                        int32_t* perm_out_dev, void* stream) {
+    FB_REQUIRE_INIT();
+    if (n_shuffles < 0 || n_strategies < 1) return fail(FB_ERR_BAD_ARG, "bad shuffle or strategy count");
+    if (n_shuffles == 0) return FB_OK;
+    permute_kernel<<<blocks_for((uint64_t)n_shuffles, 128), 128, 0, (cudaStream_t)stream>>>(
+        root_seed, k, shuffle0, n_shuffles, n_strategies, perm_out_dev);
+    return launch_check("permute_kernel");
+}
+
+int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
+                       const fb_strategy_t* strategies_dev, const int32_t* strategy_ids_dev,
+                       int n_strategies, int n_tally_ids, int32_t target_score, int32_t max_rounds,
+                       const uint64_t* override_shuffle_dev, const uint32_t* override_game_dev,
+                       const int32_t* override_max_rounds_dev, int n_overrides, int shuffles_per_slot,
+                       int64_t* tallies_dev, int64_t* totals_dev, void* rows_dev, int want_game_seeds,
+                       void* workspace_dev, size_t workspace_bytes, void* stream_v) {
+    FB_REQUIRE_INIT();
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    if (k < 1 || k > FB_MAX_PLAYERS) return fail(FB_ERR_BAD_ARG, "k=%d outside [1,%d]", k, FB_MAX_PLAYERS);
+    if (n_strategies < k || n_strategies % k != 0)
+        return fail(FB_ERR_BAD_ARG, "n_players must divide %d", n_strategies);  // run_tournament.py:274-275
+    if (n_shuffles < 0 || shuffles_per_slot < 0 || n_overrides < 0) return fail(FB_ERR_BAD_ARG, "negative count");
+    if (n_shuffles == 0) return FB_OK;
+    const uint32_t gps = (uint32_t)(n_strategies / k);
+    const uint64_t n_games = (uint64_t)n_shuffles * gps;
+    if (n_games > 0xfffffff0ull) return fail(FB_ERR_BAD_ARG, "more than 2^32 games in one launch");
+    Workspace w;
+    const size_t perm_bytes = align_up((size_t)n_shuffles * n_strategies * 4, 256);
+    if (!carve(workspace_dev, workspace_bytes, k, n_games, w) || w.extra_bytes < perm_bytes)
+        return fail(FB_ERR_WORKSPACE, "workspace too small: need %zu bytes",
+                    ws_core_bytes(k, n_games) + perm_bytes);
+    int32_t* perm = reinterpret_cast<int32_t*>(w.extra);
+    int rc = fb_permute_shuffles(root_seed, k, shuffle0, n_shuffles, n_strategies, perm, stream);
+    if (rc) return rc;
+    int32_t* limits = n_overrides > 0 ? w.limits : nullptr;
+    seed_tournament_kernel<<<blocks_for(n_games * k, 256), 256, 0, stream>>>(
+        root_seed, k, shuffle0, gps, n_games, perm, n_strategies, target_score, max_rounds,
+        override_shuffle_dev, override_game_dev, override_max_rounds_dev, n_overrides, want_game_seeds,
+        w.seat_state, w.seat_strat, w.game_seed, limits);
+    rc = launch_check("seed_tournament_kernel");
+    if (rc) return rc;
+    PlayParams P{};
+    P.seat_state = w.seat_state;
+    P.seat_strat = w.seat_strat;
+    P.strategies = strategies_dev;
+    P.strategy_ids = strategy_ids_dev;
+    P.ids_mode = strategy_ids_dev ? 1 : 0;
+    P.game_seed = want_game_seeds ? w.game_seed : nullptr;
+    P.limits = limits;
+    P.target_score = target_score;
+    P.max_rounds = max_rounds;
+    P.n_games = (uint32_t)n_games;
+    P.k = k;
+    P.games_per_slot = shuffles_per_slot > 0 ? (uint32_t)shuffles_per_slot * gps : 0u;
+    P.n_tally_ids = n_tally_ids;
+    P.tallies = reinterpret_cast<unsigned long long*>(tallies_dev);
+    P.totals = reinterpret_cast<unsigned long long*>(totals_dev);
+    P.rows = reinterpret_cast<uint32_t*>(rows_dev);
+    P.row_words = (int)(fb_row_stride(k) / 4);
+    P.outcome = nullptr;
+    P.counter = w.counter;
+    return launch_play(P, stream);
+}
+
+int fb_play_h2h(uint64_t root_seed, int n_blocks, const uint64_t* pair_id_dev, const uint8_t* order_dev,
+                const fb_strategy_t* seat1_dev, const fb_strategy_t* seat2_dev,
+                const uint32_t* attempt0_dev, const uint32_t* n_attempts_dev, uint64_t total_attempts,
+                int32_t target_score, int32_t max_rounds, uint8_t* outcome_out_dev, void* rows_dev,
+                int64_t* totals_dev, void* workspace_dev, size_t workspace_bytes, void* stream_v) {
+    FB_REQUIRE_INIT();
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    if (n_blocks < 0) return fail(FB_ERR_BAD_ARG, "negative block count");
+    if (n_blocks == 0 || total_attempts == 0) return FB_OK;
+    if (total_attempts > 0xfffffff0ull) return fail(FB_ERR_BAD_ARG, "more than 2^32 attempts in one launch");
+    Workspace w;
+    const size_t off_bytes = align_up((size_t)(n_blocks + 1) * 8, 256);
+    const size_t tab_bytes = align_up((size_t)n_blocks * 2 * sizeof(fb_strategy_t), 256);
+    if (!carve(workspace_dev, workspace_bytes, 2, total_attempts, w) || w.extra_bytes < off_bytes + tab_bytes)
+        return fail(FB_ERR_WORKSPACE, "workspace too small: need %zu bytes",
+                    ws_core_bytes(2, total_attempts) + off_bytes + tab_bytes);
+    uint64_t* offsets = reinterpret_cast<uint64_t*>(w.extra);
+    fb_strategy_t* table = reinterpret_cast<fb_strategy_t*>(w.extra + off_bytes);
+    h2h_offsets_kernel<<<1, 1024, 0, stream>>>(n_attempts_dev, n_blocks, offsets);
+    int rc = launch_check("h2h_offsets_kernel");
+    if (rc) return rc;
+    const int want_seeds = rows_dev != nullptr;
+    seed_h2h_kernel<<<blocks_for(total_attempts * 2, 256), 256, 0, stream>>>(
+        root_seed, n_blocks, pair_id_dev, order_dev, seat1_dev, seat2_dev, attempt0_dev, offsets,
+        total_attempts, want_seeds, w.seat_state, w.seat_strat, w.game_seed, table);
+    rc = launch_check("seed_h2h_kernel");
+    if (rc) return rc;
+    PlayParams P{};
+    P.seat_state = w.seat_state;
+    P.seat_strat = w.seat_strat;
+    P.strategies = table;
+    P.ids_mode = 2;
+    P.game_seed = want_seeds ? w.game_seed : nullptr;
+    P.target_score = target_score;
+    P.max_rounds = max_rounds;
+    P.n_games = (uint32_t)total_attempts;
+    P.k = 2;
+    P.totals = reinterpret_cast<unsigned long long*>(totals_dev);
+    P.rows = reinterpret_cast<uint32_t*>(rows_dev);
+    P.row_words = (int)(fb_row_stride(2) / 4);
+    P.outcome = outcome_out_dev;
+    P.counter = w.counter;
+    return launch_play(P, stream);
+}
+
+int fb_h2h_resolve(int n_blocks, const uint32_t* n_attempts_dev, const uint8_t* outcome_dev,
+                   const int32_t* n_completed_required_dev, int32_t* progress_dev, void* stream_v) {
+    FB_REQUIRE_INIT();
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    if (n_blocks <= 0) return n_blocks == 0 ? FB_OK : fail(FB_ERR_BAD_ARG, "negative block count");
+    uint64_t* offsets = nullptr;
+    FB_CUDA(cudaMallocAsync(&offsets, (size_t)(n_blocks + 1) * 8, stream));
+    h2h_offsets_kernel<<<1, 1024, 0, stream>>>(n_attempts_dev, n_blocks, offsets);
+    int rc = launch_check("h2h_offsets_kernel");
+    if (!rc) {
+        h2h_resolve_kernel<<<blocks_for((uint64_t)n_blocks * 32, 128), 128, 0, stream>>>(
+            n_blocks, n_attempts_dev, offsets, outcome_dev, n_completed_required_dev, progress_dev);
+        rc = launch_check("h2h_resolve_kernel");
+    }
+    cudaFreeAsync(offsets, stream);
+    return rc;
+}
+
+int fb_play_games(const uint64_t* coords_dev, uint64_t n_games, int k,
+                  const fb_strategy_t* seat_strategies_dev, const int32_t* seat_strategy_ids_dev,
+                  const int32_t* target_score_dev, int32_t target_score, const int32_t* max_rounds_dev,
+                  int32_t max_rounds, void* rows_dev, int64_t* totals_dev, void* workspace_dev,
+                  size_t workspace_bytes, void* stream_v) {
+    FB_REQUIRE_INIT();
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    if (k < 1 || k > FB_MAX_PLAYERS) return fail(FB_ERR_BAD_ARG, "k=%d outside [1,%d]", k, FB_MAX_PLAYERS);
+    if (n_games == 0) return FB_OK;
+    if (n_games > 0xfffffff0ull) return fail(FB_ERR_BAD_ARG, "more than 2^32 games in one launch");
+    Workspace w;
+    if (!carve(workspace_dev, workspace_bytes, k, n_games, w))
+        return fail(FB_ERR_WORKSPACE, "workspace too small: need %zu bytes", ws_core_bytes(k, n_games));
+    seed_explicit_kernel<<<blocks_for(n_games * k, 256), 256, 0, stream>>>(coords_dev, n_games, k, w.seat_state);
+    int rc = launch_check("seed_explicit_kernel");
+    if (rc) return rc;
+    int32_t* limits = nullptr;
+    if (target_score_dev || max_rounds_dev) {
+        limits = w.limits;
+        pack_limits_kernel<<<blocks_for(n_games, 256), 256, 0, stream>>>(target_score_dev, target_score,
+                                                                         max_rounds_dev, max_rounds, n_games, limits);
+        rc = launch_check("pack_limits_kernel");
+        if (rc) return rc;
+    }
+    PlayParams P{};
+    P.seat_state = w.seat_state;
+    P.seat_strat = nullptr;  // entry g*k+s of seat_strategies_dev
+    P.strategies = seat_strategies_dev;
+    P.strategy_ids = seat_strategy_ids_dev;
+    P.ids_mode = seat_strategy_ids_dev ? 1 : 2;
+    P.limits = limits;
+    P.target_score = target_score;
+    P.max_rounds = max_rounds;
+    P.n_games = (uint32_t)n_games;
+    P.k = k;
+    P.totals = reinterpret_cast<unsigned long long*>(totals_dev);
+    P.rows = reinterpret_cast<uint32_t*>(rows_dev);
+    P.row_words = (int)(fb_row_stride(k) / 4);
+    P.counter = w.counter;
+    return launch_play(P, stream);
+}
+
+int fb_run_tournament_host(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
+                           const fb_strategy_t* strategies_host, const int32_t* strategy_ids_host,
+                           int n_strategies, int n_tally_ids, int32_t target_score, int32_t max_rounds,
+                           int shuffles_per_slot, int64_t* tallies_host, int64_t* totals_host,
+                           void* rows_host, int want_game_seeds) {
+    FB_REQUIRE_INIT();
+    if (k < 1 || k > FB_MAX_PLAYERS || n_strategies < k || n_strategies % k != 0 || n_shuffles < 1)
+        return fail(FB_ERR_BAD_ARG, "bad k / strategy / shuffle count");
+    const uint64_t gps = (uint64_t)(n_strategies / k);
+    const uint64_t n_games = (uint64_t)n_shuffles * gps;
+    const int n_slots = shuffles_per_slot > 0 ? (n_shuffles + shuffles_per_slot - 1) / shuffles_per_slot : 1;
+    const size_t strat_b = align_up((size_t)n_strategies * sizeof(fb_strategy_t), 256);
+    const size_t ids_b = align_up((size_t)n_strategies * 4, 256);
+    const size_t tally_b = align_up((size_t)n_slots * n_tally_ids * FB_TALLY_WIDTH * 8, 256);
+    const size_t totals_b = 256;
+    const size_t rows_b = rows_host ? align_up(n_games * fb_row_stride(k), 256) : 0;
+    const size_t ws_b = fb_workspace_bytes(k, n_games) + align_up((size_t)n_shuffles * n_strategies * 4, 256);
+    const size_t total = strat_b + ids_b + tally_b + totals_b + rows_b + ws_b;
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (g_ctx.host_ws_bytes < total) {
+        if (g_ctx.host_ws) cudaFree(g_ctx.host_ws);
+        g_ctx.host_ws = nullptr;
+        g_ctx.host_ws_bytes = 0;
+        FB_CUDA(cudaMalloc(&g_ctx.host_ws, total));
+        g_ctx.host_ws_bytes = total;
+    }
+    uint8_t* p = static_cast<uint8_t*>(g_ctx.host_ws);
+    fb_strategy_t* d_strat = reinterpret_cast<fb_strategy_t*>(p); p += strat_b;
+    int32_t* d_ids = reinterpret_cast<int32_t*>(p); p += ids_b;
+    int64_t* d_tally = reinterpret_cast<int64_t*>(p); p += tally_b;
+    int64_t* d_totals = reinterpret_cast<int64_t*>(p); p += totals_b;
+    void* d_rows = rows_host ? p : nullptr; p += rows_b;
+    void* d_ws = p;
+    cudaStream_t stream = nullptr;
+    FB_CUDA(cudaMemcpyAsync(d_strat, strategies_host, (size_t)n_strategies * sizeof(fb_strategy_t),
+                            cudaMemcpyHostToDevice, stream));
+    if (strategy_ids_host)
+        FB_CUDA(cudaMemcpyAsync(d_ids, strategy_ids_host, (size_t)n_strategies * 4, cudaMemcpyHostToDevice, stream));
+    FB_CUDA(cudaMemsetAsync(d_tally, 0, tally_b, stream));
+    FB_CUDA(cudaMemsetAsync(d_totals, 0, totals_b, stream));
+    int rc = fb_play_tournament(root_seed, k, shuffle0, n_shuffles, d_strat, strategy_ids_host ? d_ids : nullptr,
+                                n_strategies, n_tally_ids, target_score, max_rounds, nullptr, nullptr, nullptr, 0,
+                                shuffles_per_slot, tallies_host ? d_tally : nullptr, d_totals, d_rows,
+                                want_game_seeds, d_ws, ws_b, stream);
+    if (rc) return rc;
+    if (tallies_host)
+        FB_CUDA(cudaMemcpyAsync(tallies_host, d_tally, (size_t)n_slots * n_tally_ids * FB_TALLY_WIDTH * 8,
+                                cudaMemcpyDeviceToHost, stream));
+    if (totals_host)
+        FB_CUDA(cudaMemcpyAsync(totals_host, d_totals, FB_TOTALS_WIDTH * 8, cudaMemcpyDeviceToHost, stream));
+    if (rows_host)
+        FB_CUDA(cudaMemcpyAsync(rows_host, d_rows, n_games * fb_row_stride(k), cudaMemcpyDeviceToHost, stream));
+    FB_CUDA(cudaStreamSynchronize(stream));
+    return FB_OK;
+}
+
+float fb_last_play_kernel_ms(void) {
+    if (!t_ev_valid) return -1.0f;
+    if (cudaEventSynchronize(t_ev1) != cudaSuccess) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventElapsedTime(&ms, t_ev0, t_ev1) != cudaSuccess) return -1.0f;
+    return ms;
+}
+
+}  // extern "C"

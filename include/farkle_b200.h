@@ -165,11 +165,12 @@ int fb_seed_streams(const uint64_t* coords_dev /*[n][9]*/, uint64_t n,
                     uint64_t* state_inc_out_dev /*[n][4]*/, void* stream);
 
 /* FarklePlayer._roll (src/farkle/game/engine.py:85-101): for each of n streams
- * (state_inc as produced by fb_seed_streams, has32/saved = 0) draw n_rolls
- * rolls of n_dice[r] dice; faces_out[i][r][6] (unused slots 0).  Also the
- * hook used to test the Lemire rejection branch with crafted states.        */
-int fb_roll_dice(const uint64_t* state_inc_dev, uint64_t n, const int32_t* n_dice_dev,
-                 int n_rolls, uint8_t* faces_out_dev, void* stream);
+ * (state_inc as produced by fb_seed_streams) draw n_rolls rolls of n_dice[r]
+ * dice; faces_out[i][r][6] (unused slots 0).  half_buffer_dev[i] = {has_uint32,
+ * uinteger} is NumPy's buffered 32-bit half at the start (NULL = empty); with
+ * crafted states this is the hook that tests the Lemire rejection branch.    */
+int fb_roll_dice(const uint64_t* state_inc_dev, const uint32_t* half_buffer_dev, uint64_t n,
+                 const int32_t* n_dice_dev, int n_rolls, uint8_t* faces_out_dev, void* stream);
 
 /* default_score(..., return_discards=True) (src/farkle/game/scoring.py:618-693)
  * for n rolls: faces[i][6] (0 = no die), turn_score_pre[i], strategy[i].

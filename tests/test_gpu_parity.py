@@ -1,0 +1,373 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Bar: bit-exact.  Everything on this path is integer work.
+"""
+
+from __future__ import annotations
+
+import json
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle as fo  # noqa: E402  (test infrastructure: the checker)
+from test_oracle_golden import GAME_FIXTURES, assert_rows_equal, check_expected_rows  # noqa: E402
+
+P_PLAYER, P_SHUFFLE, P_PERM, P_GAME, P_TPLAYER, P_H2H_GAME, P_H2H_PLAYER = (
+    10, 100, 101, 102, 103, 202, 203)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from farkle_ii_b200.device import get_engine
+
+    return get_engine(0)
+
+
+def _coords9(c):
+    return [c.get("purpose"), c["root_seed"], c.get("k", 0), c.get("shuffle_index", 0),
+            c.get("pair_id", 0), c.get("order", 0), c.get("game_index", 0),
+            c.get("seat_index", 0), c.get("replicate_index", 0)]
+
+
+# --------------------------------------------------------------------------- RNG
+def test_seedseq_words(eng, golden_dir):
+    data = json.loads((golden_dir / "rng.json").read_text())
+    for case in data["seedseq"]:
+        got = eng.seedseq_generate(np.array(case["entropy"], dtype=np.uint32), 8)[0]
+        assert got.tolist() == case["words"]
+    # reference KAT tests/unit/utils/test_random_utils.py:32-40,73-78
+    e = np.array([[1, 102, 32, 0, 2, 0, 194, 0, 0, 0, 0, 0, 18, 0, 0, 0, 0, 0],
+                  [1, 102, 32, 0, 2, 0, 4052, 0, 0, 0, 0, 0, 4, 0, 0, 0, 0, 0]], dtype=np.uint32)
+    assert eng.seedseq_generate(e, 1)[:, 0].tolist() == [2_963_478_802, 2_963_478_802]
+
+
+def test_coordinate_streams_and_dice(eng, golden_dir):
+    data = json.loads((golden_dir / "rng.json").read_text())
+    pattern = data["n_dice_pattern"]
+    coords = np.array([_coords9(c["coord"]) for c in data["coords"]], dtype=np.uint64)
+    si = eng.seed_streams(coords)
+    faces = eng.roll_dice(si, pattern)
+    for i, case in enumerate(data["coords"]):
+        assert (int(si[i, 0]) << 64) | int(si[i, 1]) == int(case["state"])
+        assert (int(si[i, 2]) << 64) | int(si[i, 3]) == int(case["inc"])
+        for r, n in enumerate(pattern):
+            assert faces[i, r, :n].tolist() == case["dice"][r]
+            assert not faces[i, r, n:].any()
+        c = case["coord"]
+        for as_u32, key in ((True, "seed_u32"), (False, "seed_u64")):
+            got = eng.coordinate_seeds(c["purpose"], root_seed=c["root_seed"], k=c.get("k", 0),
+                                       shuffle_index=c.get("shuffle_index", 0),
+                                       pair_id=c.get("pair_id", 0), order=c.get("order", 0),
+                                       game_index=0, vary="game_index",
+                                       base=c.get("game_index", 0), n=1, as_u32=as_u32)
+            if c.get("seat_index", 0) == 0:  # fingerprints never carry a seat
+                assert int(got[0]) == case[key]
+
+
+def test_coordinate_seed_ranges_vs_oracle(eng):
+    got = eng.coordinate_seeds(P_SHUFFLE, root_seed=42, k=2, vary="shuffle_index", base=0, n=600,
+                               as_u32=True)
+    assert int(got[0]) == 1_998_876_487 and int(got[1]) == 2_468_994_662
+    for i in (0, 17, 599):
+        assert int(got[i]) == fo.coordinate_seed(P_SHUFFLE, root_seed=42, k=2, shuffle_index=i,
+                                                 as_u32=True)
+    got = eng.coordinate_seeds(P_H2H_GAME, root_seed=7, k=2, pair_id=5, order=1, vary="game_index",
+                               base=2**33, n=50)
+    for i in (0, 49):
+        assert int(got[i]) == fo.coordinate_seed(P_H2H_GAME, root_seed=7, k=2, pair_id=5, order=1,
+                                                 game_index=2**33 + i)
+
+
+def test_lemire_rejection_branch(eng, golden_dir):
+    data = json.loads((golden_dir / "rng.json").read_text())
+    m = 2**64 - 1
+    for case in data["rejection"]:
+        state, inc = int(case["state"]), int(case["inc"])
+        si = np.array([[state >> 64, state & m, inc >> 64, inc & m]], dtype=np.uint64)
+        hb = np.array([[case.get("has32", 0), case.get("saved", 0)]], dtype=np.uint32)
+        faces = eng.roll_dice(si, case["n_dice"], half_buffer=hb)[0]
+        for r, n in enumerate(case["n_dice"]):
+            assert faces[r, :n].tolist() == case["dice"][r]
+
+
+def test_permutations(eng, golden_dir):
+    perms = np.load(golden_dir / "perm.npz")
+    for key in perms.files:
+        root, k, sh, n = (int(x) for x in key.split("_"))
+        assert np.array_equal(eng.permute_shuffles(root, k, sh, 1, n)[0], perms[key]), key
+    got = eng.permute_shuffles(42, 5, 100, 37, 5160)
+    for j in (0, 13, 36):
+        assert np.array_equal(got[j], fo.permutation(42, 5, 100 + j, 5160))
+    assert all(np.array_equal(np.sort(row), np.arange(5160)) for row in got)
+
+
+# ----------------------------------------------------------------------- scoring
+def _strategies(rows):
+    s = np.zeros(len(rows), dtype=fo.STRATEGY_DTYPE)
+    s["score_threshold"], s["dice_threshold"], s["flags"] = rows[:, 0], rows[:, 1], rows[:, 2]
+    return s
+
+
+def test_score_table_and_golden_rolls(eng, golden_dir):
+    z = np.load(golden_dir / "scoring.npz")
+    tab = z["table"]
+    faces = np.zeros((len(tab), 6), dtype=np.uint8)
+    for i, row in enumerate(tab):
+        f = [face + 1 for face in range(6) for _ in range(int(row[face]))]
+        faces[i, : len(f)] = f
+    plain = np.zeros(len(tab), dtype=fo.STRATEGY_DTYPE)
+    out = eng.default_score(faces, np.zeros(len(tab), dtype=np.int32), plain)
+    n = (faces > 0).sum(axis=1)
+    assert np.array_equal(out[:, 0], tab[:, 6]) and np.array_equal(out[:, 1], tab[:, 7])
+    assert np.array_equal(out[:, 2], n - tab[:, 7]) and not out[:, 3:].any()
+    rolls = z["csv_rolls"]  # tests/data/test_farkle_scores_data.csv of the reference
+    out = eng.default_score(rolls[:, :6].astype(np.uint8), np.zeros(len(rolls), dtype=np.int32),
+                            np.zeros(len(rolls), dtype=fo.STRATEGY_DTYPE))
+    assert np.array_equal(out[:, :3], rolls[:, 6:9])
+
+
+def test_default_score_sweep(eng, golden_dir):
+    z = np.load(golden_dir / "scoring.npz")
+    sin, want = z["sweep_in"], z["sweep_out"]
+    out = eng.default_score(sin[:, :6].astype(np.uint8), sin[:, 6], _strategies(sin[:, 7:10]))
+    assert np.array_equal(out, want)
+    disc = z["discards"]
+    faces = np.zeros((len(disc), 6), dtype=np.uint8)
+    for i, row in enumerate(disc):
+        f = [face + 1 for face in range(6) for _ in range(int(row[face]))]
+        faces[i, : len(f)] = f
+    flags = (disc[:, 12] | disc[:, 13] << 1 | disc[:, 9] << 2 | disc[:, 10] << 3 | disc[:, 11] << 4
+             | 0x80)
+    st = _strategies(np.stack([disc[:, 7], disc[:, 8], flags], axis=1))
+    out = eng.default_score(faces, disc[:, 6], st)
+    assert np.array_equal(out[:, 3:], disc[:, 14:16])
+
+
+def test_default_score_exhaustive_vs_oracle(eng, golden_dir):
+    """All 923 histograms x a parameter lattice, against the oracle's literal candidate search."""
+    tab = np.load(golden_dir / "scoring.npz")["table"]
+    rng = np.random.Generator(np.random.PCG64DXSM(7))
+    faces, ts, st = [], [], []
+    for row in tab:
+        f = [face + 1 for face in range(6) for _ in range(int(row[face]))]
+        for _ in range(40):
+            flags = int(rng.integers(0, 256))
+            if flags & 2 and not flags & 1:
+                flags &= ~2
+            if flags & 16 and (flags & 12) != 12:
+                flags &= ~16
+            faces.append(f + [0] * (6 - len(f)))
+            ts.append(int(rng.integers(0, 30)) * 50)
+            st.append((int(rng.choice([199, 200, 250, 300, 400, 550, 1000])),
+                       int(rng.integers(-1, 6)), flags))
+    faces = np.array(faces, dtype=np.uint8)
+    st_arr = _strategies(np.array(st))
+    out = eng.default_score(faces, np.array(ts, dtype=np.int32), st_arr)
+    for i in range(0, len(faces), 7):  # the oracle is called per case; sample every 7th
+        f = [int(x) for x in faces[i] if x]
+        assert tuple(int(x) for x in out[i]) == fo.default_score(f, ts[i], st_arr[i:i + 1]), i
+
+
+# ------------------------------------------------------------------- whole games
+def _play(eng, root, k, sh0, nsh, table, **kw):
+    res = eng.play_tournament(root, k, sh0, nsh, table, want_rows=True, want_game_seeds=True, **kw)
+    return res.tallies.cpu().numpy(), res.totals.cpu().numpy(), res.rows_numpy()
+
+
+@pytest.mark.parametrize("name", GAME_FIXTURES)
+def test_tournament_rows_and_tallies_golden(eng, golden_dir, name):
+    z = np.load(golden_dir / f"games_{name}.npz")
+    root, k, sh0, nsh = (int(x) for x in z["meta"])
+    tallies, totals, rows = _play(eng, root, k, sh0, nsh, z["strategies"])
+    assert_rows_equal(rows, z["rows"], k)
+    assert np.array_equal(rows["game_ordinal"], np.arange(len(rows)))
+    assert np.array_equal(tallies[0], z["tallies"])
+    want_t, want_tot, want_rows = fo.play_tournament(root, k, sh0, nsh, z["strategies"],
+                                                     want_rows=True, want_game_seeds=True)
+    assert rows.tobytes() == want_rows.tobytes()
+    assert np.array_equal(totals, want_tot)
+
+
+def test_reference_raw_oracle_12_games(eng, golden_dir):
+    z = np.load(golden_dir / "oracle12.npz")
+
+    def play(root, k, overrides):
+        tallies, _totals, rows = _play(eng, root, k, 0, 2, z["strategies"], target_score=100,
+                                       overrides=overrides)
+        assert_rows_equal(rows, z[f"rows_{root}_{k}"], k)
+        assert np.array_equal(tallies[0], z[f"tallies_{root}_{k}"])
+        return rows
+
+    check_expected_rows(play)
+
+
+def test_public_helper_kat(eng, golden_dir):
+    # reference tests/unit/simulation/test_simulation.py:184-198
+    z = np.load(golden_dir / "helpers.npz")
+    coords = np.array([[P_PLAYER, 123, 3, 0, 0, 0, g] for g in range(10)], dtype=np.uint64)
+    rows, totals = eng.play_games(coords, 3, np.tile(z["strategies"], (10, 1)), target_score=5000)
+    assert np.bincount(rows["winner_seat"], minlength=3).tolist() == [2, 6, 2]
+    want = z["rows"].copy()
+    want["game_seed"] = 0
+    assert_rows_equal(rows, want, 3)
+    assert totals[0] == 10 and totals[8:11].tolist() == [2, 6, 2]
+
+
+def test_fast_grid_seed42_full_cell(eng, golden_dir):
+    z = np.load(golden_dir / "fast42.npz")
+    res = eng.play_tournament(42, 2, 0, 600, z["strategies"])
+    tallies, totals = res.tallies.cpu().numpy(), res.totals.cpu().numpy()
+    assert np.array_equal(tallies[0], z["tallies"])
+    assert totals[:3].tolist() == [24000, 23801, 199]
+    assert tallies[0][[42, 46, 51, 37, 25], 0].tolist() == [330, 322, 407, 386, 140]
+
+
+@pytest.mark.parametrize("k,nsh,spb", [(2, 43, 0), (3, 9, 4), (4, 12, 5), (5, 10, 0), (6, 7, 3),
+                                       (8, 5, 0), (10, 4, 2), (12, 6, 0)])
+def test_full_grid_cells_vs_oracle(eng, golden_dir, k, nsh, spb):
+    """Full 5,160-strategy grid: tallies (per deterministic batch slot), totals and rows."""
+    table = np.load(golden_dir / "games_full_0_2.npz")["strategies"]
+    root, sh0 = 1000 + k, 4300 - nsh
+    res = eng.play_tournament(root, k, sh0, nsh, table, shuffles_per_slot=spb, want_rows=True)
+    want_t, want_tot, want_rows = fo.play_tournament(root, k, sh0, nsh, table,
+                                                     shuffles_per_slot=spb, want_rows=True,
+                                                     n_threads=8)
+    tallies = res.tallies.cpu().numpy()
+    assert np.array_equal(tallies, want_t)
+    assert np.array_equal(res.totals.cpu().numpy(), want_tot)
+    assert res.rows_numpy().tobytes() == want_rows.tobytes()
+    # size-independent invariants (run_tournament.py:721-726): every strategy sits once per shuffle
+    tot = tallies.sum(axis=0)
+    assert (tot[:, 1] == nsh).all() and (tot[:, 2] + tot[:, 3] == tot[:, 1]).all()
+    assert tot[:, 0].sum() == want_tot[1] and tot[:, 3].sum() == k * want_tot[2]
+
+
+def test_strategy_id_mapping_and_accumulation(eng, golden_dir):
+    table = np.load(golden_dir / "games_fast_42_2.npz")["strategies"]
+    ids = (np.arange(80, dtype=np.int32) * 3 + 5)
+    res = eng.play_tournament(9, 4, 0, 6, table, strategy_ids=ids, want_rows=True)
+    want_t, _, want_rows = fo.play_tournament(9, 4, 0, 6, table, strategy_ids=ids, want_rows=True)
+    assert np.array_equal(res.tallies.cpu().numpy(), want_t)
+    assert res.rows_numpy().tobytes() == want_rows.tobytes()
+    # two launches accumulated into the same tensors == one launch over the union
+    a = eng.play_tournament(9, 4, 0, 3, table)
+    eng.play_tournament(9, 4, 3, 3, table, tallies=a.tallies, totals=a.totals)
+    whole, tot, _ = fo.play_tournament(9, 4, 0, 6, table)
+    assert np.array_equal(a.tallies.cpu().numpy(), whole)
+    assert np.array_equal(a.totals.cpu().numpy(), tot)
+
+
+def test_edge_cases(eng, golden_dir):
+    table = np.load(golden_dir / "games_fast_42_2.npz")["strategies"]
+    # zero shuffles: nothing launched, zero tallies
+    res = eng.play_tournament(1, 2, 0, 0, table)
+    assert not res.tallies.cpu().numpy().any() and res.n_games == 0
+    # k that does not divide the grid is rejected like _init_worker (run_tournament.py:274-275)
+    from farkle_ii_b200._native import NativeError
+
+    with pytest.raises(NativeError, match="n_players must divide"):
+        eng.play_tournament(1, 3, 0, 1, table)
+    with pytest.raises(NativeError):
+        eng.play_tournament(1, 13, 0, 1, table)
+    # single-seat games, max_rounds=1 (everything safety-limited unless 10k in one turn)
+    for k, mr, tgt in ((1, 200, 10_000), (2, 1, 10_000), (5, 3, 2_000), (2, 200, 50)):
+        res = eng.play_tournament(3, k, 5, 2, table, max_rounds=mr, target_score=tgt, want_rows=True)
+        want_t, want_tot, want_rows = fo.play_tournament(3, k, 5, 2, table, max_rounds=mr,
+                                                         target_score=tgt, want_rows=True)
+        assert np.array_equal(res.tallies.cpu().numpy(), want_t), (k, mr, tgt)
+        assert np.array_equal(res.totals.cpu().numpy(), want_tot)
+        assert res.rows_numpy().tobytes() == want_rows.tobytes()
+
+
+def test_play_games_explicit_vs_oracle(eng):
+    rng = np.random.Generator(np.random.PCG64DXSM(99))
+    n, k = 700, 3
+    coords = np.zeros((n, 7), dtype=np.uint64)
+    coords[:, 0] = rng.choice([P_PLAYER, P_TPLAYER, P_H2H_PLAYER], size=n)
+    coords[:, 1] = rng.integers(0, 2**63, size=n)
+    coords[:, 2] = k
+    coords[:, 3] = rng.integers(0, 5000, size=n)
+    coords[:, 4] = rng.integers(0, 2**40, size=n)
+    coords[:, 5] = rng.integers(0, 2, size=n)
+    coords[:, 6] = rng.integers(0, 2**34, size=n)
+    st = np.zeros((n, k), dtype=fo.STRATEGY_DTYPE)
+    st["score_threshold"] = rng.integers(1, 20, size=(n, k)) * 50
+    st["dice_threshold"] = rng.integers(0, 5, size=(n, k))
+    flags = rng.integers(0, 256, size=(n, k))
+    flags &= np.where(flags & 1, 0xFF, ~2 & 0xFF)
+    flags &= np.where((flags & 12) == 12, 0xFF, ~16 & 0xFF)
+    st["flags"] = flags
+    ids = rng.integers(0, 1000, size=(n, k)).astype(np.int32)
+    tgt = rng.choice([100, 1000, 5000, 10_000], size=n).astype(np.int32)
+    mr = rng.choice([0, 1, 5, 200], size=n).astype(np.int32)
+    rows, totals = eng.play_games(coords, k, st, seat_strategy_ids=ids, target_scores=tgt,
+                                  max_rounds_v=mr)
+    want_rows, want_tot = fo.play_games(coords, k, st, seat_strategy_ids=ids, target_scores=tgt,
+                                        max_rounds_v=mr)
+    assert rows.tobytes() == want_rows.tobytes()
+    assert np.array_equal(totals, want_tot)
+
+
+# -------------------------------------------------------------------------- H2H
+def test_h2h_blocks_golden(eng, golden_dir):
+    blocks = json.loads((golden_dir / "h2h.json").read_text())
+    keys = ("games_attempted", "games_completed", "games_safety_limit", "wins_seat1", "wins_seat2")
+
+    def st(b, name):
+        s = np.zeros(len(b), dtype=fo.STRATEGY_DTYPE)
+        for i, blk in enumerate(b):
+            s[i] = tuple(blk[name])
+        return s
+
+    pair = [b["pair_id"] for b in blocks]
+    order = [b["order"] for b in blocks]
+    req = [b["n_completed_required"] for b in blocks]
+    # chunk of 13 attempts, as in the fixture (stop = min(max_attempts, attempted + chunk))
+    first = [min(13, b["max_attempts"]) for b in blocks]
+    oc, d_na, _, _ = eng.play_h2h(42, pair, order, st(blocks, "seat1"), st(blocks, "seat2"),
+                                  [0] * len(blocks), first)
+    prog = eng.h2h_resolve(d_na, oc, req, np.zeros((len(blocks), 5), dtype=np.int32))
+    for b, p in zip(blocks, prog):
+        assert p.tolist() == [b["after_chunk13"][k_] for k_ in keys]
+    # then everything up to max_attempts; the resolve kernel applies the early stop
+    rest = [b["max_attempts"] - int(p[0]) for b, p in zip(blocks, prog)]
+    oc, d_na, _, _ = eng.play_h2h(42, pair, order, st(blocks, "seat1"), st(blocks, "seat2"),
+                                  prog[:, 0], rest)
+    prog = eng.h2h_resolve(d_na, oc, req, prog)
+    for b, p in zip(blocks, prog):
+        assert p.tolist() == [b["final"][k_] for k_ in keys]
+
+
+def test_h2h_many_blocks_vs_oracle(eng, golden_dir):
+    table = np.load(golden_dir / "games_full_0_2.npz")["strategies"]
+    rng = np.random.Generator(np.random.PCG64DXSM(5))
+    nb = 60
+    a_idx, b_idx = rng.integers(0, 5160, size=nb), rng.integers(0, 5160, size=nb)
+    pair = rng.integers(0, 10_000, size=nb)
+    order = rng.integers(0, 2, size=nb)
+    req = rng.integers(5, 40, size=nb)
+    n_att = rng.integers(1, 70, size=nb)
+    att0 = rng.integers(0, 1000, size=nb)
+    oc, d_na, rows, totals = eng.play_h2h(77, pair, order, table[a_idx], table[b_idx], att0,
+                                          n_att, want_rows=True)
+    start = np.zeros((nb, 5), dtype=np.int32)
+    start[:, 0] = att0
+    prog = eng.h2h_resolve(d_na, oc, req, start)
+    oc = oc.cpu().numpy()
+    off = 0
+    for i in range(nb):
+        p, want_oc = fo.play_h2h_block(77, int(pair[i]), int(order[i]), table[a_idx[i]],
+                                       table[b_idx[i]], n_completed_required=int(req[i]),
+                                       max_attempts=int(att0[i] + n_att[i]),
+                                       chunk_games=int(n_att[i]), progress=start[i])
+        assert prog[i].tolist() == p.tolist(), i
+        assert oc[off: off + len(want_oc)].tolist() == want_oc.tolist()
+        off += int(n_att[i])
+    hrows = rows.cpu().numpy().view(fo.row_dtype(2)).reshape(-1)
+    assert int(hrows["game_seed"][0]) == fo.coordinate_seed(
+        P_H2H_GAME, root_seed=77, k=2, pair_id=int(pair[0]), order=int(order[0]),
+        game_index=int(att0[0]))
+    assert totals.cpu().numpy()[0] == n_att.sum()

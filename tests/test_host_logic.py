@@ -1,0 +1,139 @@
+"""CPU tests of the host mirror: strategy grid order/ids, packing, library exports."""
+
+from __future__ import annotations
+
+import ctypes
+import re
+
+import numpy as np
+import pytest
+
+from farkle_ii_b200 import _native, layout
+from farkle_ii_b200.strategies import (
+    FavorDiceOrScore,
+    ThresholdStrategy,
+    build_stop_at_strategy,
+    generate_strategy_grid,
+    pack_strategies,
+    parse_strategy,
+    prepare_strategy_ids,
+    unpack_strategy,
+)
+
+FAST = dict(score_thresholds=[250, 300, 350, 400], smart_five_opts=[True], smart_one_opts=[True],
+            consider_score_opts=[True], consider_dice_opts=[True], auto_hot_dice_opts=[True],
+            run_up_score_opts=[True])
+TINY = dict(score_thresholds=[500], dice_thresholds=[2], smart_five_opts=[False],
+            smart_one_opts=[False], consider_score_opts=[True], consider_dice_opts=[True],
+            auto_hot_dice_opts=[False, True], run_up_score_opts=[False])
+
+
+@pytest.mark.parametrize("fixture,kwargs,count", [
+    ("games_fast_42_2.npz", FAST, 80), ("games_full_0_2.npz", {}, 5160), ("oracle12.npz", TINY, 4)])
+def test_grid_matches_reference_table(golden_dir, fixture, kwargs, count):
+    # the fixture's table was packed from the reference's generate_strategy_grid()
+    want = np.load(golden_dir / fixture)["strategies"]
+    strategies, meta = generate_strategy_grid(**kwargs)
+    assert len(strategies) == count == len(meta)
+    assert [s.strategy_id for s in strategies] == list(range(count))
+    got = pack_strategies(strategies)
+    assert got.dtype == layout.STRATEGY_DTYPE
+    assert got.tobytes() == want.tobytes()
+    assert list(meta["strategy_idx"]) == list(range(count))
+
+
+def test_default_grid_inactive_sentinels():
+    strategies, _ = generate_strategy_grid()
+    assert {s.score_threshold for s in strategies if not s.consider_score} == {199}
+    assert {s.dice_threshold for s in strategies if not s.consider_dice} == {-1}
+    assert all(s.favor_dice_or_score is FavorDiceOrScore.DICE
+               for s in strategies if s.consider_dice and not s.consider_score)
+
+
+def test_stop_at_strategies_appended():
+    base, _ = generate_strategy_grid(**FAST)
+    both, meta = generate_strategy_grid(**FAST, include_stop_at=True,
+                                        include_stop_at_heuristic=True)
+    assert len(both) == len(base) + 8
+    assert [str(s) for s in both[-8:]] == [
+        *(f"stop_at_{t}" for t in (350, 400, 450, 500)),
+        *(f"stop_at_{t}_heuristic" for t in (350, 400, 450, 500))]
+    assert len(set(meta["strategy_id"])) == len(both)
+    with pytest.raises(ValueError):
+        build_stop_at_strategy(123)
+
+
+def test_strategy_validation_and_roundtrip():
+    with pytest.raises(ValueError):
+        ThresholdStrategy(smart_one=True, smart_five=False)
+    with pytest.raises(ValueError):
+        ThresholdStrategy(require_both=True, consider_dice=False)
+    s = ThresholdStrategy(score_threshold=350, dice_threshold=1, smart_five=True, smart_one=True,
+                          require_both=True, auto_hot_dice=True,
+                          favor_dice_or_score=FavorDiceOrScore.DICE)
+    assert str(s) == "Strat(350,1)[SD][FOFD][AND][H-]"
+    assert parse_strategy(str(s)) == s
+    assert unpack_strategy(pack_strategies([s])[0]) == s
+    with pytest.raises(ValueError):
+        parse_strategy("Strat(1,2)")
+
+
+def test_decide_truth_table():
+    # reference tests/unit/simulation/test_strategies.py style: entry gate, final round, AND/OR
+    s = ThresholdStrategy(score_threshold=300, dice_threshold=2)
+    assert s.decide(turn_score=100, dice_left=1, has_scored=False)          # 500 entry gate
+    assert not s.decide(turn_score=600, dice_left=1, has_scored=False)
+    assert s.decide(turn_score=100, dice_left=4, has_scored=True)           # both unmet
+    assert not s.decide(turn_score=300, dice_left=4, has_scored=True)       # OR: score hit
+    both = ThresholdStrategy(score_threshold=300, dice_threshold=2, require_both=True)
+    assert both.decide(turn_score=300, dice_left=4, has_scored=True)        # AND: dice unmet
+    assert s.decide(turn_score=900, dice_left=1, has_scored=True, final_round=True,
+                    score_to_beat=10_000, running_total=9_000)              # must catch up
+    assert not s.decide(turn_score=100, dice_left=6, has_scored=True, final_round=True,
+                        score_to_beat=10_000, running_total=10_050)         # ahead, no run-up
+
+
+def test_prepare_strategy_ids():
+    a, b, c = ThresholdStrategy(), ThresholdStrategy(strategy_id=0), ThresholdStrategy()
+    assert prepare_strategy_ids([a, b, c]) == [1, 0, 2]
+    with pytest.raises(ValueError):
+        prepare_strategy_ids([ThresholdStrategy(strategy_id=3), ThresholdStrategy(strategy_id=3)])
+
+
+def test_row_layout_matches_header():
+    for k in range(1, 13):
+        assert layout.row_dtype(k).itemsize == layout.row_stride(k)
+        assert layout.row_stride(k) % 16 == 0 and layout.row_stride(k) >= 16 + 28 * k
+    assert layout.row_stride(2) == 80 and layout.row_stride(12) == 352
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads on a CPU box and exports what include/farkle_b200.h declares."""
+    _native.build()
+    lib = _native.lib()
+    header = _native.HEADER.read_text()
+    declared = set(re.findall(r"\b(fb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_native.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.fb_abi_version() == 1
+    for k in (2, 5, 12):
+        assert lib.fb_row_stride(k) == layout.row_stride(k)
+    assert lib.fb_workspace_bytes(2, 1000) >= 1000 * 2 * 36
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path fails loudly instead of computing on the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    lib = _native.lib()
+    assert lib.fb_init(0) == -1  # FB_ERR_NO_DEVICE
+    assert b"no CPU fallback" in lib.fb_last_error()
+    out = (ctypes.c_uint64 * 4)()
+    assert lib.fb_seed_streams(None, 1, out, None) == -1
+    from farkle_ii_b200.device import get_engine
+
+    with pytest.raises(_native.NativeError):
+        get_engine()
