@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — simulated games/s of the tournament hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1], default_config as BASELINE.json describes it): the
+full 5,160-strategy grid, k in [2, 4], roots [42, 43].  ONE STEP = one root's two
+(root, k) cells at the planned 4,300 shuffles each (11,094,000 + 5,547,000 games):
+permutations -> per-seat PCG64DXSM seeding -> whole games -> per-strategy tallies.  Step i
+uses root 42 + (i % 2).  With N ranks (weak scaling) rank r plays shuffles
+[r*4300, (r+1)*4300) of every cell — disjoint coordinate sub-streams — and the int64
+tally tensors are merged with one NCCL all-reduce per cell, inside the timed region.
+
+`value`  = games of all ranks / max-over-ranks CUDA-event time, strategy table resident
+           in HBM, tallies left in HBM.
+`e2e`    = the same cells through the HOST-buffer C-ABI call (fb_run_tournament_host via
+           Engine.run_tournament_host): the strategy table is copied H2D and the
+           tallies/totals D2H inside the timed region, every step.
+The path is integer-issue bound: `roofline` reports algorithmic 32-bit
+lane instructions per second of play_kernel against the measured issue peak
+(fb_measure_issue_peak) and carries the HBM view as well.
+`--impl reference` times the CPU restatement of the reference (oracle/, all host
+threads) on a bounded sample of the same cells.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_STRATEGIES = 5160
+SHUFFLES = 4300                      # workload_planner: delta 0.03 -> 4265 -> 43 x 100
+SHUFFLES_PER_BATCH = 43
+CELLS_K = (2, 4)
+ROOTS = (42, 43)
+# algorithmic lane-instruction model of SURVEY.md §8d (play kernel: words, dice, rolls)
+W_OPS, D_OPS, R_OPS, S_OPS = 28, 8, 90, 1000
+METRIC = "simulated games/sec at 1/2/4/8 B200 (bit-exact tallies) vs reference CPU n_jobs"
+
+
+def full_grid_table() -> np.ndarray:
+    from farkle_ii_b200.strategies import generate_strategy_grid, pack_strategies
+
+    strategies, _ = generate_strategy_grid()
+    assert len(strategies) == N_STRATEGIES
+    return pack_strategies(strategies)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples: list[list[str]] = []
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self) -> None:
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.samples.append([x.strip() for x in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self) -> dict:
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names)
+                   if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "samples": len(self.samples), "reasons": reasons}
+
+
+def algorithmic_ops(totals: np.ndarray, k_seats: int) -> float:
+    """SURVEY.md §8d model: W*words + D*dice + R*rolls (+ S per seat for the seed kernel)."""
+    return float(W_OPS * totals[5] + D_OPS * totals[4] + R_OPS * totals[3] + S_OPS * k_seats)
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_sample(table: np.ndarray, seconds_target: float, threads: int) -> dict:
+    """Time the oracle (kind "port") on a bounded sample of the step's cells."""
+    import oracle
+
+    oracle.build()
+    # calibrate on a small slice, then size the sample
+    t0 = time.perf_counter()
+    oracle.play_tournament(ROOTS[0], 2, 0, threads, table, n_threads=threads)
+    per_shuffle = (time.perf_counter() - t0) / threads
+    n_sh = int(max(threads, min(SHUFFLES, seconds_target / max(per_shuffle, 1e-6) / 1.5)))
+    n_sh2 = max(threads, (n_sh * 2) // 3)
+    n_sh4 = max(threads, n_sh - n_sh2)
+    t0 = time.perf_counter()
+    _, tot2, _ = oracle.play_tournament(ROOTS[0], 2, 0, n_sh2, table, n_threads=threads)
+    _, tot4, _ = oracle.play_tournament(ROOTS[0], 4, 0, n_sh4, table, n_threads=threads)
+    dt = time.perf_counter() - t0
+    games = int(tot2[0] + tot4[0])
+    return {"value": games / dt, "unit": "games/s", "cores": threads, "kind": "port",
+            "sample": (f"full grid root {ROOTS[0]}: k=2 shuffles 0..{n_sh2 - 1} + k=4 shuffles "
+                       f"0..{n_sh4 - 1} ({games} games, {dt:.1f} s), C restatement of the reference "
+                       f"(oracle/farkle_oracle.c), {threads} pthreads over shuffles"),
+            "seconds": dt, "games": games}
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    table = full_grid_table()
+    threads = os.cpu_count() or 1
+    per_step = max(2.0, min(20.0, 120.0 / max(args.steps + args.warmup, 1)))
+    for _ in range(args.warmup):
+        cpu_sample(table, per_step / 4, threads)
+    results = [cpu_sample(table, per_step, threads) for _ in range(args.steps)]
+    games = sum(r["games"] for r in results)
+    secs = sum(r["seconds"] for r in results)
+    value = games / secs
+    base = {k_: results[-1][k_] for k_ in ("unit", "cores", "kind", "sample")}
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "games/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32/u64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, **base},
+        "e2e": {"value": value, "unit": "games/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "note": ("CPU arm = C restatement of the reference (the Python reference itself runs "
+                 "~200-300 games/s/core: BASELINE.md §1-2); bounded sample per step"),
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {
+        "workload": ("configs/default_config.yaml as BASELINE.json describes it: full 5,160-strategy "
+                     "grid, n_players_list [2,4], seeds [42,43]; one step = one root's k=2 and k=4 "
+                     "cells at 4,300 shuffles (16,641,000 games) per GPU"),
+        "n_strategies": N_STRATEGIES, "k": list(CELLS_K), "roots": list(ROOTS),
+        "shuffles_per_cell_per_gpu": SHUFFLES, "shuffles_per_batch": SHUFFLES_PER_BATCH,
+        "games_per_step_per_gpu": sum(SHUFFLES * (N_STRATEGIES // k) for k in CELLS_K),
+        "sharding": (f"rank r plays shuffles [r*{SHUFFLES},(r+1)*{SHUFFLES}) of each cell; "
+                     "one int64 all-reduce of the tally tensor per cell" if n_gpus > 1
+                     else "single GPU"),
+        "l2": ("per-seat stream workspace is 0.7 GB (k=2) / 0.7 GB (k=4) per cell, larger than the "
+               "126 MB L2; the kernels are not memory bound"),
+    }
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--shuffles", type=int, default=SHUFFLES, help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from farkle_ii_b200.device import get_engine
+    from farkle_ii_b200.layout import TALLY_WIDTH, TOTALS_WIDTH
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: farkle_ii_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = get_engine(local)
+    table_host = full_grid_table()
+    table_dev = eng.to_device(table_host)
+    n_sh = args.shuffles
+    shuffle0 = rank * n_sh
+
+    tallies = {k: torch.zeros((1, N_STRATEGIES, TALLY_WIDTH), dtype=torch.int64, device=eng.device)
+               for k in CELLS_K}
+    totals = {k: torch.zeros(TOTALS_WIDTH, dtype=torch.int64, device=eng.device) for k in CELLS_K}
+
+    def step(i: int) -> None:
+        root = ROOTS[i % len(ROOTS)]
+        for k in CELLS_K:
+            tallies[k].zero_()
+            totals[k].zero_()
+            eng.play_tournament(root, k, shuffle0, n_sh, table_dev, tallies=tallies[k],
+                                totals=totals[k])
+            if world > 1:
+                dist.all_reduce(tallies[k])
+
+    def sync_all() -> None:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    sync_all()
+    launches0 = eng.kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        sync_all()
+        ev0.record()
+        for i in range(args.steps):
+            step(i)
+        ev1.record()
+        sync_all()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.kernel_launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    games_per_step_rank = sum(n_sh * (N_STRATEGIES // k) for k in CELLS_K)
+    total_games = games_per_step_rank * world * args.steps
+    value = total_games / (ms * 1e-3)
+
+    # ---- dominant kernel, timed live with CUDA events on its launching stream ----
+    # (separate small loop after the timed region: one launch per cell kind, L2 irrelevant)
+    kern = {}
+    for k in CELLS_K:
+        samples = []
+        for rep in range(3):
+            totals[k].zero_()
+            tallies[k].zero_()
+            eng.play_tournament(ROOTS[rep % 2], k, shuffle0, n_sh, table_dev, tallies=tallies[k],
+                                totals=totals[k])
+            samples.append(eng.last_play_kernel_ms())
+        tot = totals[k].cpu().numpy()
+        kern[k] = {"ms": float(np.mean(samples)), "totals": tot,
+                   "games": int(tot[0]), "ops": algorithmic_ops(tot, 0)}
+    # e2e through the host-buffer C-ABI call
+    out_t = {k: np.empty((1, N_STRATEGIES, TALLY_WIDTH), dtype=np.int64) for k in CELLS_K}
+    pin = torch.from_numpy(table_host.view(np.uint8).copy()).pin_memory()
+    table_pinned = pin.numpy().view(table_host.dtype)
+
+    def e2e_step(i: int) -> None:
+        root = ROOTS[i % len(ROOTS)]
+        for k in CELLS_K:
+            eng.run_tournament_host(root, k, shuffle0, n_sh, table_pinned, out_tallies=out_t[k])
+            if world > 1:
+                t = torch.from_numpy(out_t[k]).to(eng.device)
+                dist.all_reduce(t)
+                out_t[k][...] = t.cpu().numpy()
+
+    e2e_step(0)
+    sync_all()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 4))
+    for i in range(e2e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = games_per_step_rank * world * e2e_steps / e2e_s
+    h2d = len(CELLS_K) * table_host.nbytes
+    d2h = len(CELLS_K) * (N_STRATEGIES * TALLY_WIDTH * 8 + TOTALS_WIDTH * 8)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of play_kernel (k=2 cell: the dominant launch of the step) ----
+    peak_measured = eng.measure_issue_peak()
+    clk = clocks.summary()
+    dom = max(CELLS_K, key=lambda k_: kern[k_]["ms"])
+    achieved = kern[dom]["ops"] / (kern[dom]["ms"] * 1e-3)
+    tot = kern[dom]["totals"]
+    row_bytes_alg = kern[dom]["games"] * (dom * 36 + 0)  # seat state + strategy index reads
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    nominal_peak = eng.sm_count * 4 * 32 * (clk.get("sm_max_mhz") or 1965) * 1e6
+    traffic = None
+    tpath = ROOT / "profiles" / "play_kernel_traffic.json"
+    if tpath.exists():
+        try:
+            traffic = json.loads(tpath.read_text()).get(f"k{dom}_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "issue", "kernel": f"play_kernel (k={dom} cell, {kern[dom]['games']} games/launch)",
+        "achieved": achieved / 1e12, "peak": peak_measured / 1e12, "unit": "Tlaneop/s",
+        "frac": achieved / peak_measured,
+        "peak_source": ("measured: fb_measure_issue_peak (register-only mad/xor/add chains, "
+                        "1,024 threads/SM); MEASURED_PEAKS.json holds no integer peak"),
+        "peak_nominal": nominal_peak / 1e12,
+        "model": (f"algorithmic lane-instructions = {W_OPS}*rng_words + {D_OPS}*dice + "
+                  f"{R_OPS}*rolls (SURVEY.md §8d), counts returned by the kernel"),
+        "per_game": {"rolls": float(tot[3] / tot[0]), "dice": float(tot[4] / tot[0]),
+                     "rng_words": float(tot[5] / tot[0]),
+                     "lane_ops": float(kern[dom]["ops"] / tot[0])},
+        "kernel_ms": kern[dom]["ms"],
+        "kernel_ms_by_k": {str(k_): kern[k_]["ms"] for k_ in CELLS_K},
+        "traffic": traffic,
+        "hbm": {"bound": "hbm", "algorithmic_bytes_per_launch": row_bytes_alg,
+                "achieved": row_bytes_alg / (kern[dom]["ms"] * 1e-3) / 1e9, "peak": hbm_peak,
+                "unit": "GB/s", "frac": row_bytes_alg / (kern[dom]["ms"] * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+    }
+    cpu = cpu_sample(table_host, args.cpu_seconds, os.cpu_count() or 1) if world == 1 else None
+    if cpu:
+        cpu.pop("seconds", None)
+        cpu.pop("games", None)
+    line = {
+        "metric": METRIC, "value": value, "unit": "games/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32/u64", "data": "synthetic",
+        "config": workload_config(world),
+        "e2e": {"value": e2e_value, "unit": "games/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "call": "Engine.run_tournament_host -> fb_run_tournament_host (host buffers)"},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "published_reference": {"games_per_s_1_worker": 279.1, "games_per_s_12_workers": 1142.9,
+                                "hardware": "Ryzen 7 3700X, fast grid k=2 (BASELINE.md §1)"},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

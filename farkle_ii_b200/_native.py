@@ -29,7 +29,7 @@ SYMBOLS = (
     "fb_workspace_bytes", "fb_seedseq_generate", "fb_coordinate_seeds", "fb_seed_streams",
     "fb_roll_dice", "fb_default_score", "fb_permute_shuffles", "fb_play_tournament",
     "fb_play_h2h", "fb_h2h_resolve", "fb_play_games", "fb_run_tournament_host",
-    "fb_last_play_kernel_ms", "fb_kernel_launch_count",
+    "fb_measure_issue_peak", "fb_last_play_kernel_ms", "fb_kernel_launch_count",
 )
 
 
@@ -95,6 +95,7 @@ def _declare(L: C.CDLL) -> None:
                                 _sz, _vp]
     L.fb_run_tournament_host.argtypes = [_u64, _int, _u64, _int, _vp, _vp, _int, _int, _i32, _i32,
                                          _int, _vp, _vp, _vp, _int]
+    L.fb_measure_issue_peak.argtypes = [_int, C.POINTER(C.c_double)]
     L.fb_last_play_kernel_ms.restype = C.c_float
     L.fb_kernel_launch_count.restype = _u64
 

@@ -408,6 +408,28 @@ __global__ void default_score_kernel(const ScoreLut* lut, const uint8_t* faces, 
     out[i * 5 + 4] = d1;
 }
 
+// Integer-issue roofline probe: 8 independent chains of mad / xor / mad / add per
+// thread (16 FMA-pipe + 16 ALU-pipe lane instructions per iteration, no memory).
+__global__ void __launch_bounds__(1024, 1) issue_peak_kernel(int iters, uint32_t seed, uint32_t* sink) {
+    uint32_t x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = seed + threadIdx.x * 8u + i;
+    const uint32_t m = seed | 1u, c = seed ^ 0x9e3779b9u;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(m), "r"(c));
+            asm volatile("xor.b32 %0, %0, %1;" : "+r"(x[i]) : "r"(c));
+            asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(c), "r"(m));
+            asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(m));
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc ^= x[i];
+    if (acc == 0x12345678u) sink[0] = acc;
+}
+
 // ---------------------------------------------------------------------------
 // play launch
 // ---------------------------------------------------------------------------
@@ -785,6 +807,33 @@ int fb_run_tournament_host(uint64_t root_seed, int k, uint64_t shuffle0, int n_s
     if (rows_host)
         FB_CUDA(cudaMemcpyAsync(rows_host, d_rows, n_games * fb_row_stride(k), cudaMemcpyDeviceToHost, stream));
     FB_CUDA(cudaStreamSynchronize(stream));
+    return FB_OK;
+}
+
+int fb_measure_issue_peak(int iters, double* lane_ops_per_second) {
+    FB_REQUIRE_INIT();
+    if (iters < 1 || !lane_ops_per_second) return fail(FB_ERR_BAD_ARG, "iters >= 1 and an output pointer are required");
+    uint32_t* sink = nullptr;
+    FB_CUDA(cudaMalloc(&sink, 4));
+    cudaEvent_t e0, e1;
+    FB_CUDA(cudaEventCreate(&e0));
+    FB_CUDA(cudaEventCreate(&e1));
+    const int grid = g_ctx.sm_count;
+    issue_peak_kernel<<<grid, 1024>>>(iters / 8 + 1, 12345u, sink);  // warm-up
+    int rc = launch_check("issue_peak_kernel");
+    if (rc) return rc;
+    FB_CUDA(cudaEventRecord(e0));
+    issue_peak_kernel<<<grid, 1024>>>(iters, 12345u, sink);
+    rc = launch_check("issue_peak_kernel");
+    if (rc) return rc;
+    FB_CUDA(cudaEventRecord(e1));
+    FB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    FB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *lane_ops_per_second = (double)grid * 1024.0 * (double)iters * 32.0 / (ms * 1e-3);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
     return FB_OK;
 }
 

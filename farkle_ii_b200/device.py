@@ -101,6 +101,45 @@ class Engine:
     def last_play_kernel_ms(self) -> float:
         return float(self.lib.fb_last_play_kernel_ms())
 
+    def measure_issue_peak(self, iters: int = 20000) -> float:
+        """Measured 32-bit integer lane-instructions per second (roofline denominator)."""
+        out = C.c_double()
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.fb_measure_issue_peak(iters, C.byref(out)))
+        return out.value
+
+    def run_tournament_host(self, root_seed: int, k: int, shuffle0: int, n_shuffles: int,
+                            strategies: np.ndarray, *, strategy_ids: np.ndarray | None = None,
+                            n_tally_ids: int | None = None, target_score: int = 10_000,
+                            max_rounds: int = 200, shuffles_per_slot: int = 0,
+                            want_rows: bool = False, want_game_seeds: bool = False,
+                            out_tallies: np.ndarray | None = None,
+                            out_rows: np.ndarray | None = None):
+        """HOST-buffer call (``fb_run_tournament_host``): H2D table, play, D2H tallies(/rows).
+
+        Returns ``(tallies[slots, ids, 26], totals[20], rows | None)`` as host arrays.
+        """
+        st = np.ascontiguousarray(strategies, dtype=STRATEGY_DTYPE)
+        n = len(st)
+        ids = None if strategy_ids is None else np.ascontiguousarray(strategy_ids, dtype=np.int32)
+        if n_tally_ids is None:
+            n_tally_ids = n if ids is None else int(ids.max()) + 1
+        n_slots = 1 if shuffles_per_slot <= 0 else -(-n_shuffles // shuffles_per_slot)
+        tallies = out_tallies if out_tallies is not None else np.empty(
+            (n_slots, n_tally_ids, TALLY_WIDTH), dtype=np.int64)
+        totals = np.empty(TOTALS_WIDTH, dtype=np.int64)
+        rows = None
+        if want_rows:
+            n_games = n_shuffles * (n // k)
+            rows = out_rows if out_rows is not None else np.empty(n_games, dtype=row_dtype(k))
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.fb_run_tournament_host(
+                root_seed, k, shuffle0, n_shuffles, vp(st), vp(ids), n, n_tally_ids, target_score,
+                max_rounds, shuffles_per_slot, vp(tallies), vp(totals), vp(rows),
+                int(want_game_seeds)))
+        return tallies, totals, rows
+
     def kernel_launch_count(self) -> int:
         return int(self.lib.fb_kernel_launch_count())
 

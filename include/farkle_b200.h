@@ -271,6 +271,11 @@ int fb_run_tournament_host(uint64_t root_seed, int k, uint64_t shuffle0, int n_s
  * this thread took, measured with CUDA events on the launching stream.  Blocks
  * until that kernel has finished.  Returns < 0 if nothing was launched.      */
 float fb_last_play_kernel_ms(void);
+/* Roofline probe: runs a register-only kernel of independent 32-bit integer
+ * mad / xor / add chains on every SM (1,024 threads per SM, `iters` iterations of
+ * 32 lane instructions each, half on the FMA pipe and half on the ALU pipe) and
+ * returns the measured lane-instructions per second.  Synchronous.           */
+int fb_measure_issue_peak(int iters, double* lane_ops_per_second);
 /* Number of kernels this library has launched since fb_init (all threads).  */
 uint64_t fb_kernel_launch_count(void);
 

@@ -129,6 +129,7 @@ typedef struct {
     u128 state, inc;
     int has32;
     uint32_t saved;
+    uint64_t words, dice; /* work counters: fresh 64-bit outputs / dice drawn */
 } pcg_t;
 
 static void pcg_seed_words(pcg_t* g, const uint64_t w[4]) {
@@ -141,6 +142,8 @@ static void pcg_seed_words(pcg_t* g, const uint64_t w[4]) {
     g->state = g->state * PCG_DEFAULT_MULT + g->inc;
     g->has32 = 0;
     g->saved = 0;
+    g->words = 0;
+    g->dice = 0;
 }
 static void pcg_seed_coord(pcg_t* g, const fo_coord_t* c) {
     uint32_t e[18], s[8];
@@ -171,27 +174,21 @@ static inline uint32_t pcg_next32(pcg_t* g) {
     return (uint32_t)n;
 }
 
-/* Work counters (per thread) so the roofline model can use exact N_words /
- * N_dice / N_rolls. */
-static __thread uint64_t t_words, t_dice;
-
 /* Generator.integers(1, 7) — Lemire 32-bit path; game/engine.py:101. */
 static inline int pcg_die(pcg_t* g) {
     const uint32_t rng_excl = 6;
-    int before = g->has32;
+    if (!g->has32) g->words++;
     uint64_t m = (uint64_t)pcg_next32(g) * rng_excl;
-    if (!before) t_words++;
     uint32_t left = (uint32_t)m;
     if (left < rng_excl) {
         const uint32_t thr = (0xffffffffu - 5u) % rng_excl;
         while (left < thr) {
-            before = g->has32;
+            if (!g->has32) g->words++;
             m = (uint64_t)pcg_next32(g) * rng_excl;
-            if (!before) t_words++;
             left = (uint32_t)m;
         }
     }
-    t_dice++;
+    g->dice++;
     return 1 + (int)(m >> 32);
 }
 
@@ -215,6 +212,7 @@ void fo_roll_dice_state(const uint64_t state_inc[4], int has32, uint32_t saved,
     g.inc = ((u128)state_inc[2] << 64) | state_inc[3];
     g.has32 = has32;
     g.saved = saved;
+    g.words = g.dice = 0;
     for (int r = 0; r < n_rolls; r++)
         for (int i = 0; i < 6; i++) faces_out[r * 6 + i] = i < n_dice[r] ? (uint8_t)pcg_die(&g) : 0;
 }
@@ -482,7 +480,7 @@ static void play_game(const fo_coord_t* seat_coord_base, int k, const fb_strateg
         pl[s].strat = strat_unpack(&strats[s]);
         pl[s].strategy_id = strat_ids ? strat_ids[s] : s;
     }
-    uint64_t w0 = t_words, d0 = t_dice, rolls = 0;
+    uint64_t rolls = 0;
     int final_round = 0, score_to_beat = target_score, rounds = 0, err = 0;
     while (rounds < max_rounds && !err) {
         rounds++;
@@ -539,8 +537,10 @@ static void play_game(const fo_coord_t* seat_coord_base, int k, const fb_strateg
     h->flags = flags;
     if (work) {
         work->rolls += rolls;
-        work->dice += t_dice - d0;
-        work->words += t_words - w0;
+        for (int s = 0; s < k; s++) {
+            work->dice += pl[s].rng.dice;
+            work->words += pl[s].rng.words;
+        }
         work->turns += turns;
     }
 }
