@@ -398,8 +398,9 @@ __global__ void default_score_kernel(const ScoreLut* lut, const uint8_t* faces, 
     int used = (int)((e >> 7) & 7u);
     const int sf = (int)((e >> 10) & 3u), so = (int)((e >> 12) & 3u);
     const uint2 sv = reinterpret_cast<const uint2*>(strat)[i];
-    const uint32_t dd = rscore ? smart_discards(rscore, used, sf, so, nd, ts_pre[i], (int)sv.x, sv.y) : 0u;
-    const int d5 = (int)(dd & 0xffu), d1 = (int)(dd >> 8);
+    const uint32_t dd =
+        rscore ? smart_discards(lut, disc_base(sv.y), rscore, used, sf, so, nd, ts_pre[i], (int)sv.x, sv.y) : 0u;
+    const int d5 = (int)(dd & 3u), d1 = (int)(dd >> 2);
     used -= d5 + d1;
     out[i * 5 + 0] = rscore - 50 * d5 - 100 * d1;
     out[i * 5 + 1] = used;

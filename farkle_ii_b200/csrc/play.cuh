@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
     uint32_t saved = 0;
     bool has32 = false, has_scored = false;
     int score = 0, highest = 0, st = 0;
-    uint32_t c_fr = 0, c_th = 0, c_sf = 0, c_so = 0, p1 = 0;
+    uint32_t c_fr = 0, c_th = 0, c_sf = 0, c_so = 0, p1 = 0, dbase = 0;
     // active turn
     int ts = 0, dice = 6, rolls_turn = 0;
     // work/total accumulators (reduced once at kernel end)
@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
             c_so = SEATW(seat, W_SO);
             st = (int)SEATW(seat, W_P0);
             p1 = SEATW(seat, W_P1);
+            dbase = disc_base(p1);
             dice = 6;
             ts = 0;
             rolls_turn = 0;
@@ -391,8 +392,8 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
                 ts = 0;
                 turn_over = true;
             } else {
-                const uint32_t dd = smart_discards(rscore, used, sf, so, n, ts, st, p1);
-                const int d5 = (int)(dd & 0xffu), d1 = (int)(dd >> 8);
+                const uint32_t dd = smart_discards(lut, dbase, rscore, used, sf, so, n, ts, st, p1);
+                const int d5 = (int)(dd & 3u), d1 = (int)(dd >> 2);
                 const int pts = rscore - 50 * d5 - 100 * d1;
                 used -= d5 + d1;
                 if (d5) c_sf += 1u + ((uint32_t)d5 << 16);

@@ -6,10 +6,11 @@
 //   apply_discards                 src/farkle/game/scoring.py:548-578
 //   _decide_continue               src/farkle/simulation/strategies.py:125-162
 //
-// Layout of the lookup in shared memory (15,136 bytes per CTA):
+// Layout of the lookup in shared memory (18,592 bytes per CTA):
 //   idxA[512] u8   packed 3-bit counts of faces 1,2,3 -> combo index 0..83
 //   idxB[512] u8   packed 3-bit counts of faces 4,5,6 -> combo index 0..83
 //   tab[84*84] u16 score/50 (7 bits) | used (3) | single_fives (2) | single_ones (2)
+//   disc[3456] u8  smart-discard decision, see disc_index()
 // A roll's histogram h = sum 1 << 3*(face-1) indexes it as
 //   tab[idxA[h & 511] * 84 + idxB[h >> 9]].
 #pragma once
@@ -22,12 +23,16 @@ namespace fb {
 constexpr int LUT_COMBOS = 84;  // multisets of <= 6 dice over 3 faces = C(9,3)
 constexpr int LUT_IDX = 512;
 constexpr int LUT_TAB = LUT_COMBOS * LUT_COMBOS;
-constexpr int LUT_BYTES = 2 * LUT_IDX + 2 * LUT_TAB;  // 15,136
+// discard table: [favor_score 2][require_both 2][all_singles 2][sf 3][bmax 3][xs 8][yd 6]
+constexpr int DISC_INNER = 2 * 3 * 3 * 8 * 6;  // entries per (favor, both) pair = 864
+constexpr int LUT_DISC = 4 * DISC_INNER;       // 3,456
+constexpr int LUT_BYTES = 2 * LUT_IDX + 2 * LUT_TAB + LUT_DISC;  // 18,592
 
 struct ScoreLut {
     uint8_t idxA[LUT_IDX];
     uint8_t idxB[LUT_IDX];
     uint16_t tab[LUT_TAB];
+    uint8_t disc[LUT_DISC];
 };
 static_assert(sizeof(ScoreLut) == LUT_BYTES, "lut layout");
 
@@ -88,6 +93,38 @@ inline void host_build_lut(ScoreLut& lut) {
             }
             lut.tab[i * LUT_COMBOS + j] = e;
         }
+    // Smart-discard table.  A candidate "drop a lone fives and b lone ones" loses
+    // u = a + 2b units of 50 points and frees D = a + b dice; whether it must bank depends
+    // only on u < xs (score threshold still met) and D < yd (dice threshold still met),
+    // and the preference key is (-u, D) or (D, -u).  So the whole search of
+    // decide_smart_discards (scoring.py:303-467) is a function of seven small integers.
+    for (int fav = 0; fav < 2; fav++)
+        for (int both = 0; both < 2; both++)
+            for (int excl = 0; excl < 2; excl++)
+                for (int sf = 0; sf < 3; sf++)
+                    for (int bm = 0; bm < 3; bm++)
+                        for (int xs = 0; xs < 8; xs++)
+                            for (int yd = 0; yd < 6; yd++) {
+                                int best_k1 = -100, best_k2 = -100, pick = 0;
+                                bool have = false;
+                                for (int a = 0; a <= sf; a++)
+                                    for (int b = 0; b <= bm; b++) {
+                                        if (excl && a == sf && b == bm) continue;  // candidate scores 0
+                                        const int u = a + 2 * b, D = a + b;
+                                        const bool hit_s = u < xs, hit_d = D < yd;
+                                        if (both ? (hit_s && hit_d) : (hit_s || hit_d)) continue;
+                                        const int k1 = fav ? -u : D, k2 = fav ? D : -u;
+                                        if (!have || k1 > best_k1 || (k1 == best_k1 && k2 > best_k2)) {
+                                            have = true;
+                                            best_k1 = k1;
+                                            best_k2 = k2;
+                                            pick = a | (b << 2);
+                                        }
+                                    }
+                                const int idx = (fav * 2 + both) * DISC_INNER +
+                                                ((excl * 3 + sf) * 3 + bm) * 48 + xs * 6 + yd;
+                                lut.disc[idx] = (uint8_t)pick;
+                            }
 }
 
 #ifdef __CUDACC__
@@ -102,41 +139,34 @@ __device__ __forceinline__ uint32_t lut_lookup(const ScoreLut* lut, uint32_t his
 __device__ __forceinline__ int strat_dice_threshold(uint32_t p1) { return (int)(int16_t)(p1 & 0xffffu); }
 __device__ __forceinline__ bool strat_flag(uint32_t p1, uint32_t f) { return (p1 >> 16) & f; }
 
-// Closed form of decide_smart_discards (scoring.py:369-467): the candidate
-// multisets that survive _select_candidate's filter are exactly "drop a of the
-// sf lone fives and b of the so lone ones"; re-scoring such a candidate through
-// the table gives score-50a-100b with used-a-b dice (no special 6-dice pattern
-// can appear because used != n).  Enumeration order and the strict '>' keep the
-// reference's tie-breaking.  Returns d5 | d1 << 8.
-__device__ __forceinline__ uint32_t smart_discards(int score, int used, int sf, int so, int n,
-                                                   int ts, int st, uint32_t p1) {
-    if (!strat_flag(p1, FB_SF_SMART_FIVE) || used == n || (sf | so) == 0) return 0u;
-    const int dt = strat_dice_threshold(p1);
-    const bool cs = strat_flag(p1, FB_SF_CONSIDER_SCORE);
-    const bool cd = strat_flag(p1, FB_SF_CONSIDER_DICE);
-    const bool both = cs && cd && strat_flag(p1, FB_SF_REQUIRE_BOTH);
-    const bool fav_score = strat_flag(p1, FB_SF_FAVOR_SCORE);
-    const int bmax = strat_flag(p1, FB_SF_SMART_ONE) ? so : 0;
-    int best = -1;
-    uint32_t pick = 0u;
-    for (int a = 0; a <= sf; a++) {
-        for (int b = 0; b <= bmax; b++) {
-            const int cand = score - 50 * a - 100 * b;
-            if (cand == 0) continue;  // score_lister drops non-scoring candidates
-            const int sa = ts + cand;
-            const int dl = n - used + a + b;
-            const bool hit_s = cs && sa >= st;
-            const bool hit_d = cd && dl <= dt;
-            const bool bank = both ? (hit_s && hit_d) : (hit_s || hit_d);
-            if (bank) continue;
-            const int key = fav_score ? ((sa << 3) | dl) : ((dl << 27) | sa);
-            if (key > best) {
-                best = key;
-                pick = (uint32_t)a | ((uint32_t)b << 8);
-            }
-        }
-    }
-    return pick;
+// Per-strategy part of the discard-table index: (favor_score * 2 + require_both) * 864.
+__device__ __forceinline__ uint32_t disc_base(uint32_t p1) {
+    const bool both = strat_flag(p1, FB_SF_CONSIDER_SCORE) && strat_flag(p1, FB_SF_CONSIDER_DICE) &&
+                      strat_flag(p1, FB_SF_REQUIRE_BOTH);
+    return ((strat_flag(p1, FB_SF_FAVOR_SCORE) ? 2u : 0u) + (both ? 1u : 0u)) * DISC_INNER;
+}
+
+// decide_smart_discards (scoring.py:369-467) as ONE table lookup, branch free.
+// The candidates that survive _select_candidate's filter are exactly "drop a of the sf
+// lone fives and b of the so lone ones" (b = 0 unless smart_one); re-scoring one through
+// the table gives score-50a-100b with used-a-b dice (no special 6-dice pattern can appear
+// because used != n).  With X = ts + score - score_threshold and Y = dice_threshold -
+// (n - used):  hit_score <=> consider_score and 50(a+2b) <= X,  hit_dice <=>
+// consider_dice and a+b <= Y.  xs / yd below count how many values of a+2b / a+b hit.
+// Returns d5 | d1 << 2.
+__device__ __forceinline__ uint32_t smart_discards(const ScoreLut* lut, uint32_t dbase, int score,
+                                                   int used, int sf, int so, int n, int ts,
+                                                   int st, uint32_t p1) {
+    const bool on = strat_flag(p1, FB_SF_SMART_FIVE) && used != n;
+    const int sfi = on ? sf : 0;
+    const int bm = (on && strat_flag(p1, FB_SF_SMART_ONE)) ? so : 0;
+    int xs = min(max(ts + score - st + 50, 0), 399);
+    xs = (xs * 1311) >> 16;  // floor(xs / 50) for 0 <= xs <= 399
+    xs = strat_flag(p1, FB_SF_CONSIDER_SCORE) ? xs : 0;
+    int yd = min(max(strat_dice_threshold(p1) - (n - used) + 1, 0), 5);
+    yd = strat_flag(p1, FB_SF_CONSIDER_DICE) ? yd : 0;
+    const int excl = score == 50 * sfi + 100 * bm ? 1 : 0;  // the all-discard candidate scores 0
+    return lut->disc[dbase + ((excl * 3 + sfi) * 3 + bm) * 48 + xs * 6 + yd];
 }
 
 // _decide_continue (strategies.py:125-162).
