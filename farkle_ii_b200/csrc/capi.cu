@@ -13,6 +13,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -444,6 +445,10 @@ int launch_play(const PlayParams& P, cudaStream_t stream) {
     int warps = (int)((budget - lut_bytes) / per_warp);
     if (warps < 1) return fail(FB_ERR_BAD_ARG, "k=%d does not fit the shared-memory seat store", k);
     if (warps > 32) warps = 32;
+    if (const char* env = getenv("FB_PLAY_WARPS")) {  // tuning knob: cap resident warps per SM
+        const int cap = atoi(env);
+        if (cap >= 1 && cap < warps) warps = cap;
+    }
     const uint64_t lanes_needed = P.n_games;
     int grid = g_ctx.sm_count;
     const uint64_t per_cta = (uint64_t)warps * 32;
@@ -462,17 +467,17 @@ int launch_play(const PlayParams& P, cudaStream_t stream) {
         FB_CUDA(cudaEventCreate(&t_ev0));
         FB_CUDA(cudaEventCreate(&t_ev1));
     }
-    if (warps > 16) {
-        FB_CUDA(cudaFuncSetAttribute(play_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)budget));
+    auto launch = [&](auto kernel) -> int {
+        FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
         FB_CUDA(cudaEventRecord(t_ev0, stream));
-        play_kernel<1024><<<grid, warps * 32, smem, stream>>>(P, g_ctx.lut_dev);
-    } else {
-        FB_CUDA(cudaFuncSetAttribute(play_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)budget));
-        FB_CUDA(cudaEventRecord(t_ev0, stream));
-        play_kernel<512><<<grid, warps * 32, smem, stream>>>(P, g_ctx.lut_dev);
-    }
+        kernel<<<grid, warps * 32, smem, stream>>>(P, g_ctx.lut_dev);
+        return FB_OK;
+    };
+    int lrc;
+    if (warps > 24) lrc = launch(play_kernel<1024>);
+    else if (warps > 16) lrc = launch(play_kernel<768>);
+    else lrc = launch(play_kernel<512>);
+    if (lrc) return lrc;
     int rc = launch_check("play_kernel");
     if (rc) return rc;
     FB_CUDA(cudaEventRecord(t_ev1, stream));

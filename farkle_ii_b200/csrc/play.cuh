@@ -315,40 +315,51 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
             status = ST_PLAY;
         }
 
-        // ================= P: one roll ==========================================
+        // ================= P: one roll (straight-line, no divergent branches) =====
         if (status == ST_PLAY) {
             const int n = dice;
-            // -- dice: n consecutive 32-bit halves of the seat's stream (engine.py:101)
+            // -- dice: n consecutive 32-bit halves of the seat's stream (engine.py:101).
+            // Halves H0..H6 = [buffered half, lo/hi of up to three fresh 64-bit outputs];
+            // die i reads H[i + p].  All three outputs are always computed; the state only
+            // advances past the nw words this roll really consumes.
             const uint32_t p = has32 ? 0u : 1u;
-            const int nw = (n + (int)p) >> 1;  // fresh 64-bit words this roll needs
+            const int nw = (n + (int)p) >> 1;
             uint64_t shi = rng.hi, slo = rng.lo;
-            uint32_t H1 = 0, H2 = 0, H3 = 0, H4 = 0, H5 = 0, H6 = 0;
-            if (nw > 0) {
-                const uint64_t o = pcg_output(shi, slo);
-                pcg_step(shi, slo, rng.ihi, rng.ilo);
-                H1 = (uint32_t)o;
-                H2 = (uint32_t)(o >> 32);
+            const uint64_t o1 = pcg_output(shi, slo);
+            {
+                uint64_t th = shi, tl = slo;
+                pcg_step(th, tl, rng.ihi, rng.ilo);
+                const bool c = nw > 0;
+                shi = c ? th : shi;
+                slo = c ? tl : slo;
             }
-            if (nw > 1) {
-                const uint64_t o = pcg_output(shi, slo);
-                pcg_step(shi, slo, rng.ihi, rng.ilo);
-                H3 = (uint32_t)o;
-                H4 = (uint32_t)(o >> 32);
+            const uint64_t o2 = pcg_output(shi, slo);
+            {
+                uint64_t th = shi, tl = slo;
+                pcg_step(th, tl, rng.ihi, rng.ilo);
+                const bool c = nw > 1;
+                shi = c ? th : shi;
+                slo = c ? tl : slo;
             }
-            if (nw > 2) {
-                const uint64_t o = pcg_output(shi, slo);
-                pcg_step(shi, slo, rng.ihi, rng.ilo);
-                H5 = (uint32_t)o;
-                H6 = (uint32_t)(o >> 32);
+            const uint64_t o3 = pcg_output(shi, slo);
+            {
+                uint64_t th = shi, tl = slo;
+                pcg_step(th, tl, rng.ihi, rng.ilo);
+                const bool c = nw > 2;
+                shi = c ? th : shi;
+                slo = c ? tl : slo;
             }
+            const uint32_t H1 = (uint32_t)o1, H2 = (uint32_t)(o1 >> 32);
+            const uint32_t H3 = (uint32_t)o2, H4 = (uint32_t)(o2 >> 32);
+            const uint32_t H5 = (uint32_t)o3, H6 = (uint32_t)(o3 >> 32);
             uint32_t hist = 0;
-            bool rej = false;
+            uint32_t minlo = 0xffffffffu;  // Lemire leftover; < 4 means NumPy redraws
 #define FB_DIE(i_, Ha_, Hb_)                                       \
-    if ((i_) < n) {                                                \
+    {                                                              \
         const uint32_t u_ = p ? (Hb_) : (Ha_);                     \
         const uint64_t m_ = (uint64_t)u_ * 6u;                     \
-        rej |= (uint32_t)m_ < 4u;                                  \
-        hist += 1u << (3u * (uint32_t)(m_ >> 32));                 \
+        minlo = min(minlo, (uint32_t)m_);                          \
+        if ((i_) < n) hist += 1u << (3u * (uint32_t)(m_ >> 32));   \
     }
             FB_DIE(0, saved, H1)
             FB_DIE(1, H1, H2)
@@ -361,8 +372,9 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
             bool nhas = (q & 1u) == 0u;
             uint32_t nsaved = q == 2u ? H2 : (q == 4u ? H4 : H6);
             uint32_t words = (uint32_t)nw;
-            if (rej) {
-                // Lemire rejection (4 in 2^32 per die): replay this roll draw by draw.
+            if (minlo < 4u) {
+                // A draw with leftover < 4 somewhere in the window (4 in 2^32 per die; unused
+                // slots can only add false alarms): replay this roll draw by draw.
                 PcgStream s{rng, saved, has32};
                 hist = 0;
                 words = 0;
@@ -379,43 +391,35 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
             a_dice += (uint32_t)n;
             a_words += words;
 
-            // -- score the roll (engine.py:103-147)
+            // -- score the roll (engine.py:103-147), discards, counters
             const uint32_t e = lut_lookup(lut, hist);
             const int rscore = (int)(e & 127u) * 50;
-            int used = (int)((e >> 7) & 7u);
+            const int used0 = (int)((e >> 7) & 7u);
             const int sf = (int)((e >> 10) & 3u), so = (int)((e >> 12) & 3u);
-            c_fr += 0x10000u;  // n_rolls += 1
+            const bool farkle = rscore == 0;
+            const uint32_t dd = smart_discards(lut, dbase, rscore, used0, sf, so, n, ts, st, p1);
+            const uint32_t d5 = dd & 3u, d1 = dd >> 2;  // both 0 on a farkle
+            const int pts = rscore - 50 * (int)d5 - 100 * (int)d1;
+            const int used = used0 - (int)d5 - (int)d1;
+            c_sf += (d5 << 16) + ((d5 + 1u) >> 1);  // uses += (d5 > 0), dice += d5
+            c_so += (d1 << 16) + ((d1 + 1u) >> 1);
+            c_fr += 0x10000u + (farkle ? 1u : 0u);  // n_rolls += 1, n_farkles += farkle
             rolls_turn++;
-            bool turn_over = false;
-            if (rscore == 0) {
-                c_fr += 1u;  // n_farkles += 1
-                ts = 0;
-                turn_over = true;
-            } else {
-                const uint32_t dd = smart_discards(lut, dbase, rscore, used, sf, so, n, ts, st, p1);
-                const int d5 = (int)(dd & 3u), d1 = (int)(dd >> 2);
-                const int pts = rscore - 50 * d5 - 100 * d1;
-                used -= d5 + d1;
-                if (d5) c_sf += 1u + ((uint32_t)d5 << 16);
-                if (d1) c_so += 1u + ((uint32_t)d1 << 16);
-                dice = used == n ? 6 : n - used;
-                ts += pts;
-                if (strat_flag(p1, FB_SF_AUTO_HOT_DICE) && dice == 6) {
-                    c_th += 0x10000u;  // n_hot_dice += 1, roll again (engine.py:149-154)
-                } else {
-                    // _should_continue (engine.py:156-205) + decide (strategies.py:212-275)
-                    const bool fin = trigger >= 0;
-                    const bool runup = strat_flag(p1, FB_SF_RUN_UP_SCORE);
-                    const int rt = score + ts;
-                    bool keep;
-                    if (fin && rt > stb && !runup) keep = false;
-                    else if (!has_scored && ts < 500) keep = true;
-                    else if (fin && rt <= stb) keep = true;
-                    else keep = decide_continue(ts, dice, st, p1);
-                    if (fin && rt <= stb) keep = true;
-                    turn_over = !keep;
-                }
-            }
+            const int ndice = used == n ? 6 : n - used;
+            const int ts2 = ts + pts;
+            // -- hot dice (engine.py:149-154), then _should_continue (engine.py:156-205) and
+            //    ThresholdStrategy.decide (strategies.py:212-275)
+            const bool hot = !farkle && ndice == 6 && strat_flag(p1, FB_SF_AUTO_HOT_DICE);
+            c_th += hot ? 0x10000u : 0u;
+            const bool fin = trigger >= 0;
+            const int rt = score + ts2;
+            const bool behind = fin && rt <= stb;
+            const bool stop_ahead = fin && rt > stb && !strat_flag(p1, FB_SF_RUN_UP_SCORE);
+            const bool gate = !has_scored && ts2 < 500;
+            const bool keep = !stop_ahead && (gate || behind || decide_continue(ts2, ndice, st, p1));
+            bool turn_over = farkle || (!hot && !keep);
+            ts = farkle ? 0 : ts2;
+            dice = ndice;
             if (!turn_over && rolls_turn >= ROLL_LIMIT) {  // engine.py:242-243 raises
                 err |= FB_ROW_ROLL_LIMIT;
                 turn_over = true;

@@ -169,14 +169,15 @@ __device__ __forceinline__ uint32_t smart_discards(const ScoreLut* lut, uint32_t
     return lut->disc[dbase + ((excl * 3 + sfi) * 3 + bm) * 48 + xs * 6 + yd];
 }
 
-// _decide_continue (strategies.py:125-162).
+// _decide_continue (strategies.py:125-162), branch free: with only one threshold
+// considered the other "want" is false, so OR gives the single-threshold answer.
 __device__ __forceinline__ bool decide_continue(int ts, int dice, int st, uint32_t p1) {
     const bool cs = strat_flag(p1, FB_SF_CONSIDER_SCORE);
     const bool cd = strat_flag(p1, FB_SF_CONSIDER_DICE);
     const bool want_s = cs && ts < st;
     const bool want_d = cd && dice > strat_dice_threshold(p1);
-    if (cs && cd) return strat_flag(p1, FB_SF_REQUIRE_BOTH) ? (want_s || want_d) : (want_s && want_d);
-    return cs ? want_s : (cd ? want_d : false);
+    const bool and_mode = cs && cd && !strat_flag(p1, FB_SF_REQUIRE_BOTH);
+    return and_mode ? (want_s && want_d) : (want_s || want_d);
 }
 #endif  // __CUDACC__
 
