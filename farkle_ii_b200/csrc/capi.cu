@@ -5,7 +5,8 @@
 //   seed_h2h_kernel         same for H2H attempts
 //   seed_explicit_kernel    same for explicit coordinates
 //   permute_kernel          Generator.permutation per shuffle
-//   play_kernel             (play.cuh) the game state machine, rows and tallies
+//   play_kernel             (play.cuh) the game state machine over L2-resident seat records
+//   finish_kernel           (play.cuh) dense pass: winner, compact rows, tallies, totals
 //   h2h_resolve_kernel      early-stop prefix rule over attempt outcomes
 //   test kernels            seedseq / coordinate_seed / roll_dice / default_score
 #include <cuda_runtime.h>
@@ -82,8 +83,9 @@ inline int launch_check(const char* what) {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
-    uint32_t* seat_state;
-    int32_t* seat_strat;
+    SeatMut* mut;
+    SeatImm* imm;
+    uint32_t* header;
     uint64_t* game_seed;
     int32_t* limits;
     unsigned int* counter;
@@ -92,18 +94,20 @@ struct Workspace {
 };
 
 size_t ws_core_bytes(int k, uint64_t n) {
-    return align_up(n * (uint64_t)k * 32, 256) + align_up(n * (uint64_t)k * 4, 256) +
-           align_up(n * 8, 256) + align_up(n * 8, 256) + 256;
+    return align_up(n * (uint64_t)k * sizeof(SeatMut), 256) + align_up(n * (uint64_t)k * sizeof(SeatImm), 256) +
+           align_up(n * 4, 256) + align_up(n * 8, 256) + align_up(n * 8, 256) + 256;
 }
 
 bool carve(void* base, size_t bytes, int k, uint64_t n, Workspace& w) {
     uint8_t* p = static_cast<uint8_t*>(base);
     const size_t core = ws_core_bytes(k, n);
     if (bytes < core) return false;
-    w.seat_state = reinterpret_cast<uint32_t*>(p);
-    p += align_up(n * (uint64_t)k * 32, 256);
-    w.seat_strat = reinterpret_cast<int32_t*>(p);
-    p += align_up(n * (uint64_t)k * 4, 256);
+    w.mut = reinterpret_cast<SeatMut*>(p);
+    p += align_up(n * (uint64_t)k * sizeof(SeatMut), 256);
+    w.imm = reinterpret_cast<SeatImm*>(p);
+    p += align_up(n * (uint64_t)k * sizeof(SeatImm), 256);
+    w.header = reinterpret_cast<uint32_t*>(p);
+    p += align_up(n * 4, 256);
     w.game_seed = reinterpret_cast<uint64_t*>(p);
     p += align_up(n * 8, 256);
     w.limits = reinterpret_cast<int32_t*>(p);
@@ -120,10 +124,17 @@ bool carve(void* base, size_t bytes, int k, uint64_t n, Workspace& w) {
 // ---------------------------------------------------------------------------
 // device helpers / kernels
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void store_state(uint32_t* dst, const Pcg& g) {
-    uint4* d = reinterpret_cast<uint4*>(dst);
-    d[0] = make_uint4((uint32_t)g.lo, (uint32_t)(g.lo >> 32), (uint32_t)g.hi, (uint32_t)(g.hi >> 32));
-    d[1] = make_uint4((uint32_t)g.ilo, (uint32_t)(g.ilo >> 32), (uint32_t)g.ihi, (uint32_t)(g.ihi >> 32));
+// Fresh seat records: seeded stream, zero score / counters, the seat's strategy.
+__device__ __forceinline__ void store_seat(SeatMut* mut, SeatImm* imm, const Pcg& g, const fb_strategy_t* table,
+                                           uint32_t strat_index) {
+    uint4* m = reinterpret_cast<uint4*>(mut);
+    m[0] = make_uint4((uint32_t)g.lo, (uint32_t)(g.lo >> 32), (uint32_t)g.hi, (uint32_t)(g.hi >> 32));
+    m[1] = make_uint4(0u, 0u, 0u, 0u);
+    m[2] = make_uint4(0u, 0u, 0u, 0u);
+    const uint2 sv = reinterpret_cast<const uint2*>(table)[strat_index];
+    uint4* i = reinterpret_cast<uint4*>(imm);
+    i[0] = make_uint4((uint32_t)g.ilo, (uint32_t)(g.ilo >> 32), (uint32_t)g.ihi, (uint32_t)(g.ihi >> 32));
+    i[1] = make_uint4(sv.x, sv.y, strat_index, 0u);
 }
 
 __device__ __forceinline__ uint64_t coord_fingerprint(const Coord& c, bool as_u32) {
@@ -138,7 +149,7 @@ __global__ void __launch_bounds__(256) seed_tournament_kernel(
     uint64_t root, int k, uint64_t shuffle0, uint32_t gps, uint64_t n_games, const int32_t* perm,
     int n_strategies, int32_t target, int32_t max_rounds, const uint64_t* ov_shuffle,
     const uint32_t* ov_game, const int32_t* ov_rounds, int n_ov, int want_seeds,
-    uint32_t* seat_state, int32_t* seat_strat, uint64_t* game_seed, int32_t* limits) {
+    const fb_strategy_t* table, SeatMut* mut, SeatImm* imm, uint64_t* game_seed, int32_t* limits) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_games * (uint64_t)k) return;
     const uint64_t g = t / (uint64_t)k;
@@ -148,8 +159,7 @@ __global__ void __launch_bounds__(256) seed_tournament_kernel(
     Coord c{FB_PURPOSE_TOURNAMENT_PLAYER, root, (uint64_t)k, shuffle0 + sl, 0, 0, gi, s, 0};
     Pcg pg;
     pcg_seed_coord(pg, c);
-    store_state(seat_state + t * 8, pg);
-    seat_strat[t] = perm[sl * (uint64_t)n_strategies + (uint64_t)gi * k + s];
+    store_seat(mut + t, imm + t, pg, table, (uint32_t)perm[sl * (uint64_t)n_strategies + (uint64_t)gi * k + s]);
     if (s == 0) {
         if (want_seeds) {
             Coord gc = c;
@@ -199,8 +209,8 @@ __global__ void h2h_offsets_kernel(const uint32_t* n_attempts, int n_blocks, uin
 __global__ void __launch_bounds__(256) seed_h2h_kernel(
     uint64_t root, int n_blocks, const uint64_t* pair_id, const uint8_t* order,
     const fb_strategy_t* seat1, const fb_strategy_t* seat2, const uint32_t* attempt0,
-    const uint64_t* offsets, uint64_t total, int want_seeds, uint32_t* seat_state,
-    int32_t* seat_strat, uint64_t* game_seed, fb_strategy_t* table) {
+    const uint64_t* offsets, uint64_t total, int want_seeds, SeatMut* mut, SeatImm* imm,
+    uint64_t* game_seed) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total * 2) return;
     const uint64_t g = t >> 1;
@@ -215,9 +225,7 @@ __global__ void __launch_bounds__(256) seed_h2h_kernel(
     Coord c{FB_PURPOSE_H2H_PLAYER, root, 2, 0, pair_id[b], order[b], a, s, 0};
     Pcg pg;
     pcg_seed_coord(pg, c);
-    store_state(seat_state + t * 8, pg);
-    seat_strat[t] = b * 2 + (int)s;
-    if (g == offsets[b]) table[b * 2 + s] = s ? seat2[b] : seat1[b];
+    store_seat(mut + t, imm + t, pg, s ? seat2 : seat1, (uint32_t)b);
     if (s == 0 && want_seeds) {
         Coord gc = c;
         gc.purpose = FB_PURPOSE_H2H_GAME;
@@ -225,8 +233,9 @@ __global__ void __launch_bounds__(256) seed_h2h_kernel(
     }
 }
 
-__global__ void __launch_bounds__(256) seed_explicit_kernel(const uint64_t* coords, uint64_t n_games,
-                                                            int k, uint32_t* seat_state) {
+__global__ void __launch_bounds__(256) seed_explicit_kernel(const uint64_t* coords, uint64_t n_games, int k,
+                                                            const fb_strategy_t* seat_table, SeatMut* mut,
+                                                            SeatImm* imm) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_games * (uint64_t)k) return;
     const uint64_t g = t / (uint64_t)k;
@@ -234,7 +243,7 @@ __global__ void __launch_bounds__(256) seed_explicit_kernel(const uint64_t* coor
     Coord c{(uint32_t)cc[0], cc[1], cc[2], cc[3], cc[4], cc[5], cc[6], t - g * (uint64_t)k, 0};
     Pcg pg;
     pcg_seed_coord(pg, c);
-    store_state(seat_state + t * 8, pg);
+    store_seat(mut + t, imm + t, pg, seat_table, (uint32_t)t);
 }
 
 __global__ void pack_limits_kernel(const int32_t* tv, int32_t t0, const int32_t* mv, int32_t m0,
@@ -437,23 +446,17 @@ __global__ void __launch_bounds__(1024, 1) issue_peak_kernel(int iters, uint32_t
 // ---------------------------------------------------------------------------
 namespace {
 
-int launch_play(const PlayParams& P, cudaStream_t stream) {
-    const int k = P.k;
-    const size_t lut_bytes = (LUT_BYTES + 15) & ~15;
-    const size_t per_warp = (size_t)k * SEAT_WORDS * STORE_STRIDE * 4;
-    const size_t budget = (size_t)g_ctx.max_smem_optin - 1024;  // static smem + slack
-    int warps = (int)((budget - lut_bytes) / per_warp);
-    if (warps < 1) return fail(FB_ERR_BAD_ARG, "k=%d does not fit the shared-memory seat store", k);
-    if (warps > 32) warps = 32;
-    if (const char* env = getenv("FB_PLAY_WARPS")) {  // tuning knob: cap resident warps per SM
+int launch_play(const PlayParams& P, const FinishParams& F, cudaStream_t stream) {
+    // One persistent CTA per SM; shared memory holds only the lookup tables.
+    int warps = 32;
+    if (const char* env = getenv("FB_PLAY_WARPS")) {  // tuning knob: resident warps per SM
         const int cap = atoi(env);
         if (cap >= 1 && cap < warps) warps = cap;
     }
     const uint64_t lanes_needed = P.n_games;
     int grid = g_ctx.sm_count;
     const uint64_t per_cta = (uint64_t)warps * 32;
-    if ((uint64_t)grid * per_cta > lanes_needed) {
-        // small launch: fewer CTAs, then fewer warps
+    if ((uint64_t)grid * per_cta > lanes_needed) {  // small launch: fewer CTAs, then fewer warps
         grid = (int)((lanes_needed + per_cta - 1) / per_cta);
         if (grid < 1) grid = 1;
         if (grid == 1) {
@@ -461,28 +464,20 @@ int launch_play(const PlayParams& P, cudaStream_t stream) {
             if (warps < 1) warps = 1;
         }
     }
-    const size_t smem = lut_bytes + per_warp * (size_t)warps;
+    const size_t smem = (LUT_BYTES + 15) & ~15;
     FB_CUDA(cudaMemsetAsync(P.counter, 0, sizeof(unsigned int), stream));
     if (!t_ev0) {
         FB_CUDA(cudaEventCreate(&t_ev0));
         FB_CUDA(cudaEventCreate(&t_ev1));
     }
-    auto launch = [&](auto kernel) -> int {
-        FB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-        FB_CUDA(cudaEventRecord(t_ev0, stream));
-        kernel<<<grid, warps * 32, smem, stream>>>(P, g_ctx.lut_dev);
-        return FB_OK;
-    };
-    int lrc;
-    if (warps > 24) lrc = launch(play_kernel<1024>);
-    else if (warps > 16) lrc = launch(play_kernel<768>);
-    else lrc = launch(play_kernel<512>);
-    if (lrc) return lrc;
+    FB_CUDA(cudaEventRecord(t_ev0, stream));
+    play_kernel<1024><<<grid, warps * 32, smem, stream>>>(P, g_ctx.lut_dev);
     int rc = launch_check("play_kernel");
     if (rc) return rc;
     FB_CUDA(cudaEventRecord(t_ev1, stream));
     t_ev_valid = true;
-    return FB_OK;
+    finish_kernel<<<(unsigned)((F.n_games + 255) / 256), 256, 0, stream>>>(F);
+    return launch_check("finish_kernel");
 }
 
 inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -629,30 +624,36 @@ int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuff
     seed_tournament_kernel<<<blocks_for(n_games * k, 256), 256, 0, stream>>>(
         root_seed, k, shuffle0, gps, n_games, perm, n_strategies, target_score, max_rounds,
         override_shuffle_dev, override_game_dev, override_max_rounds_dev, n_overrides, want_game_seeds,
-        w.seat_state, w.seat_strat, w.game_seed, limits);
+        strategies_dev, w.mut, w.imm, w.game_seed, limits);
     rc = launch_check("seed_tournament_kernel");
     if (rc) return rc;
     PlayParams P{};
-    P.seat_state = w.seat_state;
-    P.seat_strat = w.seat_strat;
-    P.strategies = strategies_dev;
-    P.strategy_ids = strategy_ids_dev;
-    P.ids_mode = strategy_ids_dev ? 1 : 0;
-    P.game_seed = want_game_seeds ? w.game_seed : nullptr;
+    P.mut = w.mut;
+    P.imm = w.imm;
+    P.header = w.header;
     P.limits = limits;
     P.target_score = target_score;
     P.max_rounds = max_rounds;
     P.n_games = (uint32_t)n_games;
     P.k = k;
-    P.games_per_slot = shuffles_per_slot > 0 ? (uint32_t)shuffles_per_slot * gps : 0u;
-    P.n_tally_ids = n_tally_ids;
-    P.tallies = reinterpret_cast<unsigned long long*>(tallies_dev);
     P.totals = reinterpret_cast<unsigned long long*>(totals_dev);
-    P.rows = reinterpret_cast<uint32_t*>(rows_dev);
-    P.row_words = (int)(fb_row_stride(k) / 4);
-    P.outcome = nullptr;
     P.counter = w.counter;
-    return launch_play(P, stream);
+    FinishParams F{};
+    F.mut = w.mut;
+    F.imm = w.imm;
+    F.header = w.header;
+    F.strategy_ids = strategy_ids_dev;
+    F.ids_mode = strategy_ids_dev ? 1 : 0;
+    F.game_seed = want_game_seeds ? w.game_seed : nullptr;
+    F.n_games = (uint32_t)n_games;
+    F.k = k;
+    F.games_per_slot = shuffles_per_slot > 0 ? (uint32_t)shuffles_per_slot * gps : 0u;
+    F.n_tally_ids = n_tally_ids;
+    F.tallies = reinterpret_cast<unsigned long long*>(tallies_dev);
+    F.totals = reinterpret_cast<unsigned long long*>(totals_dev);
+    F.rows = reinterpret_cast<uint32_t*>(rows_dev);
+    F.row_words = (int)(fb_row_stride(k) / 4);
+    return launch_play(P, F, stream);
 }
 
 int fb_play_h2h(uint64_t root_seed, int n_blocks, const uint64_t* pair_id_dev, const uint8_t* order_dev,
@@ -667,37 +668,42 @@ int fb_play_h2h(uint64_t root_seed, int n_blocks, const uint64_t* pair_id_dev, c
     if (total_attempts > 0xfffffff0ull) return fail(FB_ERR_BAD_ARG, "more than 2^32 attempts in one launch");
     Workspace w;
     const size_t off_bytes = align_up((size_t)(n_blocks + 1) * 8, 256);
-    const size_t tab_bytes = align_up((size_t)n_blocks * 2 * sizeof(fb_strategy_t), 256);
-    if (!carve(workspace_dev, workspace_bytes, 2, total_attempts, w) || w.extra_bytes < off_bytes + tab_bytes)
+    if (!carve(workspace_dev, workspace_bytes, 2, total_attempts, w) || w.extra_bytes < off_bytes)
         return fail(FB_ERR_WORKSPACE, "workspace too small: need %zu bytes",
-                    ws_core_bytes(2, total_attempts) + off_bytes + tab_bytes);
+                    ws_core_bytes(2, total_attempts) + off_bytes);
     uint64_t* offsets = reinterpret_cast<uint64_t*>(w.extra);
-    fb_strategy_t* table = reinterpret_cast<fb_strategy_t*>(w.extra + off_bytes);
     h2h_offsets_kernel<<<1, 1024, 0, stream>>>(n_attempts_dev, n_blocks, offsets);
     int rc = launch_check("h2h_offsets_kernel");
     if (rc) return rc;
     const int want_seeds = rows_dev != nullptr;
     seed_h2h_kernel<<<blocks_for(total_attempts * 2, 256), 256, 0, stream>>>(
         root_seed, n_blocks, pair_id_dev, order_dev, seat1_dev, seat2_dev, attempt0_dev, offsets,
-        total_attempts, want_seeds, w.seat_state, w.seat_strat, w.game_seed, table);
+        total_attempts, want_seeds, w.mut, w.imm, w.game_seed);
     rc = launch_check("seed_h2h_kernel");
     if (rc) return rc;
     PlayParams P{};
-    P.seat_state = w.seat_state;
-    P.seat_strat = w.seat_strat;
-    P.strategies = table;
-    P.ids_mode = 2;
-    P.game_seed = want_seeds ? w.game_seed : nullptr;
+    P.mut = w.mut;
+    P.imm = w.imm;
+    P.header = w.header;
     P.target_score = target_score;
     P.max_rounds = max_rounds;
     P.n_games = (uint32_t)total_attempts;
     P.k = 2;
     P.totals = reinterpret_cast<unsigned long long*>(totals_dev);
-    P.rows = reinterpret_cast<uint32_t*>(rows_dev);
-    P.row_words = (int)(fb_row_stride(2) / 4);
-    P.outcome = outcome_out_dev;
     P.counter = w.counter;
-    return launch_play(P, stream);
+    FinishParams F{};
+    F.mut = w.mut;
+    F.imm = w.imm;
+    F.header = w.header;
+    F.ids_mode = 2;
+    F.game_seed = want_seeds ? w.game_seed : nullptr;
+    F.n_games = (uint32_t)total_attempts;
+    F.k = 2;
+    F.totals = reinterpret_cast<unsigned long long*>(totals_dev);
+    F.rows = reinterpret_cast<uint32_t*>(rows_dev);
+    F.row_words = (int)(fb_row_stride(2) / 4);
+    F.outcome = outcome_out_dev;
+    return launch_play(P, F, stream);
 }
 
 int fb_h2h_resolve(int n_blocks, const uint32_t* n_attempts_dev, const uint8_t* outcome_dev,
@@ -731,7 +737,8 @@ int fb_play_games(const uint64_t* coords_dev, uint64_t n_games, int k,
     Workspace w;
     if (!carve(workspace_dev, workspace_bytes, k, n_games, w))
         return fail(FB_ERR_WORKSPACE, "workspace too small: need %zu bytes", ws_core_bytes(k, n_games));
-    seed_explicit_kernel<<<blocks_for(n_games * k, 256), 256, 0, stream>>>(coords_dev, n_games, k, w.seat_state);
+    seed_explicit_kernel<<<blocks_for(n_games * k, 256), 256, 0, stream>>>(coords_dev, n_games, k,
+                                                                          seat_strategies_dev, w.mut, w.imm);
     int rc = launch_check("seed_explicit_kernel");
     if (rc) return rc;
     int32_t* limits = nullptr;
@@ -743,21 +750,28 @@ int fb_play_games(const uint64_t* coords_dev, uint64_t n_games, int k,
         if (rc) return rc;
     }
     PlayParams P{};
-    P.seat_state = w.seat_state;
-    P.seat_strat = nullptr;  // entry g*k+s of seat_strategies_dev
-    P.strategies = seat_strategies_dev;
-    P.strategy_ids = seat_strategy_ids_dev;
-    P.ids_mode = seat_strategy_ids_dev ? 1 : 2;
+    P.mut = w.mut;
+    P.imm = w.imm;
+    P.header = w.header;
     P.limits = limits;
     P.target_score = target_score;
     P.max_rounds = max_rounds;
     P.n_games = (uint32_t)n_games;
     P.k = k;
     P.totals = reinterpret_cast<unsigned long long*>(totals_dev);
-    P.rows = reinterpret_cast<uint32_t*>(rows_dev);
-    P.row_words = (int)(fb_row_stride(k) / 4);
     P.counter = w.counter;
-    return launch_play(P, stream);
+    FinishParams F{};
+    F.mut = w.mut;
+    F.imm = w.imm;
+    F.header = w.header;
+    F.strategy_ids = seat_strategy_ids_dev;
+    F.ids_mode = seat_strategy_ids_dev ? 1 : 2;
+    F.n_games = (uint32_t)n_games;
+    F.k = k;
+    F.totals = reinterpret_cast<unsigned long long*>(totals_dev);
+    F.rows = reinterpret_cast<uint32_t*>(rows_dev);
+    F.row_words = (int)(fb_row_stride(k) / 4);
+    return launch_play(P, F, stream);
 }
 
 int fb_run_tournament_host(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,

@@ -1,4 +1,4 @@
-// play.cuh — the persistent one-game-per-lane Farkle state machine.
+// play.cuh — the persistent one-game-per-lane Farkle state machine + the dense finish pass.
 //
 // Replaces the interpreter loops of the reference:
 //   FarklePlayer.take_turn / _score_roll / _apply_hot_dice / _should_continue
@@ -9,19 +9,25 @@
 //   OutcomeCounter.record_row + winner metric sums
 //                                         src/farkle/simulation/run_tournament.py:177-195,375-391
 //
-// Execution model
-//   * one game per lane; the loop body is ONE ROLL, so turn / seat / round /
-//     final-round changes are state transitions inside a warp-uniform loop;
-//   * the active seat lives in registers, parked seats in a per-warp shared
-//     memory store laid out [word][33] (stride 33 => the owner lane's column
-//     access and the cooperative row access of the epilogue are both
-//     bank-conflict free);
-//   * persistent CTAs (one per SM): a lane whose game ended takes the next game
-//     ordinal from a global counter (lane refill), so the 100x spread of game
-//     lengths does not idle the warp;
-//   * game end is handled by the whole warp for one lane at a time: lane s ranks
-//     seat s, lane w writes word w of the compact row (one coalesced store),
-//     lanes 0..22 issue the winner's tally REDs in a single instruction.
+// Data layout in HBM (per (game, seat), written by the seed kernels)
+//   SeatMut  48 B  PCG state (16 B) | saved half, score, highest|flags, farkles|rolls |
+//                  turns|hot, sf uses|dice, so uses|dice, pad
+//   SeatImm  32 B  PCG increment (16 B) | score_threshold, dice_threshold|flags,
+//                  strategy table index, pad
+//   game header 4 B  n_rounds | flags << 16, written when the game ends
+// The active seat lives in registers; a turn switch is three 16-byte stores of the
+// outgoing SeatMut and five 16-byte loads of the incoming seat.  The records of all
+// games in flight (148 SMs x 1,024 lanes x k seats x 80 B) stay L2-resident, so the
+// traffic is L2 traffic; shared memory holds only the lookup tables, which leaves the
+// SM at full occupancy for every k.
+//
+// play_kernel   one game per lane, loop body = ONE ROLL, straight-line; persistent CTAs
+//               (one per SM); a lane whose game ended takes the next ordinal from a
+//               global counter (lane refill), so the 100x spread of game lengths does
+//               not idle the warp.  It only plays: at game end it writes the header.
+// finish_kernel one thread per finished game, dense and lane-parallel: ranks the seats,
+//               emits the compact row (every byte of a row is written by one thread, L2
+//               merges the sectors), and adds the tallies with RED.64.
 #pragma once
 #include <cstdint>
 
@@ -31,259 +37,88 @@
 namespace fb {
 
 constexpr int ROLL_LIMIT = 1000;  // src/farkle/game/engine.py:36
-
-// parked seat record, 32-bit words
-enum SeatWord {
-    W_LO0 = 0, W_LO1, W_HI0, W_HI1,  // PCG state (lo, hi)
-    W_ILO0, W_ILO1, W_IHI0, W_IHI1,  // PCG increment
-    W_SAVED,                          // buffered high half of the last 64-bit draw
-    W_SCORE,
-    W_HIGH,   // highest_turn | has32 << 30 | has_scored << 31
-    W_FR,     // n_farkles | n_rolls << 16
-    W_TH,     // n_turns | n_hot_dice << 16
-    W_SF,     // smart_five_uses | n_smart_five_dice << 16
-    W_SO,     // smart_one_uses | n_smart_one_dice << 16
-    W_P0,     // score_threshold
-    W_P1,     // (u16)dice_threshold | flags << 16
-    SEAT_WORDS
-};
-constexpr int STORE_STRIDE = 33;
 constexpr uint32_t HIGH_MASK = 0x3fffffffu;
+constexpr uint32_t HW_HAS32 = 1u << 30;
+constexpr uint32_t HW_SCORED = 1u << 31;
+constexpr uint32_t FULL = 0xffffffffu;
+
+struct __align__(16) SeatMut {
+    uint32_t lo0, lo1, hi0, hi1;    // PCG state
+    uint32_t saved, score, hw, fr;  // buffered half | score | highest|has32<<30|has_scored<<31 | farkles|rolls<<16
+    uint32_t th, sf, so, pad;       // turns|hot<<16 | sf uses|dice<<16 | so uses|dice<<16
+};
+struct __align__(16) SeatImm {
+    uint32_t ilo0, ilo1, ihi0, ihi1;  // PCG increment
+    uint32_t st, p1, strat, pad;      // score_threshold | (u16)dice_threshold|flags<<16 | table index
+};
+static_assert(sizeof(SeatMut) == 48 && sizeof(SeatImm) == 32, "seat record layout");
 
 struct PlayParams {
-    const uint32_t* seat_state;       // [n_games*k][8]: lo, hi, ilo, ihi as u32 pairs
-    const int32_t* seat_strat;        // [n_games*k] index into `strategies`
-    const fb_strategy_t* strategies;  // table
-    const int32_t* strategy_ids;      // id of table entry (ids_mode 1)
-    int ids_mode;                     // 0 id = index, 1 id = strategy_ids[index], 2 id = seat
-    const uint64_t* game_seed;        // [n_games] or nullptr
-    const int32_t* limits;            // [n_games][2] {target, max_rounds} or nullptr
+    SeatMut* mut;           // [n_games*k]
+    const SeatImm* imm;     // [n_games*k]
+    uint32_t* header;       // [n_games]
+    const int32_t* limits;  // [n_games][2] {target, max_rounds} or nullptr
     int32_t target_score, max_rounds;
     uint32_t n_games;
     int k;
-    uint32_t games_per_slot;  // 0 = one tally slot
-    int n_tally_ids;
-    unsigned long long* tallies;  // [slots][ids][26] or nullptr
-    unsigned long long* totals;   // [FB_TOTALS_WIDTH] or nullptr
-    uint32_t* rows;               // or nullptr
-    int row_words;
-    uint8_t* outcome;  // [n_games] or nullptr
+    unsigned long long* totals;  // [FB_TOTALS_WIDTH] or nullptr (dice / rng words only)
     unsigned int* counter;
 };
 
 enum LaneStatus { ST_NEED = 0, ST_LOAD = 1, ST_PLAY = 2, ST_DEAD = 3 };
 
-constexpr uint32_t FULL = 0xffffffffu;
-
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const ScoreLut* __restrict__ lut_g) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ unsigned long long s_tot[FB_TOTALS_WIDTH];
+    __shared__ unsigned long long s_tot[2];
     ScoreLut* lut = reinterpret_cast<ScoreLut*>(smem_raw);
-    uint32_t* store = reinterpret_cast<uint32_t*>(smem_raw + ((LUT_BYTES + 15) & ~15));
-
     for (int i = threadIdx.x; i < LUT_BYTES / 4; i += blockDim.x)
         reinterpret_cast<uint32_t*>(lut)[i] = reinterpret_cast<const uint32_t*>(lut_g)[i];
-    if (threadIdx.x < FB_TOTALS_WIDTH) s_tot[threadIdx.x] = 0ull;
+    if (threadIdx.x < 2) s_tot[threadIdx.x] = 0ull;
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
     const int k = P.k;
-    const int seat_words = k * SEAT_WORDS;
-    uint32_t* ws = store + (size_t)warp * seat_words * STORE_STRIDE;
     const uint32_t lt_mask = (1u << lane) - 1u;
-
-#define SEATW(seat_, w_) ws[((seat_) * SEAT_WORDS + (w_)) * STORE_STRIDE + lane]
 
     // ---- per-lane game state ------------------------------------------------
     int status = ST_NEED;
-    bool have_result = false, newgame = false;
     uint32_t g = 0, err = 0;
     int seat = 0, round = 0, trigger = -1, stb = 0, target = 0, max_rounds = 0;
-    // active seat
+    // active seat (SeatMut / SeatImm in registers)
     Pcg rng{0, 0, 0, 0};
-    uint32_t saved = 0;
-    bool has32 = false, has_scored = false;
-    int score = 0, highest = 0, st = 0;
+    uint32_t saved = 0, hw = 0;
+    int score = 0, st = 0;
     uint32_t c_fr = 0, c_th = 0, c_sf = 0, c_so = 0, p1 = 0, dbase = 0;
     // active turn
     int ts = 0, dice = 6, rolls_turn = 0;
-    // work/total accumulators (reduced once at kernel end)
-    uint32_t a_done = 0, a_safe = 0, a_err = 0, a_swins = 0, a_dice = 0, a_words = 0;
-    unsigned long long a_rolls = 0, a_turns = 0;
+    uint32_t a_dice = 0, a_words = 0;
 
     for (;;) {
-        // ================= R: game end (cooperative) + lane refill =============
+        // ================= R: lane refill =====================================
         const uint32_t need = __ballot_sync(FULL, status == ST_NEED);
         if (need) {
-            __syncwarp();  // parked seat records of finished lanes are visible to the warp
-            uint32_t fin = __ballot_sync(FULL, status == ST_NEED && have_result);
-            while (fin) {
-                const int f = __ffs(fin) - 1;
-                fin &= fin - 1;
-                const uint32_t gf = __shfl_sync(FULL, g, f);
-                const int roundf = __shfl_sync(FULL, round, f);
-                const int trigf = __shfl_sync(FULL, trigger, f);
-                const uint32_t errf = __shfl_sync(FULL, err, f);
-                const bool safety = trigf < 0;
-                const uint32_t* col = ws + f;  // column of lane f
-                // winner = highest score, ties to the lower seat (stable sort, engine.py:483)
-                int sc = 0;
-                int sid = 0;
-                if (lane < k) {
-                    sc = (int)col[(lane * SEAT_WORDS + W_SCORE) * STORE_STRIDE];
-                    const uint32_t idx = P.seat_strat ? (uint32_t)P.seat_strat[(size_t)gf * k + lane]
-                                                      : gf * (uint32_t)k + lane;
-                    sid = P.ids_mode == 0 ? (int)idx : (P.ids_mode == 1 ? P.strategy_ids[idx] : lane);
-                }
-                const uint32_t key = lane < k ? (((uint32_t)sc << 4) | (uint32_t)(15 - lane)) : 0u;
-                const uint32_t best = __reduce_max_sync(FULL, key);
-                const int winner = safety ? 0xFF : 15 - (int)(best & 15u);
-                uint32_t i16 = 0;
-                if (lane < k) {
-                    const uint32_t fr = col[(lane * SEAT_WORDS + W_FR) * STORE_STRIDE];
-                    const uint32_t th = col[(lane * SEAT_WORDS + W_TH) * STORE_STRIDE];
-                    const uint32_t sfw = col[(lane * SEAT_WORDS + W_SF) * STORE_STRIDE];
-                    const uint32_t sow = col[(lane * SEAT_WORDS + W_SO) * STORE_STRIDE];
-                    const uint32_t hi = col[(lane * SEAT_WORDS + W_HIGH) * STORE_STRIDE] & HIGH_MASK;
-                    a_rolls += fr >> 16;
-                    a_turns += th & 0xffffu;
-                    i16 = ((fr >> 16) > 32767u) | (hi > 32767u) | ((sfw >> 16) > 32767u) |
-                          ((sow >> 16) > 32767u) | ((th & 0xffffu) > 32767u) | ((th >> 16) > 32767u);
-                }
-                const bool any16 = __any_sync(FULL, i16 != 0);
-                const uint32_t flags = (safety ? FB_ROW_SAFETY_LIMIT : 0u) | errf |
-                                       (any16 ? FB_ROW_I16_OVERFLOW : 0u);
-                if (lane == 0) {
-                    a_done += 1;
-                    a_safe += safety ? 1u : 0u;
-                    a_err += (flags & (FB_ROW_ROLL_LIMIT | FB_ROW_I16_OVERFLOW)) ? 1u : 0u;
-                    if (P.outcome)
-                        P.outcome[gf] = (uint8_t)((safety ? 0 : winner + 1) |
-                                                  ((flags & ~FB_ROW_SAFETY_LIMIT) ? 0x80 : 0));
-                }
-                if (lane == winner) a_swins += 1;
-
-                // ---- compact row: lane w writes word w (coalesced) ----
-                if (P.rows) {
-                    uint32_t* row = P.rows + (size_t)gf * P.row_words;
-                    for (int base = 0; base < P.row_words; base += 32) {
-                        const int w = base + lane;
-                        const int t = w - 4;
-                        const int s = t >= 0 ? t / 7 : 0;
-                        const int j = t - s * 7;
-                        const int sidv = __shfl_sync(FULL, sid, s & 31);
-                        uint32_t val = 0;
-                        if (w < 4) {
-                            if (w < 2) {
-                                const uint64_t gs = P.game_seed ? P.game_seed[gf] : 0ull;
-                                val = w == 0 ? (uint32_t)gs : (uint32_t)(gs >> 32);
-                            } else if (w == 2) {
-                                val = gf;
-                            } else {
-                                val = (uint32_t)roundf | ((uint32_t)winner << 16) | (flags << 24);
-                            }
-                        } else if (s < k) {
-                            const uint32_t* sp = col + (s * SEAT_WORDS) * STORE_STRIDE;
-                            switch (j) {
-                                case 0: val = sp[W_SCORE * STORE_STRIDE]; break;
-                                case 1: val = (uint32_t)sidv; break;
-                                case 2: val = sp[W_HIGH * STORE_STRIDE] & HIGH_MASK; break;
-                                case 3: val = sp[W_FR * STORE_STRIDE]; break;
-                                case 4: val = sp[W_TH * STORE_STRIDE]; break;
-                                case 5: val = sp[W_SF * STORE_STRIDE]; break;
-                                default: val = sp[W_SO * STORE_STRIDE]; break;
-                            }
-                        }
-                        if (w < P.row_words) row[w] = val;
-                    }
-                }
-                // ---- tallies: REDs spread over the lanes ----
-                if (P.tallies) {
-                    const uint32_t slot = P.games_per_slot ? gf / P.games_per_slot : 0u;
-                    unsigned long long* T =
-                        P.tallies + (size_t)slot * (size_t)P.n_tally_ids * FB_TALLY_WIDTH;
-                    if (lane < k) {
-                        atomicAdd(&T[(size_t)sid * FB_TALLY_WIDTH + 1], 1ull);
-                        atomicAdd(&T[(size_t)sid * FB_TALLY_WIDTH + (safety ? 3 : 2)], 1ull);
-                    }
-                    if (!safety) {
-                        const int wsid = __shfl_sync(FULL, sid, winner);
-                        const uint32_t* sp = col + (winner * SEAT_WORDS) * STORE_STRIDE;
-                        const int j = lane < FB_N_METRICS ? lane : lane - FB_N_METRICS;
-                        unsigned long long v = 0;
-                        switch (j) {  // METRIC_LABELS order, run_tournament.py:109-121
-                            case 0: v = sp[W_SCORE * STORE_STRIDE]; break;
-                            case 1: v = (unsigned)roundf; break;
-                            case 2: v = sp[W_FR * STORE_STRIDE] & 0xffffu; break;
-                            case 3: v = sp[W_FR * STORE_STRIDE] >> 16; break;
-                            case 4: v = sp[W_HIGH * STORE_STRIDE] & HIGH_MASK; break;
-                            case 5: v = sp[W_SF * STORE_STRIDE] & 0xffffu; break;
-                            case 6: v = sp[W_SF * STORE_STRIDE] >> 16; break;
-                            case 7: v = sp[W_SO * STORE_STRIDE] & 0xffffu; break;
-                            case 8: v = sp[W_SO * STORE_STRIDE] >> 16; break;
-                            case 9: v = sp[W_TH * STORE_STRIDE] >> 16; break;
-                            default: v = 0; break;  // winner_hit_max_rounds: False when completed
-                        }
-                        unsigned long long* Tw = T + (size_t)wsid * FB_TALLY_WIDTH;
-                        if (lane < FB_N_METRICS) atomicAdd(&Tw[4 + j], v);
-                        else if (lane < 2 * FB_N_METRICS) atomicAdd(&Tw[4 + FB_N_METRICS + j], v * v);
-                        else if (lane == 2 * FB_N_METRICS) atomicAdd(&Tw[0], 1ull);
-                    }
-                }
-            }
-            // ---- refill: contiguous ordinals for the lanes that need a game ----
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(P.counter, (unsigned)__popc(need));
             base = __shfl_sync(FULL, base, 0);
             if (status == ST_NEED) {
-                have_result = false;
                 const uint32_t ng = base + (uint32_t)__popc(need & lt_mask);
                 if (ng < P.n_games) {
                     g = ng;
-                    status = ST_LOAD;
-                    newgame = true;
+                    seat = 0;
+                    round = 0;
+                    trigger = -1;
+                    err = 0;
+                    target = P.limits ? P.limits[2 * (size_t)g] : P.target_score;
+                    max_rounds = P.limits ? P.limits[2 * (size_t)g + 1] : P.max_rounds;
+                    stb = target;
+                    if (max_rounds <= 0) {  // `while rounds < max_rounds` never runs (engine.py:455)
+                        P.header[g] = (uint32_t)FB_ROW_SAFETY_LIMIT << 16;
+                    } else {
+                        status = ST_LOAD;
+                    }
                 } else {
                     status = ST_DEAD;
-                }
-            }
-            uint32_t fresh = __ballot_sync(FULL, newgame);
-            while (fresh) {
-                const int f = __ffs(fresh) - 1;
-                fresh &= fresh - 1;
-                const uint32_t gf = __shfl_sync(FULL, g, f);
-                for (int base_w = 0; base_w < seat_words; base_w += 32) {
-                    const int w = base_w + lane;
-                    if (w < seat_words) {
-                        const int s = w / SEAT_WORDS;
-                        const int fld = w - s * SEAT_WORDS;
-                        uint32_t val = 0;
-                        if (fld < 8) {
-                            val = P.seat_state[((size_t)gf * k + s) * 8 + fld];
-                        } else if (fld >= W_P0) {
-                            const uint32_t idx = P.seat_strat ? (uint32_t)P.seat_strat[(size_t)gf * k + s]
-                                                              : gf * (uint32_t)k + s;
-                            const uint2 sv = reinterpret_cast<const uint2*>(P.strategies)[idx];
-                            val = fld == W_P0 ? sv.x : sv.y;
-                        }
-                        ws[w * STORE_STRIDE + f] = val;
-                    }
-                }
-            }
-            __syncwarp();
-            if (newgame) {
-                newgame = false;
-                seat = 0;
-                round = 0;
-                trigger = -1;
-                err = 0;
-                target = P.limits ? P.limits[2 * (size_t)g] : P.target_score;
-                max_rounds = P.limits ? P.limits[2 * (size_t)g + 1] : P.max_rounds;
-                stb = target;
-                if (max_rounds <= 0) {  // while rounds < max_rounds never runs (engine.py:455)
-                    status = ST_NEED;
-                    have_result = true;
                 }
             }
         }
@@ -292,22 +127,25 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
         // ================= L: seat the next player, start the turn ==============
         if (status == ST_LOAD) {
             if (trigger < 0 && seat == 0) round++;
-            rng.lo = (uint64_t)SEATW(seat, W_LO0) | ((uint64_t)SEATW(seat, W_LO1) << 32);
-            rng.hi = (uint64_t)SEATW(seat, W_HI0) | ((uint64_t)SEATW(seat, W_HI1) << 32);
-            rng.ilo = (uint64_t)SEATW(seat, W_ILO0) | ((uint64_t)SEATW(seat, W_ILO1) << 32);
-            rng.ihi = (uint64_t)SEATW(seat, W_IHI0) | ((uint64_t)SEATW(seat, W_IHI1) << 32);
-            saved = SEATW(seat, W_SAVED);
-            score = (int)SEATW(seat, W_SCORE);
-            const uint32_t hw = SEATW(seat, W_HIGH);
-            highest = (int)(hw & HIGH_MASK);
-            has32 = (hw >> 30) & 1u;
-            has_scored = hw >> 31;
-            c_fr = SEATW(seat, W_FR);
-            c_th = SEATW(seat, W_TH) + 1u;  // n_turns += 1 (engine.py:237)
-            c_sf = SEATW(seat, W_SF);
-            c_so = SEATW(seat, W_SO);
-            st = (int)SEATW(seat, W_P0);
-            p1 = SEATW(seat, W_P1);
+            const size_t rec = (size_t)g * (size_t)k + (size_t)seat;
+            const uint4* mp = reinterpret_cast<const uint4*>(P.mut + rec);
+            const uint4* ip = reinterpret_cast<const uint4*>(P.imm + rec);
+            const uint4 m0 = __ldcg(mp), m1 = __ldcg(mp + 1), m2 = __ldcg(mp + 2);
+            const uint4 i0 = __ldcg(ip);
+            const uint2 i1 = __ldcg(reinterpret_cast<const uint2*>(ip + 1));
+            rng.lo = (uint64_t)m0.x | ((uint64_t)m0.y << 32);
+            rng.hi = (uint64_t)m0.z | ((uint64_t)m0.w << 32);
+            rng.ilo = (uint64_t)i0.x | ((uint64_t)i0.y << 32);
+            rng.ihi = (uint64_t)i0.z | ((uint64_t)i0.w << 32);
+            saved = m1.x;
+            score = (int)m1.y;
+            hw = m1.z;
+            c_fr = m1.w;
+            c_th = m2.x + 1u;  // n_turns += 1 (engine.py:237)
+            c_sf = m2.y;
+            c_so = m2.z;
+            st = (int)i1.x;
+            p1 = i1.y;
             dbase = disc_base(p1);
             dice = 6;
             ts = 0;
@@ -322,7 +160,7 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
             // Halves H0..H6 = [buffered half, lo/hi of up to three fresh 64-bit outputs];
             // die i reads H[i + p].  All three outputs are always computed; the state only
             // advances past the nw words this roll really consumes.
-            const uint32_t p = has32 ? 0u : 1u;
+            const uint32_t p = (hw & HW_HAS32) ? 0u : 1u;
             const int nw = (n + (int)p) >> 1;
             uint64_t shi = rng.hi, slo = rng.lo;
             const uint64_t o1 = pcg_output(shi, slo);
@@ -375,7 +213,7 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
             if (minlo < 4u) {
                 // A draw with leftover < 4 somewhere in the window (4 in 2^32 per die; unused
                 // slots can only add false alarms): replay this roll draw by draw.
-                PcgStream s{rng, saved, has32};
+                PcgStream s{rng, saved, (hw & HW_HAS32) != 0u};
                 hist = 0;
                 words = 0;
                 for (int i = 0; i < n; i++) hist += 1u << (3u * s.die0(words));
@@ -386,7 +224,7 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
             }
             rng.hi = shi;
             rng.lo = slo;
-            has32 = nhas;
+            hw = nhas ? (hw | HW_HAS32) : (hw & ~HW_HAS32);
             saved = nsaved;
             a_dice += (uint32_t)n;
             a_words += words;
@@ -415,34 +253,29 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
             const int rt = score + ts2;
             const bool behind = fin && rt <= stb;
             const bool stop_ahead = fin && rt > stb && !strat_flag(p1, FB_SF_RUN_UP_SCORE);
-            const bool gate = !has_scored && ts2 < 500;
+            const bool gate = !(hw & HW_SCORED) && ts2 < 500;
             const bool keep = !stop_ahead && (gate || behind || decide_continue(ts2, ndice, st, p1));
             bool turn_over = farkle || (!hot && !keep);
             ts = farkle ? 0 : ts2;
             dice = ndice;
             if (!turn_over && rolls_turn >= ROLL_LIMIT) {  // engine.py:242-243 raises
-                err |= FB_ROW_ROLL_LIMIT;
+                err = FB_ROW_ROLL_LIMIT;
                 turn_over = true;
             }
 
             // ================= T: bank, park the seat, pick the next one ========
             if (turn_over) {
-                if (!has_scored && ts >= 500) has_scored = true;
-                if (has_scored) {
+                if (ts >= 500) hw |= HW_SCORED;  // entry turn (engine.py:266-267)
+                if (hw & HW_SCORED) {
                     score += ts;
-                    highest = max(highest, ts);
+                    const uint32_t hi_turn = max(hw & HIGH_MASK, (uint32_t)ts);
+                    hw = (hw & ~HIGH_MASK) | hi_turn;
                 }
-                SEATW(seat, W_LO0) = (uint32_t)rng.lo;
-                SEATW(seat, W_LO1) = (uint32_t)(rng.lo >> 32);
-                SEATW(seat, W_HI0) = (uint32_t)rng.hi;
-                SEATW(seat, W_HI1) = (uint32_t)(rng.hi >> 32);
-                SEATW(seat, W_SAVED) = saved;
-                SEATW(seat, W_SCORE) = (uint32_t)score;
-                SEATW(seat, W_HIGH) = (uint32_t)highest | ((uint32_t)has32 << 30) | ((uint32_t)has_scored << 31);
-                SEATW(seat, W_FR) = c_fr;
-                SEATW(seat, W_TH) = c_th;
-                SEATW(seat, W_SF) = c_sf;
-                SEATW(seat, W_SO) = c_so;
+                uint4* mp = reinterpret_cast<uint4*>(P.mut + ((size_t)g * (size_t)k + (size_t)seat));
+                __stcg(mp, make_uint4((uint32_t)rng.lo, (uint32_t)(rng.lo >> 32), (uint32_t)rng.hi,
+                                      (uint32_t)(rng.hi >> 32)));
+                __stcg(mp + 1, make_uint4(saved, (uint32_t)score, hw, c_fr));
+                __stcg(mp + 2, make_uint4(c_th, c_sf, c_so, 0u));
                 bool over;
                 if (trigger < 0) {
                     if (score >= target) {  // first trigger starts the final round (engine.py:466-471)
@@ -466,29 +299,161 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
                 }
                 if (err) over = true;
                 if (over) {
+                    P.header[g] = (uint32_t)round |
+                                  (((trigger < 0 ? FB_ROW_SAFETY_LIMIT : 0u) | err) << 16);
                     status = ST_NEED;
-                    have_result = true;
                 } else {
                     status = ST_LOAD;
                 }
             }
         }
     }
-#undef SEATW
 
-    // ---- totals: warp shuffle -> shared memory -> one global RED per CTA ------
-    unsigned long long v[8] = {a_done, (unsigned long long)a_done - a_safe, a_safe, a_rolls,
-                               a_dice,  a_words, a_turns, a_err};
+    // ---- work counters: warp shuffle -> shared memory -> one global RED per CTA ----
+    unsigned long long v[2] = {a_dice, a_words};
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < 2; i++) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(FULL, v[i], o);
         if (lane == 0 && v[i]) atomicAdd(&s_tot[i], v[i]);
     }
-    if (lane < k && a_swins) atomicAdd(&s_tot[8 + lane], (unsigned long long)a_swins);
     __syncthreads();
-    if (P.totals && threadIdx.x < FB_TOTALS_WIDTH && s_tot[threadIdx.x])
-        atomicAdd(&P.totals[threadIdx.x], s_tot[threadIdx.x]);
+    if (P.totals && threadIdx.x < 2 && s_tot[threadIdx.x])
+        atomicAdd(&P.totals[4 + threadIdx.x], s_tot[threadIdx.x]);
+}
+
+// ---------------------------------------------------------------------------
+// finish pass
+// ---------------------------------------------------------------------------
+struct FinishParams {
+    const SeatMut* mut;
+    const SeatImm* imm;
+    const uint32_t* header;
+    const int32_t* strategy_ids;  // id of table entry (ids_mode 1)
+    int ids_mode;                 // 0 id = table index, 1 id = strategy_ids[index], 2 id = seat
+    const uint64_t* game_seed;    // [n_games] or nullptr
+    uint32_t n_games;
+    int k;
+    uint32_t games_per_slot;  // 0 = one tally slot
+    int n_tally_ids;
+    unsigned long long* tallies;  // [slots][ids][26] or nullptr
+    unsigned long long* totals;   // [FB_TOTALS_WIDTH] or nullptr
+    uint32_t* rows;               // or nullptr
+    int row_words;
+    uint8_t* outcome;  // [n_games] or nullptr
+};
+
+__global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
+    __shared__ unsigned long long s_tot[FB_TOTALS_WIDTH];
+    if (threadIdx.x < FB_TOTALS_WIDTH) s_tot[threadIdx.x] = 0ull;
+    __syncthreads();
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = F.k;
+    unsigned long long t_rolls = 0, t_turns = 0;
+    uint32_t t_done = 0, t_safe = 0, t_err = 0;
+    int winner = -1;
+    if (g < F.n_games) {
+        const uint32_t hdr = F.header[g];
+        const uint32_t rounds = hdr & 0xffffu;
+        uint32_t flags = hdr >> 16;
+        const bool safety = flags & FB_ROW_SAFETY_LIMIT;
+        const SeatMut* mut = F.mut + (size_t)g * k;
+        const SeatImm* imm = F.imm + (size_t)g * k;
+        // pass 1: winner = highest score, ties to the lower seat (stable sort, engine.py:483)
+        int best = -1;
+        for (int s = 0; s < k; s++) {
+            const uint4 a = __ldcg(reinterpret_cast<const uint4*>(mut + s) + 1);
+            const uint4 b = __ldcg(reinterpret_cast<const uint4*>(mut + s) + 2);
+            const int sc = (int)a.y;
+            if (sc > best) {
+                best = sc;
+                winner = s;
+            }
+            t_rolls += a.w >> 16;
+            t_turns += b.x & 0xffffu;
+            if ((a.w >> 16) > 32767u || (a.z & HIGH_MASK) > 32767u || (b.y >> 16) > 32767u ||
+                (b.z >> 16) > 32767u || (b.x & 0xffffu) > 32767u || (b.x >> 16) > 32767u)
+                flags |= FB_ROW_I16_OVERFLOW;
+        }
+        if (safety) winner = -1;
+        t_done = 1;
+        t_safe = safety ? 1u : 0u;
+        t_err = (flags & (FB_ROW_ROLL_LIMIT | FB_ROW_I16_OVERFLOW)) ? 1u : 0u;
+        if (F.outcome)
+            F.outcome[g] = (uint8_t)((safety ? 0 : winner + 1) | ((flags & ~FB_ROW_SAFETY_LIMIT) ? 0x80 : 0));
+        unsigned long long* T = nullptr;
+        if (F.tallies) {
+            const uint32_t slot = F.games_per_slot ? g / F.games_per_slot : 0u;
+            T = F.tallies + (size_t)slot * (size_t)F.n_tally_ids * FB_TALLY_WIDTH;
+        }
+        uint32_t* row = F.rows ? F.rows + (size_t)g * F.row_words : nullptr;
+        if (row) {
+            const uint64_t gs = F.game_seed ? F.game_seed[g] : 0ull;
+            reinterpret_cast<uint4*>(row)[0] =
+                make_uint4((uint32_t)gs, (uint32_t)(gs >> 32), g,
+                           rounds | ((uint32_t)(safety ? 0xFF : winner) << 16) | (flags << 24));
+        }
+        // pass 2: rows, exposures, winner metrics
+        for (int s = 0; s < k; s++) {
+            const uint4 a = __ldcg(reinterpret_cast<const uint4*>(mut + s) + 1);
+            const uint4 b = __ldcg(reinterpret_cast<const uint4*>(mut + s) + 2);
+            const uint32_t idx = __ldcg(&imm[s].strat);
+            const int sid = F.ids_mode == 0 ? (int)idx : (F.ids_mode == 1 ? F.strategy_ids[idx] : s);
+            if (row) {
+                uint32_t* w = row + 4 + s * 7;
+                w[0] = a.y;
+                w[1] = (uint32_t)sid;
+                w[2] = a.z & HIGH_MASK;
+                w[3] = a.w;
+                w[4] = b.x;
+                w[5] = b.y;
+                w[6] = b.z;
+            }
+            if (T) {
+                unsigned long long* Ts = T + (size_t)sid * FB_TALLY_WIDTH;
+                atomicAdd(&Ts[1], 1ull);
+                atomicAdd(&Ts[safety ? 3 : 2], 1ull);
+                if (s == winner) {
+                    // METRIC_LABELS order, run_tournament.py:109-121; winner_hit_max_rounds is
+                    // False for every completed game, so its sums stay 0.
+                    const unsigned long long m[10] = {a.y, rounds, a.w & 0xffffu, a.w >> 16,
+                                                      a.z & HIGH_MASK, b.y & 0xffffu, b.y >> 16,
+                                                      b.z & 0xffffu, b.z >> 16, b.x >> 16};
+                    atomicAdd(&Ts[0], 1ull);
+#pragma unroll
+                    for (int j = 0; j < 10; j++) {
+                        atomicAdd(&Ts[4 + j], m[j]);
+                        atomicAdd(&Ts[4 + FB_N_METRICS + j], m[j] * m[j]);
+                    }
+                }
+            }
+        }
+        if (row) {
+            for (int w = 4 + 7 * k; w < F.row_words; w++) row[w] = 0u;  // padding
+        }
+    }
+    // ---- totals: warp shuffle -> shared memory -> one global RED per CTA ----
+    if (F.totals) {
+        const int lane = threadIdx.x & 31;
+        unsigned long long v[6] = {t_done, (unsigned long long)t_done - t_safe, t_safe, t_rolls, t_turns, t_err};
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(FULL, v[i], o);
+        }
+        if (lane == 0) {
+            if (v[0]) atomicAdd(&s_tot[0], v[0]);
+            if (v[1]) atomicAdd(&s_tot[1], v[1]);
+            if (v[2]) atomicAdd(&s_tot[2], v[2]);
+            if (v[3]) atomicAdd(&s_tot[3], v[3]);
+            if (v[4]) atomicAdd(&s_tot[6], v[4]);
+            if (v[5]) atomicAdd(&s_tot[7], v[5]);
+        }
+        if (winner >= 0) atomicAdd(&s_tot[8 + winner], 1ull);
+        __syncthreads();
+        if (threadIdx.x < FB_TOTALS_WIDTH && s_tot[threadIdx.x])
+            atomicAdd(&F.totals[threadIdx.x], s_tot[threadIdx.x]);
+    }
 }
 
 }  // namespace fb
