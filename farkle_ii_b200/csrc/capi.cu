@@ -4,7 +4,7 @@
 //   seed_tournament_kernel  coordinate_rng for every (game, seat) of a run of shuffles
 //   seed_h2h_kernel         same for H2H attempts
 //   seed_explicit_kernel    same for explicit coordinates
-//   permute_kernel          Generator.permutation per shuffle
+//   permute_warp_kernel     Generator.permutation, one warp per shuffle, jump-ahead draws
 //   play_kernel             (play.cuh) the game state machine over L2-resident seat records
 //   finish_kernel           (play.cuh) dense pass: winner, compact rows, tallies, totals
 //   h2h_resolve_kernel      early-stop prefix rule over attempt outcomes
@@ -27,6 +27,12 @@
 
 using namespace fb;
 
+// LCG jump-ahead constants for permute_warp_kernel: entry j holds A^j and
+// 1 + A + ... + A^(j-1) (mod 2^128) for the cheap PCG64DXSM multiplier A.
+struct JumpTable {
+    uint64_t a_hi[33], a_lo[33], g_hi[33], g_lo[33];
+};
+
 // ---------------------------------------------------------------------------
 // host state
 // ---------------------------------------------------------------------------
@@ -37,6 +43,7 @@ struct Ctx {
     int sm_count = 0, clock_khz = 0, cc_major = 0, cc_minor = 0;
     int max_smem_optin = 0;
     ScoreLut* lut_dev = nullptr;
+    JumpTable* jump_dev = nullptr;
     // cached buffers of fb_run_tournament_host
     void* host_ws = nullptr;
     size_t host_ws_bytes = 0;
@@ -255,7 +262,82 @@ __global__ void pack_limits_kernel(const int32_t* tv, int32_t t0, const int32_t*
 }
 
 // Generator.permutation(n) per shuffle: Fisher-Yates from the top with masked
-// rejection on buffered 32-bit draws (run_tournament.py:312-318).
+// rejection on buffered 32-bit draws (run_tournament.py:312-318).  The swap chain is
+// sequential per shuffle but the draws are not: ONE WARP walks one shuffle.  Per batch,
+// lane j jumps the LCG ahead by j steps (S_j = A^j S + (A^j-1)/(A-1) inc, constants in
+// JumpTable) and emits the j-th 64-bit output, i.e. 64 buffered 32-bit draws per batch;
+// then every lane replays the same accept/reject walk over them (warp-uniform, broadcast
+// shared-memory reads) and swaps in the shuffle's uint16 array in shared memory.
+__device__ __forceinline__ void mul128(uint64_t ahi, uint64_t alo, uint64_t bhi, uint64_t blo, uint64_t& rhi,
+                                       uint64_t& rlo) {
+    rlo = alo * blo;
+    rhi = __umul64hi(alo, blo) + alo * bhi + ahi * blo;
+}
+
+constexpr int PERM_WARPS = 4;
+
+__global__ void __launch_bounds__(PERM_WARPS * 32) permute_warp_kernel(uint64_t root, int k, uint64_t shuffle0,
+                                                                      int n_shuffles, int n,
+                                                                      const JumpTable* __restrict__ jt,
+                                                                      int32_t* out) {
+    extern __shared__ __align__(16) uint8_t perm_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * PERM_WARPS + warp;  // shuffle handled by this warp
+    const size_t per_warp = (((size_t)n * 2 + 15) & ~(size_t)15) + 64 * 4;
+    uint16_t* a = reinterpret_cast<uint16_t*>(perm_smem + warp * per_warp);
+    uint32_t* ring = reinterpret_cast<uint32_t*>(perm_smem + warp * per_warp + (per_warp - 64 * 4));
+    if (j >= n_shuffles) return;
+    for (int i = lane; i < n; i += 32) a[i] = (uint16_t)i;
+    Coord c{FB_PURPOSE_SHUFFLE_PERMUTATION, root, (uint64_t)k, shuffle0 + (uint64_t)j, 0, 0, 0, 0, 0};
+    Pcg g;
+    pcg_seed_coord(g, c);  // every lane derives the same stream
+    const uint64_t ahi = jt->a_hi[lane], alo = jt->a_lo[lane], ghi = jt->g_hi[lane], glo = jt->g_lo[lane];
+    const uint64_t nahi = jt->a_hi[32], nalo = jt->a_lo[32], nghi = jt->g_hi[32], nglo = jt->g_lo[32];
+    int grp = 16;  // ring = 16 groups of four 32-bit draws
+    int i = n - 1;
+    uint32_t mask = 0xffffffffu >> __clz(i | 1);
+    __syncwarp();
+    while (i >= 1) {
+        if (grp == 16) {
+            // batch: lane's state S_lane, its output -> halves 2*lane, 2*lane+1; then S += 32 steps
+            uint64_t thi, tlo, uhi, ulo;
+            mul128(ahi, alo, g.hi, g.lo, thi, tlo);
+            mul128(ghi, glo, g.ihi, g.ilo, uhi, ulo);
+            uint64_t slo = tlo + ulo;
+            uint64_t shi = thi + uhi + (slo < tlo ? 1u : 0u);
+            const uint64_t o = pcg_output(shi, slo);
+            __syncwarp();
+            reinterpret_cast<uint2*>(ring)[lane] = make_uint2((uint32_t)o, (uint32_t)(o >> 32));
+            mul128(nahi, nalo, g.hi, g.lo, thi, tlo);
+            mul128(nghi, nglo, g.ihi, g.ilo, uhi, ulo);
+            g.lo = tlo + ulo;
+            g.hi = thi + uhi + (g.lo < tlo ? 1u : 0u);
+            grp = 0;
+            __syncwarp();
+        }
+        // Every lane performs the identical walk and the identical swaps (same values to the
+        // same addresses), so each lane's own program order keeps the array consistent.
+        // Branch free: a rejected draw swaps a[i] with itself.
+        const uint4 h = reinterpret_cast<const uint4*>(ring)[grp++];
+        const uint32_t hs[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const uint32_t v = hs[d] & mask;
+            const bool accept = v <= (uint32_t)i && i >= 1;
+            const int iv = accept ? (int)v : i;
+            const uint16_t x = a[i], y = a[iv];
+            a[i] = y;
+            a[iv] = x;
+            i -= accept ? 1 : 0;
+            mask = 0xffffffffu >> __clz(i | 1);
+        }
+    }
+    __syncwarp();
+    int32_t* dst = out + (size_t)j * n;
+    for (int t = lane; t < n; t += 32) dst[t] = (int32_t)a[t];
+}
+
+// Fallback for grids too large for shared memory: the array lives in global memory.
 __global__ void __launch_bounds__(128) permute_kernel(uint64_t root, int k, uint64_t shuffle0,
                                                       int n_shuffles, int n, int32_t* out) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -516,6 +598,19 @@ int fb_init(int device) {
     FB_CUDA(cudaMalloc(&g_ctx.lut_dev, sizeof(ScoreLut)));
     FB_CUDA(cudaMemcpy(g_ctx.lut_dev, host_lut, sizeof(ScoreLut), cudaMemcpyHostToDevice));
     delete host_lut;
+    {   // LCG jump-ahead constants for permute_warp_kernel: A^j and 1 + A + ... + A^(j-1) mod 2^128
+        JumpTable jt;
+        unsigned __int128 a = 1, gsum = 0;
+        for (int j = 0; j <= 32; j++) {
+            jt.a_hi[j] = (uint64_t)(a >> 64); jt.a_lo[j] = (uint64_t)a;
+            jt.g_hi[j] = (uint64_t)(gsum >> 64); jt.g_lo[j] = (uint64_t)gsum;
+            gsum += a;
+            a *= (unsigned __int128)PCG_CHEAP_MULT;
+        }
+        if (g_ctx.jump_dev) cudaFree(g_ctx.jump_dev);
+        FB_CUDA(cudaMalloc(&g_ctx.jump_dev, sizeof(JumpTable)));
+        FB_CUDA(cudaMemcpy(g_ctx.jump_dev, &jt, sizeof(JumpTable), cudaMemcpyHostToDevice));
+    }
     g_ctx.device = device;
     return FB_OK;
 }
@@ -590,6 +685,15 @@ int fb_permute_shuffles(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuf
     FB_REQUIRE_INIT();
     if (n_shuffles < 0 || n_strategies < 1) return fail(FB_ERR_BAD_ARG, "bad shuffle or strategy count");
     if (n_shuffles == 0) return FB_OK;
+    const size_t per_warp = (((size_t)n_strategies * 2 + 15) & ~(size_t)15) + 64 * 4;
+    const size_t smem = per_warp * PERM_WARPS;
+    if (n_strategies <= 65535 && smem <= (size_t)g_ctx.max_smem_optin - 1024) {
+        FB_CUDA(cudaFuncSetAttribute(permute_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        permute_warp_kernel<<<(n_shuffles + PERM_WARPS - 1) / PERM_WARPS, PERM_WARPS * 32, smem,
+                              (cudaStream_t)stream>>>(root_seed, k, shuffle0, n_shuffles, n_strategies,
+                                                      g_ctx.jump_dev, perm_out_dev);
+        return launch_check("permute_warp_kernel");
+    }
     permute_kernel<<<blocks_for((uint64_t)n_shuffles, 128), 128, 0, (cudaStream_t)stream>>>(
         root_seed, k, shuffle0, n_shuffles, n_strategies, perm_out_dev);
     return launch_check("permute_kernel");
@@ -611,7 +715,7 @@ int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuff
     if (n_shuffles == 0) return FB_OK;
     const uint32_t gps = (uint32_t)(n_strategies / k);
     const uint64_t n_games = (uint64_t)n_shuffles * gps;
-    if (n_games > 0xfffffff0ull) return fail(FB_ERR_BAD_ARG, "more than 2^32 games in one launch");
+    if (n_games * (uint64_t)k > 0xfffffff0ull) return fail(FB_ERR_BAD_ARG, "more than 2^32 seats in one launch");
     Workspace w;
     const size_t perm_bytes = align_up((size_t)n_shuffles * n_strategies * 4, 256);
     if (!carve(workspace_dev, workspace_bytes, k, n_games, w) || w.extra_bytes < perm_bytes)
@@ -665,7 +769,7 @@ int fb_play_h2h(uint64_t root_seed, int n_blocks, const uint64_t* pair_id_dev, c
     cudaStream_t stream = (cudaStream_t)stream_v;
     if (n_blocks < 0) return fail(FB_ERR_BAD_ARG, "negative block count");
     if (n_blocks == 0 || total_attempts == 0) return FB_OK;
-    if (total_attempts > 0xfffffff0ull) return fail(FB_ERR_BAD_ARG, "more than 2^32 attempts in one launch");
+    if (total_attempts * 2 > 0xfffffff0ull) return fail(FB_ERR_BAD_ARG, "more than 2^31 attempts in one launch");
     Workspace w;
     const size_t off_bytes = align_up((size_t)(n_blocks + 1) * 8, 256);
     if (!carve(workspace_dev, workspace_bytes, 2, total_attempts, w) || w.extra_bytes < off_bytes)
@@ -733,7 +837,7 @@ int fb_play_games(const uint64_t* coords_dev, uint64_t n_games, int k,
     cudaStream_t stream = (cudaStream_t)stream_v;
     if (k < 1 || k > FB_MAX_PLAYERS) return fail(FB_ERR_BAD_ARG, "k=%d outside [1,%d]", k, FB_MAX_PLAYERS);
     if (n_games == 0) return FB_OK;
-    if (n_games > 0xfffffff0ull) return fail(FB_ERR_BAD_ARG, "more than 2^32 games in one launch");
+    if (n_games * (uint64_t)k > 0xfffffff0ull) return fail(FB_ERR_BAD_ARG, "more than 2^32 seats in one launch");
     Workspace w;
     if (!carve(workspace_dev, workspace_bytes, k, n_games, w))
         return fail(FB_ERR_WORKSPACE, "workspace too small: need %zu bytes", ws_core_bytes(k, n_games));

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
         // ================= L: seat the next player, start the turn ==============
         if (status == ST_LOAD) {
             if (trigger < 0 && seat == 0) round++;
-            const size_t rec = (size_t)g * (size_t)k + (size_t)seat;
+            const uint32_t rec = g * (uint32_t)k + (uint32_t)seat;  // n_games * k < 2^32 (checked on the host)
             const uint4* mp = reinterpret_cast<const uint4*>(P.mut + rec);
             const uint4* ip = reinterpret_cast<const uint4*>(P.imm + rec);
             const uint4 m0 = __ldcg(mp), m1 = __ldcg(mp + 1), m2 = __ldcg(mp + 2);
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
                     const uint32_t hi_turn = max(hw & HIGH_MASK, (uint32_t)ts);
                     hw = (hw & ~HIGH_MASK) | hi_turn;
                 }
-                uint4* mp = reinterpret_cast<uint4*>(P.mut + ((size_t)g * (size_t)k + (size_t)seat));
+                uint4* mp = reinterpret_cast<uint4*>(P.mut + (g * (uint32_t)k + (uint32_t)seat));
                 __stcg(mp, make_uint4((uint32_t)rng.lo, (uint32_t)(rng.lo >> 32), (uint32_t)rng.hi,
                                       (uint32_t)(rng.hi >> 32)));
                 __stcg(mp + 1, make_uint4(saved, (uint32_t)score, hw, c_fr));
