@@ -1,0 +1,398 @@
+"""Game-level host surface: rows, ``_play_game`` and the ``simulate_many_games`` helpers.
+
+Mirror of the reference's ``farkle.simulation.simulation`` for the hot path:
+
+* ``PlayerRngCoordinates``               simulation.py:332-358
+* ``_play_game``                         simulation.py:576-655
+* ``simulate_many_games[_from_seeds]``   simulation.py:658-790
+* ``simulation_rows_to_table``           simulation.py:565-573 with the Arrow schema of
+                                         utils/schema_helpers.py:23-90
+
+The games themselves are played by the CUDA library (``fb_play_games`` /
+``fb_play_tournament``); this module only turns compact ``fb_row_*`` records into the
+reference's flat row mapping (same keys, same key order, same Python types, ``None`` where
+the reference writes nulls) or — for ingest-rate output — straight into an Arrow table.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Iterable, Mapping, Sequence
+
+import numpy as np
+
+from .layout import ROW_I16_OVERFLOW, ROW_ROLL_LIMIT, ROW_SAFETY_LIMIT, STRATEGY_DTYPE
+from .random import RNG_SCHEME_VERSION, RandomPurpose, coordinate_entropy, spawn_seeds
+from .strategies import ThresholdStrategy, pack_strategies, prepare_strategy_ids
+
+OUTCOME_SCHEMA_VERSION = 2      # utils/schema_helpers.py:17
+TOURNAMENT_METHOD_VERSION = 2   # utils/schema_helpers.py:18
+DEFAULT_TARGET_SCORE = 10_000
+DEFAULT_MAX_ROUNDS = 200
+
+# PlayerStats field order (game/engine.py:385-398) = order of the per-seat row keys
+SEAT_FIELDS = ("score", "farkles", "rolls", "n_turns", "highest_turn", "strategy", "rank",
+               "loss_margin", "smart_five_uses", "n_smart_five_dice", "smart_one_uses",
+               "n_smart_one_dice", "hot_dice", "hit_max_rounds")
+
+
+class RollLimitError(RuntimeError):
+    """A turn exceeded ROLL_LIMIT=1000 rolls (the reference raises at engine.py:242-243)."""
+
+
+@dataclass(frozen=True, slots=True)
+class PlayerRngCoordinates:
+    """Complete semantic coordinates of a table's seat streams (simulation.py:332-358)."""
+
+    purpose: RandomPurpose
+    root_seed: int
+    k: int
+    shuffle_index: int = 0
+    pair_id: int = 0
+    order: int = 0
+    game_index: int | None = None
+    attempt_index: int | None = None
+
+    def coords7(self) -> list[int]:
+        """``fb_play_games`` coordinate row {purpose, root, k, shuffle, pair, order, game}."""
+        e = coordinate_entropy(self.purpose, root_seed=self.root_seed, k=self.k,
+                               shuffle_index=self.shuffle_index, pair_id=self.pair_id,
+                               order=self.order, game_index=self.game_index,
+                               attempt_index=self.attempt_index)
+        v = [e[2 + 2 * i] | (e[3 + 2 * i] << 32) for i in range(6)]
+        return [int(self.purpose), *v]
+
+
+def _prepare_public_helper_strategies(strategies: Sequence[ThresholdStrategy]
+                                      ) -> list[ThresholdStrategy]:
+    """Copies with one unique canonical id per seat (simulation.py:361-409)."""
+    from dataclasses import replace
+
+    ids = prepare_strategy_ids(strategies)
+    return [replace(s, strategy_id=i) for s, i in zip(strategies, ids, strict=True)]
+
+
+# --------------------------------------------------------------------------- row expansion
+def check_row_flags(rows: np.ndarray) -> None:
+    """Surface the conditions under which the reference raises instead of returning a row."""
+    flags = rows["flags"]
+    if (flags & ROW_ROLL_LIMIT).any():
+        raise RollLimitError("Roll limit reached in a turn")  # engine.py:242-243
+    if (flags & ROW_I16_OVERFLOW).any():
+        raise OverflowError("a per-seat counter left the int16 range of the row schema "
+                            "(utils/schema_helpers.py:44-58); the reference's Arrow conversion raises")
+
+
+def derive_ranks(rows: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """``(rank[n, k] (1-based, 0 = null), order[n, k])`` — stable sort by score desc, seat asc
+    (game/engine.py:483), nulls for safety-limit rows."""
+    scores = rows["seats"]["score"].astype(np.int64)
+    n, k = scores.shape
+    order = np.argsort(-scores, axis=1, kind="stable")
+    rank = np.empty((n, k), dtype=np.int8)
+    np.put_along_axis(rank, order, np.arange(1, k + 1, dtype=np.int8)[None, :], axis=1)
+    safety = (rows["flags"] & ROW_SAFETY_LIMIT) != 0
+    rank[safety] = 0
+    return rank, order
+
+
+def expand_rows(rows: np.ndarray, provenance: Sequence[Mapping[str, Any]] | None = None,
+                *, root_seed: Sequence[int] | int = 0,
+                purpose_namespace: int = int(RandomPurpose.INDEXED_SEED)) -> list[dict[str, Any]]:
+    """Compact rows -> the reference's flat row mappings (simulation.py:612-654).
+
+    ``provenance[i]`` is applied exactly like ``flat.update(provenance)``; without it the
+    defaults of ``_play_game`` are used (``root_seed``/``game_seed`` = the seed argument).
+    """
+    check_row_flags(rows)
+    n = len(rows)
+    k = rows["seats"].shape[1] if n else 0
+    rank, order = derive_ranks(rows) if n else (None, None)
+    seeds = np.broadcast_to(np.asarray(root_seed, dtype=np.uint64), (n,))
+    out: list[dict[str, Any]] = []
+    for i in range(n):
+        r = rows[i]
+        safety = bool(r["flags"] & ROW_SAFETY_LIMIT)
+        seats = r["seats"]
+        scores = [int(x) for x in seats["score"]]
+        if safety:
+            winner, winner_strategy, seat_ranks = None, None, [None] * k
+            winning_score = margin = None
+        else:
+            w = int(r["winner_seat"])
+            winner = f"P{w + 1}"
+            winner_strategy = int(seats["strategy"][w])
+            seat_ranks = [f"P{int(s) + 1}" for s in order[i]]
+            winning_score = scores[w]
+            ordered = sorted(scores, reverse=True)
+            margin = ordered[0] - (ordered[1] if k > 1 else 0)
+        flat: dict[str, Any] = {
+            "termination_status": "safety_limit" if safety else "completed",
+            "hit_safety_limit": safety,
+            "outcome_schema_version": OUTCOME_SCHEMA_VERSION,
+            "winner_seat": winner,
+            "winner_strategy": winner_strategy,
+            "seat_ranks": seat_ranks,
+            "winning_score": winning_score,
+            "victory_margin": margin,
+            "n_rounds": int(r["n_rounds"]),
+            "root_seed": int(seeds[i]),
+            "k": k,
+            "shuffle_index": None,
+            "game_index": None,
+            "deterministic_batch_id": None,
+            "game_seed": int(seeds[i]),
+            "rng_scheme_version": RNG_SCHEME_VERSION,
+            "rng_purpose_namespace": purpose_namespace,
+        }
+        if provenance is not None:
+            flat.update(provenance[i])
+        for s in range(k):
+            seat = seats[s]
+            p = f"P{s + 1}_"
+            flat[p + "score"] = scores[s]
+            flat[p + "farkles"] = int(seat["farkles"])
+            flat[p + "rolls"] = int(seat["rolls"])
+            flat[p + "n_turns"] = int(seat["n_turns"])
+            flat[p + "highest_turn"] = int(seat["highest_turn"])
+            flat[p + "strategy"] = int(seat["strategy"])
+            flat[p + "rank"] = None if safety else int(rank[i, s])
+            flat[p + "loss_margin"] = None if safety else winning_score - scores[s]
+            flat[p + "smart_five_uses"] = int(seat["smart_five_uses"])
+            flat[p + "n_smart_five_dice"] = int(seat["n_smart_five_dice"])
+            flat[p + "smart_one_uses"] = int(seat["smart_one_uses"])
+            flat[p + "n_smart_one_dice"] = int(seat["n_smart_one_dice"])
+            flat[p + "hot_dice"] = int(seat["hot_dice"])
+            flat[p + "hit_max_rounds"] = safety
+        out.append(flat)
+    return out
+
+
+def raw_simulation_schema_for(n_players: int):
+    """Arrow schema of persisted rows (utils/schema_helpers.py:23-90), field for field."""
+    import pyarrow as pa
+
+    if n_players < 1:
+        raise ValueError("n_players must be positive")
+    str_list = pa.list_(pa.field("item", pa.string(), nullable=True))
+    base = [
+        pa.field("root_seed", pa.int64(), nullable=False),
+        pa.field("k", pa.int16(), nullable=False),
+        pa.field("shuffle_index", pa.int64(), nullable=False),
+        pa.field("game_index", pa.int32(), nullable=False),
+        pa.field("deterministic_batch_id", pa.int32(), nullable=False),
+        pa.field("shuffle_seed", pa.int64(), nullable=False),
+        pa.field("termination_status", pa.string(), nullable=False),
+        pa.field("hit_safety_limit", pa.bool_(), nullable=False),
+        pa.field("outcome_schema_version", pa.int16(), nullable=False),
+        pa.field("winner_seat", pa.string(), nullable=True),
+        pa.field("winner_strategy", pa.int32(), nullable=True),
+        pa.field("game_seed", pa.int64(), nullable=False),
+        pa.field("rng_scheme_version", pa.int16(), nullable=False),
+        pa.field("rng_purpose_namespace", pa.int32(), nullable=False),
+        pa.field("seat_ranks", str_list, nullable=False),
+        pa.field("winning_score", pa.int32(), nullable=True),
+        pa.field("victory_margin", pa.int32(), nullable=True),
+        pa.field("n_rounds", pa.int16(), nullable=False),
+    ]
+    seat = {
+        "score": (pa.int32(), False), "farkles": (pa.int16(), False), "rolls": (pa.int16(), False),
+        "highest_turn": (pa.int16(), False), "strategy": (pa.int32(), False),
+        "rank": (pa.int8(), True), "loss_margin": (pa.int32(), True),
+        "smart_five_uses": (pa.int16(), False), "n_smart_five_dice": (pa.int16(), False),
+        "smart_one_uses": (pa.int16(), False), "n_smart_one_dice": (pa.int16(), False),
+        "hot_dice": (pa.int16(), False), "n_turns": (pa.int16(), False),
+        "hit_max_rounds": (pa.bool_(), False),
+    }
+    fields = [pa.field(f"P{i}_{name}", t, nullable=nullable)
+              for i in range(1, n_players + 1) for name, (t, nullable) in seat.items()]
+    return pa.schema([*base, *fields])
+
+
+def simulation_rows_to_table(rows: Sequence[Mapping[str, Any]], n_players: int):
+    """Row mappings -> Arrow table (simulation.py:565-573)."""
+    import pyarrow as pa
+
+    for row in rows:
+        if int(row["k"]) != n_players:
+            raise ValueError(f"Simulation row k={row['k']} does not match schema k={n_players}")
+    return pa.Table.from_pylist(list(rows), schema=raw_simulation_schema_for(n_players))
+
+
+def compact_rows_to_table(rows: np.ndarray, *, root_seed: int, k: int, shuffle_index,
+                          game_index, deterministic_batch_id, shuffle_seed,
+                          purpose_namespace: int = int(RandomPurpose.TOURNAMENT_GAME)):
+    """Vectorised compact rows -> Arrow table with the schema above (no Python per-row loop).
+
+    Equal, column for column, to ``simulation_rows_to_table(expand_rows(...))``; this is the
+    ingest-rate path for tournament row shards.  ``shuffle_index`` / ``game_index`` /
+    ``deterministic_batch_id`` / ``shuffle_seed`` are scalars or per-row arrays.
+    """
+    import pyarrow as pa
+
+    check_row_flags(rows)
+    n = len(rows)
+    schema = raw_simulation_schema_for(k)
+    safety = (rows["flags"] & ROW_SAFETY_LIMIT) != 0
+    rank, order = derive_ranks(rows)
+    seats = rows["seats"]
+    scores = seats["score"].astype(np.int32)
+    w = np.where(safety, 0, rows["winner_seat"]).astype(np.int64)
+    ar = np.arange(n)
+    win_score = scores[ar, w]
+    sorted_scores = np.sort(scores, axis=1)[:, ::-1]
+    margin = sorted_scores[:, 0] - (sorted_scores[:, 1] if k > 1 else 0)
+    names = np.array([f"P{i + 1}" for i in range(k)], dtype=object)
+
+    def full(v, dtype):
+        return np.broadcast_to(np.asarray(v, dtype=dtype), (n,))
+
+    seat_rank_values = pa.array(names[order].reshape(-1), type=pa.string(),
+                                mask=np.repeat(safety, k))
+    seat_ranks = pa.ListArray.from_arrays(pa.array(np.arange(0, n * k + 1, k, dtype=np.int32)),
+                                          seat_rank_values, type=schema.field("seat_ranks").type)
+    cols: dict[str, Any] = {
+        "root_seed": pa.array(full(root_seed, np.int64)),
+        "k": pa.array(full(k, np.int16)),
+        "shuffle_index": pa.array(full(shuffle_index, np.int64)),
+        "game_index": pa.array(full(game_index, np.int32)),
+        "deterministic_batch_id": pa.array(full(deterministic_batch_id, np.int32)),
+        "shuffle_seed": pa.array(full(shuffle_seed, np.int64)),
+        "termination_status": pa.array(np.where(safety, "safety_limit", "completed").astype(object),
+                                       type=pa.string()),
+        "hit_safety_limit": pa.array(safety),
+        "outcome_schema_version": pa.array(full(OUTCOME_SCHEMA_VERSION, np.int16)),
+        "winner_seat": pa.array(names[w], type=pa.string(), mask=safety),
+        "winner_strategy": pa.array(seats["strategy"][ar, w].astype(np.int32), mask=safety),
+        "game_seed": pa.array(rows["game_seed"].astype(np.int64)),
+        "rng_scheme_version": pa.array(full(RNG_SCHEME_VERSION, np.int16)),
+        "rng_purpose_namespace": pa.array(full(purpose_namespace, np.int32)),
+        "seat_ranks": seat_ranks,
+        "winning_score": pa.array(win_score, mask=safety),
+        "victory_margin": pa.array(margin.astype(np.int32), mask=safety),
+        "n_rounds": pa.array(rows["n_rounds"].astype(np.int16)),
+    }
+    for s in range(k):
+        p = f"P{s + 1}_"
+        seat = seats[:, s]
+        cols[p + "score"] = pa.array(scores[:, s])
+        cols[p + "farkles"] = pa.array(seat["farkles"].astype(np.int16))
+        cols[p + "rolls"] = pa.array(seat["rolls"].astype(np.int16))
+        cols[p + "highest_turn"] = pa.array(seat["highest_turn"].astype(np.int16))
+        cols[p + "strategy"] = pa.array(seat["strategy"].astype(np.int32))
+        cols[p + "rank"] = pa.array(rank[:, s], mask=safety)
+        cols[p + "loss_margin"] = pa.array((win_score - scores[:, s]).astype(np.int32), mask=safety)
+        cols[p + "smart_five_uses"] = pa.array(seat["smart_five_uses"].astype(np.int16))
+        cols[p + "n_smart_five_dice"] = pa.array(seat["n_smart_five_dice"].astype(np.int16))
+        cols[p + "smart_one_uses"] = pa.array(seat["smart_one_uses"].astype(np.int16))
+        cols[p + "n_smart_one_dice"] = pa.array(seat["n_smart_one_dice"].astype(np.int16))
+        cols[p + "hot_dice"] = pa.array(seat["hot_dice"].astype(np.int16))
+        cols[p + "n_turns"] = pa.array(seat["n_turns"].astype(np.int16))
+        cols[p + "hit_max_rounds"] = pa.array(safety)
+    return pa.Table.from_arrays([cols[f.name] for f in schema], schema=schema)
+
+
+# --------------------------------------------------------------------------- games
+def play_games_batch(strategy_rows: Sequence[Sequence[ThresholdStrategy]],
+                     coordinates: Sequence[PlayerRngCoordinates], *,
+                     target_score: int | Sequence[int] = DEFAULT_TARGET_SCORE,
+                     max_rounds: int | Sequence[int] = DEFAULT_MAX_ROUNDS,
+                     device: int | None = None) -> np.ndarray:
+    """Play ``len(coordinates)`` independent tables in ONE launch; returns compact rows."""
+    from .device import get_engine
+
+    n = len(coordinates)
+    if n == 0:
+        raise ValueError("no games requested")
+    k = len(strategy_rows[0])
+    table = np.empty((n, k), dtype=STRATEGY_DTYPE)
+    ids = np.empty((n, k), dtype=np.int32)
+    for i, (strats, c) in enumerate(zip(strategy_rows, coordinates, strict=True)):
+        if len(strats) != k or c.k != k:
+            raise ValueError(
+                "Player RNG coordinate k does not match the number of seated strategies")
+        table[i] = pack_strategies(strats)
+        sid = [s.strategy_id for s in strats]
+        if any(x is None for x in sid):
+            raise ValueError("every seated strategy needs a strategy_id "
+                             "(use _prepare_public_helper_strategies)")
+        if len(set(sid)) != k:
+            raise ValueError("Simulation row must seat distinct strategies")
+        ids[i] = sid
+    coords = np.array([c.coords7() for c in coordinates], dtype=np.uint64)
+    scalar_t, scalar_m = np.isscalar(target_score), np.isscalar(max_rounds)
+    rows, _totals = get_engine(device).play_games(
+        coords, k, table, seat_strategy_ids=ids,
+        target_score=int(target_score) if scalar_t else DEFAULT_TARGET_SCORE,
+        max_rounds=int(max_rounds) if scalar_m else DEFAULT_MAX_ROUNDS,
+        target_scores=None if scalar_t else np.asarray(target_score, dtype=np.int32),
+        max_rounds_v=None if scalar_m else np.asarray(max_rounds, dtype=np.int32))
+    return rows
+
+
+def _play_game(seed: int, strategies: Sequence[ThresholdStrategy], target_score: int = 10_000,
+               provenance: Mapping[str, Any] | None = None, max_rounds: int = 200,
+               player_rng_coordinates: PlayerRngCoordinates | None = None,
+               *, device: int | None = None) -> Mapping[str, Any]:
+    """Play a single game on the GPU and return the reference's flat row (simulation.py:576-655)."""
+    coords = player_rng_coordinates or PlayerRngCoordinates(
+        purpose=RandomPurpose.PLAYER, root_seed=seed, k=len(strategies))
+    if coords.k != len(strategies):
+        raise ValueError("Player RNG coordinate k does not match the number of seated strategies")
+    rows = play_games_batch([strategies], [coords], target_score=target_score,
+                            max_rounds=max_rounds, device=device)
+    return expand_rows(rows, None if provenance is None else [provenance], root_seed=seed)[0]
+
+
+def _helper_rows(seeds: Iterable[int], strategies: Sequence[ThresholdStrategy], target_score: int,
+                 root_seed: int | None, device: int | None) -> list[dict[str, Any]]:
+    resolved = _prepare_public_helper_strategies(strategies)
+    k = len(resolved)
+    seeds = [int(s) for s in seeds]
+    if not seeds:
+        return []
+    coords, prov = [], []
+    for game_index, game_seed in enumerate(seeds):
+        root = game_seed if root_seed is None else root_seed
+        coords.append(PlayerRngCoordinates(
+            purpose=RandomPurpose.PLAYER, root_seed=root, k=k,
+            game_index=0 if root_seed is None else game_index))
+        prov.append({"root_seed": root, "k": k, "shuffle_index": None, "game_index": game_index,
+                     "deterministic_batch_id": None, "game_seed": game_seed,
+                     "rng_scheme_version": RNG_SCHEME_VERSION,
+                     "rng_purpose_namespace": int(RandomPurpose.INDEXED_SEED)})
+    rows = play_games_batch([resolved] * len(seeds), coords, target_score=target_score,
+                            device=device)
+    return expand_rows(rows, prov, root_seed=seeds)
+
+
+def simulate_many_games(*, n_games: int, strategies: Sequence[ThresholdStrategy],
+                        target_score: int = 10_000, seed: int | None = None, n_jobs: int = 1,
+                        device: int | None = None):
+    """``n_games`` games of one table as a DataFrame (simulation.py:658-722).
+
+    ``n_jobs`` is accepted for signature compatibility; all games run in one launch.
+    """
+    import pandas as pd
+
+    if seed is None:
+        raise ValueError("simulate_many_games requires an explicit seed")
+    del n_jobs
+    return pd.DataFrame(_helper_rows(spawn_seeds(n_games, seed=seed), strategies, target_score,
+                                     seed, device))
+
+
+def simulate_many_games_from_seeds(*, seeds: Iterable[int], strategies: Sequence[ThresholdStrategy],
+                                   target_score: int = 10_000, n_jobs: int = 1,
+                                   root_seed: int | None = None, device: int | None = None):
+    """Games for predetermined seeds (simulation.py:725-790)."""
+    import pandas as pd
+
+    del n_jobs
+    return pd.DataFrame(_helper_rows(seeds, strategies, target_score, root_seed, device))
+
+
+def aggregate_metrics(df) -> Mapping[str, Any]:
+    """Summary of a results frame (simulation.py:823-838)."""
+    return {"games": len(df), "avg_rounds": df["n_rounds"].mean(),
+            "winner_freq": df["winner_seat"].value_counts().to_dict()}
