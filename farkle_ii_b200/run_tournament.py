@@ -1,0 +1,590 @@
+"""Tournament host surface over the CUDA engine.
+
+Mirror of the reference's ``farkle.simulation.run_tournament`` for the seams its tests and
+callers already treat as replaceable:
+
+* ``TournamentConfig`` / ``ShuffleTask``                run_tournament.py:78-104
+* ``METRIC_LABELS``                                      :108-121
+* ``OutcomeCounter``                                     :165-250
+* ``_init_worker`` / ``WorkerState``                     :253-277
+* ``_play_one_shuffle`` / ``_play_shuffle``              :301-400
+* ``_run_chunk`` / ``_run_chunk_item`` / ``_run_chunk_metrics``   :403-585
+* ``run_tournament``                                     :1050-1859 (reduce loop, checkpoint
+  payload, ``{k}p_metrics.parquet``; the artifact-contract sidecars are out of scope)
+
+Same names, same argument meaning, same return types.  The bodies differ: a chunk of
+shuffles is ONE ``fb_play_tournament`` launch (contiguous shuffle runs), the per-strategy
+tallies come back as an ``int64[ids][26]`` tensor and are unpacked into the reference's
+``OutcomeCounter`` / ``dict[label][strategy] -> float`` shapes.  With ``torch.distributed``
+initialised, ``run_tournament`` shards deterministic batches round-robin over ranks and
+merges the tally tensors with one all-reduce per cell (NCCL on the GPUs).
+"""
+
+from __future__ import annotations
+
+import json
+import logging
+import os
+import pickle
+import tempfile
+from collections import Counter, defaultdict
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Any, Callable, Dict, Iterator, List, Mapping, Sequence, Tuple
+
+import numpy as np
+
+from .game_profile import GameProfile
+from .layout import N_METRICS, T_ATTEMPTED, T_COMPLETED, T_SAFETY, T_SQ_SUMS, T_SUMS, T_WINS, TALLY_WIDTH
+from .random import RNG_SCHEME_VERSION, RandomPurpose, coordinate_seed
+from .simulation import (
+    OUTCOME_SCHEMA_VERSION,
+    TOURNAMENT_METHOD_VERSION,
+    _prepare_public_helper_strategies,
+    check_row_flags,
+    compact_rows_to_table,
+    expand_rows,
+)
+from .strategies import ThresholdStrategy, generate_strategy_grid, pack_strategies
+
+LOGGER = logging.getLogger(__name__)
+
+NUM_SHUFFLES: int = 5_907
+DESIRED_SEC_PER_CHUNK: int = 10
+CKPT_EVERY_SEC: int = 30
+
+
+@dataclass
+class TournamentConfig:
+    """Runtime configuration (run_tournament.py:78-94)."""
+
+    n_players: int = 5
+    num_shuffles: int = NUM_SHUFFLES
+    desired_sec_per_chunk: int = DESIRED_SEC_PER_CHUNK
+    ckpt_every_sec: int = CKPT_EVERY_SEC
+    n_strategies: int = 7_140
+    mp_start_method: str | None = None
+    deterministic_batch_size: int = 30
+
+    @property
+    def games_per_shuffle(self) -> int:
+        return self.n_strategies // self.n_players
+
+
+@dataclass(frozen=True, slots=True)
+class ShuffleTask:
+    """Stable coordinate identity of one tournament shuffle (run_tournament.py:97-104)."""
+
+    root_seed: int
+    k: int
+    shuffle_index: int
+    shuffle_seed: int
+    deterministic_batch_id: int
+
+
+METRIC_LABELS: Tuple[str, ...] = (
+    "winning_score", "n_rounds", "winner_farkles", "winner_rolls", "winner_highest_turn",
+    "winner_smart_five_uses", "winner_n_smart_five_dice", "winner_smart_one_uses",
+    "winner_n_smart_one_dice", "winner_hot_dice", "winner_hit_max_rounds",
+)
+assert len(METRIC_LABELS) == N_METRICS
+
+
+class OutcomeCounter(Counter):
+    """Win counter carrying attempted/completed exposure conservation (run_tournament.py:165-230)."""
+
+    def __init__(self, *args: Any, **kwargs: Any) -> None:
+        self.attempted_exposures: Counter = Counter()
+        self.completed_exposures: Counter = Counter()
+        self.safety_limit_exposures: Counter = Counter()
+        self.games_attempted = 0
+        self.games_completed = 0
+        self.games_safety_limit = 0
+        super().__init__(*args, **kwargs)
+
+    def record_row(self, row: Mapping[str, Any], *, k: int, source: str) -> str:
+        status = row.get("termination_status")
+        if row.get("outcome_schema_version") != OUTCOME_SCHEMA_VERSION:
+            raise RuntimeError(f"{source} is not outcome-schema-v{OUTCOME_SCHEMA_VERSION} compatible; "
+                               "explicit-outcome tournament aggregation is disabled for this row")
+        if status not in ("completed", "safety_limit"):
+            raise RuntimeError(f"{source} has unsupported termination_status={status!r}")
+        completed = status == "completed"
+        has_winner = row.get("winner_seat") is not None or row.get("winner_strategy") is not None
+        if not completed and has_winner:
+            raise RuntimeError(f"{source} fabricates a winner for a safety-limit attempt")
+        if completed and (row.get("winner_seat") is None or row.get("winner_strategy") is None):
+            raise RuntimeError(f"{source} is completed but has no canonical winner")
+        for seat in range(1, k + 1):
+            strategy = row.get(f"P{seat}_strategy")
+            if strategy is None:
+                raise ValueError(f"{source} is missing strategy exposure for P{seat}")
+            self.attempted_exposures[strategy] += 1
+            (self.completed_exposures if completed else self.safety_limit_exposures)[strategy] += 1
+        self.games_attempted += 1
+        if completed:
+            self.games_completed += 1
+        else:
+            self.games_safety_limit += 1
+        return status
+
+    def absorb(self, other: Counter) -> None:
+        super().update(other)
+        if isinstance(other, OutcomeCounter):
+            self.attempted_exposures.update(other.attempted_exposures)
+            self.completed_exposures.update(other.completed_exposures)
+            self.safety_limit_exposures.update(other.safety_limit_exposures)
+            self.games_attempted += other.games_attempted
+            self.games_completed += other.games_completed
+            self.games_safety_limit += other.games_safety_limit
+            return
+        completed = int(sum(other.values()))
+        self.attempted_exposures.update(other)
+        self.completed_exposures.update(other)
+        self.games_attempted += completed
+        self.games_completed += completed
+
+    def outcome_payload(self) -> dict[str, Any]:
+        return {
+            "games_attempted": self.games_attempted,
+            "games_completed": self.games_completed,
+            "games_safety_limit": self.games_safety_limit,
+            "attempted_exposures": dict(self.attempted_exposures),
+            "completed_exposures": dict(self.completed_exposures),
+            "safety_limit_exposures": dict(self.safety_limit_exposures),
+        }
+
+    def __reduce__(self):
+        return (_restore_outcome_counter, (dict(self), self.outcome_payload()))
+
+
+def _restore_outcome_counter(counts: dict, outcome_counts: dict[str, Any]) -> OutcomeCounter:
+    restored = OutcomeCounter(counts)
+    restored.attempted_exposures.update(outcome_counts.get("attempted_exposures", {}))
+    restored.completed_exposures.update(outcome_counts.get("completed_exposures", {}))
+    restored.safety_limit_exposures.update(outcome_counts.get("safety_limit_exposures", {}))
+    restored.games_attempted = int(outcome_counts.get("games_attempted", 0))
+    restored.games_completed = int(outcome_counts.get("games_completed", 0))
+    restored.games_safety_limit = int(outcome_counts.get("games_safety_limit", 0))
+    return restored
+
+
+# --------------------------------------------------------------------------- tallies <-> counters
+MetricSums = Dict[str, Dict[Any, float]]
+
+
+def tallies_to_outcome(tallies: np.ndarray, ids: Sequence[int], games: Tuple[int, int, int]
+                       ) -> Tuple[OutcomeCounter, MetricSums, MetricSums]:
+    """``int64[n][26]`` -> ``(OutcomeCounter, sums, sq_sums)`` exactly as run_tournament.py:331-393
+    would have built them: keys exist only where the reference would have touched them."""
+    t = np.asarray(tallies).reshape(-1, TALLY_WIDTH)
+    wins = OutcomeCounter()
+    sums: MetricSums = {m: defaultdict(float) for m in METRIC_LABELS}
+    sq_sums: MetricSums = {m: defaultdict(float) for m in METRIC_LABELS}
+    ids = [int(i) for i in ids]
+    for col, target in ((T_ATTEMPTED, wins.attempted_exposures),
+                        (T_COMPLETED, wins.completed_exposures),
+                        (T_SAFETY, wins.safety_limit_exposures)):
+        for j in np.flatnonzero(t[:, col]):
+            target[ids[j]] = int(t[j, col])
+    winners = np.flatnonzero(t[:, T_WINS])
+    for j in winners:
+        wins[ids[j]] = int(t[j, T_WINS])
+        for m, label in enumerate(METRIC_LABELS):
+            sums[label][ids[j]] = float(t[j, T_SUMS + m])
+            sq_sums[label][ids[j]] = float(t[j, T_SQ_SUMS + m])
+    wins.games_attempted, wins.games_completed, wins.games_safety_limit = (int(x) for x in games)
+    return wins, sums, sq_sums
+
+
+# --------------------------------------------------------------------------- worker state
+@dataclass(slots=True)
+class WorkerState:
+    strats: list[ThresholdStrategy]
+    cfg: TournamentConfig
+    game_profile: GameProfile | None = None
+    table: np.ndarray | None = None      # packed fb_strategy_t table
+    ids: np.ndarray | None = None        # strategy id of table entry i
+    device: int | None = None
+
+
+_STATE: WorkerState | None = None
+
+
+def _init_worker(strategies: Sequence[ThresholdStrategy], config: TournamentConfig,
+                 game_profile: GameProfile | None = None, progress_endpoint: object | None = None,
+                 *, device: int | None = None) -> None:
+    """Initialise per-process state (run_tournament.py:265-277)."""
+    global _STATE
+    del progress_endpoint
+    if len(strategies) % config.n_players != 0:
+        raise ValueError(f"n_players must divide {len(strategies):,}")
+    strats = _prepare_public_helper_strategies(strategies)
+    config.n_strategies = len(strats)
+    _STATE = WorkerState(strats, config, game_profile, pack_strategies(strats),
+                         np.array([s.strategy_id for s in strats], dtype=np.int64), device)
+
+
+def _coerce_shuffle_task(task: ShuffleTask | int) -> ShuffleTask:
+    if isinstance(task, ShuffleTask):
+        return task
+    k = _STATE.cfg.n_players if _STATE is not None else 0
+    return ShuffleTask(root_seed=int(task), k=k, shuffle_index=0, shuffle_seed=int(task),
+                       deterministic_batch_id=0)
+
+
+def _require_state() -> WorkerState:
+    if _STATE is None:
+        raise RuntimeError("_init_worker has not been called")
+    return _STATE
+
+
+def _contiguous_runs(tasks: Sequence[ShuffleTask]) -> Iterator[Tuple[int, int]]:
+    """``(start, stop)`` slices of ``tasks`` that are one (root, k) with consecutive shuffles."""
+    start = 0
+    for i in range(1, len(tasks) + 1):
+        if (i == len(tasks) or tasks[i].root_seed != tasks[start].root_seed
+                or tasks[i].k != tasks[start].k
+                or tasks[i].shuffle_index != tasks[i - 1].shuffle_index + 1):
+            yield start, i
+            start = i
+
+
+def _launch_run(state: WorkerState, tasks: Sequence[ShuffleTask], *, want_rows: bool):
+    """One ``fb_play_tournament`` launch for a contiguous shuffle run.
+
+    Returns ``(tallies[n, 26], (attempted, completed, safety_limit), rows | None)`` as host
+    values for the whole run.
+    """
+    from .device import get_engine
+
+    first = tasks[0]
+    k, n = first.k, len(tasks)
+    if k != state.cfg.n_players:
+        raise ValueError(f"task k={k} does not match the worker's n_players={state.cfg.n_players}")
+    prof = state.game_profile
+    eng = get_engine(state.device)
+    res = eng.play_tournament(
+        first.root_seed, k, first.shuffle_index, n, state.table,
+        target_score=prof.default_target_score if prof else 10_000,
+        max_rounds=prof.default_max_rounds if prof else 200,
+        overrides=(prof.tournament_overrides_for(first.root_seed, k, first.shuffle_index, n)
+                   if prof else ()),
+        want_rows=want_rows, want_game_seeds=want_rows)
+    tallies = res.tallies.cpu().numpy()[0]
+    totals = res.totals.cpu().numpy()
+    rows = res.rows_numpy() if res.rows is not None else None
+    if rows is not None:
+        check_row_flags(rows)
+    elif totals[7]:
+        raise RuntimeError("a game hit ROLL_LIMIT or overflowed an int16 row counter")
+    return tallies, (int(totals[0]), int(totals[1]), int(totals[2])), rows
+
+
+def _expand_shuffle_rows(state: WorkerState, task: ShuffleTask, rows: np.ndarray) -> List[Dict[str, Any]]:
+    """Row mappings of one shuffle with the reference's provenance block (:350-361)."""
+    rows = rows.copy()
+    rows["seats"]["strategy"] = state.ids[rows["seats"]["strategy"]]
+    prov = [{
+        "root_seed": task.root_seed, "k": task.k, "shuffle_index": task.shuffle_index,
+        "game_index": g, "deterministic_batch_id": task.deterministic_batch_id,
+        "shuffle_seed": task.shuffle_seed, "game_seed": int(rows["game_seed"][g]),
+        "rng_scheme_version": RNG_SCHEME_VERSION,
+        "rng_purpose_namespace": int(RandomPurpose.TOURNAMENT_GAME),
+    } for g in range(len(rows))]
+    return expand_rows(rows, prov)
+
+
+def _play_one_shuffle(task: ShuffleTask | int, *, collect_rows: bool = False) -> Tuple[
+        Counter, MetricSums, MetricSums, List[Dict[str, Any]]]:
+    """Play all games of one shuffle and aggregate the results (run_tournament.py:301-393)."""
+    state = _require_state()
+    work = _coerce_shuffle_task(task)
+    tallies, games, rows = _launch_run(state, [work], want_rows=collect_rows)
+    wins, sums, sq_sums = tallies_to_outcome(tallies, state.ids, games)
+    out_rows = _expand_shuffle_rows(state, work, rows) if collect_rows else []
+    return wins, sums, sq_sums, out_rows
+
+
+def _play_shuffle(task: ShuffleTask | int) -> Counter:
+    wins, _, _, _ = _play_one_shuffle(task, collect_rows=False)
+    return wins
+
+
+def _run_chunk(shuffle_tasks: Sequence[ShuffleTask | int]) -> Counter:
+    """Play a batch of shuffles and tally wins (run_tournament.py:403-457): one launch per
+    contiguous run instead of one Python game loop per shuffle."""
+    state = _require_state()
+    tasks = [_coerce_shuffle_task(t) for t in shuffle_tasks]
+    total = OutcomeCounter()
+    for a, b in _contiguous_runs(tasks):
+        tallies, games, _ = _launch_run(state, tasks[a:b], want_rows=False)
+        wins, _, _ = tallies_to_outcome(tallies, state.ids, games)
+        total.absorb(wins)
+    return total
+
+
+def _run_chunk_item(item: Tuple[int, Sequence[ShuffleTask]], *,
+                    chunk_fn: Callable[[Sequence[ShuffleTask]], object]
+                    ) -> Tuple[int, tuple, object]:
+    chunk_index, seeds = item
+    tasks = tuple(seeds)
+    return chunk_index, tasks, chunk_fn(tasks)
+
+
+def _atomic_write(path: Path, write: Callable[[Path], None]) -> None:
+    """temp -> fsync -> rename in the target directory (utils/writer.py:41-124 semantics)."""
+    path.parent.mkdir(parents=True, exist_ok=True)
+    fd, tmp = tempfile.mkstemp(prefix=f".{path.name}.", suffix=".tmp", dir=path.parent)
+    os.close(fd)
+    try:
+        write(Path(tmp))
+        with open(tmp, "rb") as fh:
+            os.fsync(fh.fileno())
+        os.replace(tmp, path)
+    finally:
+        if os.path.exists(tmp):
+            os.unlink(tmp)
+
+
+def _append_manifest(manifest_path: Path, record: Mapping[str, Any]) -> None:
+    """One NDJSON line per shard (utils/manifest.py:134-166)."""
+    manifest_path.parent.mkdir(parents=True, exist_ok=True)
+    with open(manifest_path, "a", encoding="utf-8") as fh:
+        fh.write(json.dumps(record, sort_keys=True, separators=(",", ":")) + "\n")
+        fh.flush()
+        os.fsync(fh.fileno())
+
+
+def _run_chunk_metrics(shuffle_tasks: Sequence[ShuffleTask | int], *, collect_rows: bool = False,
+                       row_dir: Path | None = None, manifest_path: Path | None = None,
+                       row_sidecar: object | None = None) -> Tuple[Counter, MetricSums, MetricSums]:
+    """Play shuffles and accumulate metrics (run_tournament.py:473-585).
+
+    In rows mode every shuffle leaves one Parquet shard
+    ``rows_{root}_{k}p_{shuffle:012d}.parquet`` plus one manifest line before returning,
+    written temp->rename.  ``row_sidecar`` (the reference's hash-bound artifact sidecar) is
+    accepted but not produced: the artifact contract is outside this path.
+    """
+    import pyarrow.parquet as pq
+
+    del row_sidecar
+    state = _require_state()
+    tasks = [_coerce_shuffle_task(t) for t in shuffle_tasks]
+    wins_total = OutcomeCounter()
+    sums_total: MetricSums = {m: defaultdict(float) for m in METRIC_LABELS}
+    sq_total: MetricSums = {m: defaultdict(float) for m in METRIC_LABELS}
+    want_rows = collect_rows and row_dir is not None
+    gps = state.cfg.games_per_shuffle
+    for a, b in _contiguous_runs(tasks):
+        run = tasks[a:b]
+        tallies, games, rows = _launch_run(state, run, want_rows=want_rows)
+        wins, sums, sqs = tallies_to_outcome(tallies, state.ids, games)
+        wins_total.absorb(wins)
+        for label in METRIC_LABELS:
+            for key, v in sums[label].items():
+                sums_total[label][key] += v
+            for key, v in sqs[label].items():
+                sq_total[label][key] += v
+        if not want_rows:
+            continue
+        rows = rows.copy()
+        rows["seats"]["strategy"] = state.ids[rows["seats"]["strategy"]]
+        for i, task in enumerate(run):
+            shard = rows[i * gps:(i + 1) * gps]
+            tbl = compact_rows_to_table(
+                shard, root_seed=task.root_seed, k=task.k, shuffle_index=task.shuffle_index,
+                game_index=np.arange(gps), deterministic_batch_id=task.deterministic_batch_id,
+                shuffle_seed=task.shuffle_seed)
+            out = Path(row_dir) / f"rows_{task.root_seed}_{task.k}p_{task.shuffle_index:012d}.parquet"
+            _atomic_write(out, lambda p, t=tbl: pq.write_table(t, p))
+            record = {
+                "path": out.name, "rows": tbl.num_rows, "root_seed": task.root_seed,
+                "n_players": task.k, "shuffle_index": task.shuffle_index,
+                "shuffle_seed": task.shuffle_seed,
+                "deterministic_batch_id": task.deterministic_batch_id,
+                "rng_scheme_version": RNG_SCHEME_VERSION,
+                "rng_purpose_namespace": int(RandomPurpose.TOURNAMENT_SHUFFLE),
+                "outcome_schema_version": OUTCOME_SCHEMA_VERSION,
+                "tournament_method_version": TOURNAMENT_METHOD_VERSION, "pid": os.getpid(),
+            }
+            if state.game_profile is not None:
+                record["game_profile_sha256"] = state.game_profile.sha256
+            _append_manifest(Path(manifest_path or (Path(row_dir) / "manifest.jsonl")), record)
+    return wins_total, sums_total, sq_total
+
+
+# --------------------------------------------------------------------------- cell runner
+def make_shuffle_tasks(root_seed: int, k: int, shuffle_indices: Sequence[int],
+                       deterministic_batch_size: int) -> List[ShuffleTask]:
+    """Tasks with the purpose-100 fingerprint, as ``_iter_original_chunk_items`` builds them
+    (run_tournament.py:944-984)."""
+    return [ShuffleTask(root_seed=root_seed, k=k, shuffle_index=s,
+                        shuffle_seed=coordinate_seed(RandomPurpose.TOURNAMENT_SHUFFLE,
+                                                     root_seed=root_seed, k=k, shuffle_index=s,
+                                                     dtype=np.uint32),
+                        deterministic_batch_id=s // deterministic_batch_size)
+            for s in shuffle_indices]
+
+
+def shard_batches(num_shuffles: int, batch_size: int, rank: int, world: int
+                  ) -> List[Tuple[int, int, int]]:
+    """``(batch_id, shuffle0, n_shuffles)`` of the deterministic batches rank ``rank`` owns:
+    batch b (shuffles [b*B, min((b+1)*B, S)), the reference's recovery unit,
+    run_tournament.py:974) goes to rank ``b % world``."""
+    if batch_size < 1 or world < 1 or not 0 <= rank < world:
+        raise ValueError("bad batch size / rank / world")
+    n_batches = -(-num_shuffles // batch_size)
+    return [(b, b * batch_size, min(batch_size, num_shuffles - b * batch_size))
+            for b in range(rank, n_batches, world)]
+
+
+def merge_ranges(batches: Sequence[Tuple[int, int, int]]) -> List[Tuple[int, int]]:
+    """Coalesce owned batches into maximal contiguous ``(shuffle0, n_shuffles)`` launches."""
+    out: List[Tuple[int, int]] = []
+    for _, s0, n in batches:
+        if out and out[-1][0] + out[-1][1] == s0:
+            out[-1] = (out[-1][0], out[-1][1] + n)
+        else:
+            out.append((s0, n))
+    return out
+
+
+def all_reduce_tallies(tallies, totals):
+    """Sum the small tally / totals tensors over ranks (the path's ONE exchange step)."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(tallies)
+        dist.all_reduce(totals)
+    return tallies, totals
+
+
+def run_cell(root_seed: int, k: int, num_shuffles: int, table, *, batch_size: int,
+             launch: Callable[..., Tuple[Any, Any]], rank: int = 0, world: int = 1,
+             max_shuffles_per_launch: int = 1 << 20):
+    """Play this rank's share of a (root, k) cell and merge.
+
+    ``launch(root_seed, k, shuffle0, n_shuffles, table, tallies, totals)`` accumulates into
+    the ``int64`` tensors it is given (``Engine.play_tournament`` on a GPU; the tests pass a
+    CPU stand-in).  Returns the merged ``(tallies[1, n, 26], totals[20])`` tensors.
+    """
+    import torch
+
+    from .layout import TOTALS_WIDTH
+
+    n = len(table) if isinstance(table, np.ndarray) else table.numel() // 8
+    tallies = totals = None
+    for s0, cnt in merge_ranges(shard_batches(num_shuffles, batch_size, rank, world)):
+        while cnt > 0:
+            step = min(cnt, max_shuffles_per_launch)
+            tallies, totals = launch(root_seed, k, s0, step, table, tallies, totals)
+            s0 += step
+            cnt -= step
+    if tallies is None:  # a rank that owns no batch still takes part in the reduction
+        dev = table.device if hasattr(table, "device") else "cpu"
+        tallies = torch.zeros((1, n, TALLY_WIDTH), dtype=torch.int64, device=dev)
+        totals = torch.zeros(TOTALS_WIDTH, dtype=torch.int64, device=dev)
+    return all_reduce_tallies(tallies, totals)
+
+
+def _engine_launch(eng, want_kw: Mapping[str, Any]):
+    def launch(root_seed, k, shuffle0, n_shuffles, table, tallies, totals):
+        res = eng.play_tournament(root_seed, k, shuffle0, n_shuffles, table, tallies=tallies,
+                                  totals=totals, **want_kw)
+        return res.tallies, res.totals
+    return launch
+
+
+def run_tournament(*, config: TournamentConfig | None = None, global_seed: int = 0,
+                   checkpoint_path: Path | str = "checkpoint.pkl", n_jobs: int | None = None,
+                   collect_metrics: bool = False, row_output_directory: Path | None = None,
+                   num_shuffles: int = NUM_SHUFFLES,
+                   strategies: Sequence[ThresholdStrategy] | None = None, resume: bool = True,
+                   checkpoint_metadata: Mapping[str, Any] | None = None,
+                   oracle_game_profile: GameProfile | None = None,
+                   write_final_metrics_artifact: bool = True, device: int | None = None) -> None:
+    """Run one (root, k) tournament cell on the GPU(s) (run_tournament.py:1050-1859).
+
+    Keeps the reference's observable results: the checkpoint pickle
+    ``{"win_totals": OutcomeCounter, "outcome_counts", "metric_sums", "metric_square_sums",
+    "meta"}`` and ``{k}p_metrics.parquet``; with ``row_output_directory`` one Parquet shard +
+    manifest line per shuffle (already-listed shuffles are skipped when ``resume``).
+    ``n_jobs`` is accepted for compatibility: parallelism is the GPU's.
+    """
+    import torch
+    import torch.distributed as dist
+
+    from .device import get_engine
+
+    del n_jobs
+    if strategies is None:
+        strategies, _ = generate_strategy_grid()
+    cfg = config or TournamentConfig()
+    if num_shuffles != cfg.num_shuffles:
+        cfg.num_shuffles = num_shuffles
+    _init_worker(strategies, cfg, oracle_game_profile, device=device)
+    state = _require_state()
+    k, root = cfg.n_players, int(global_seed)
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    ckpt_path = Path(checkpoint_path)
+    collect_rows = row_output_directory is not None
+    if collect_rows:
+        row_dir = Path(row_output_directory)
+        manifest = row_dir / "manifest.jsonl"
+        done: set[int] = set()
+        if resume and manifest.exists():
+            for line in manifest.read_text().splitlines():
+                if line.strip():
+                    done.add(int(json.loads(line)["shuffle_index"]))
+        wins, sums, sqs = OutcomeCounter(), None, None
+        for _, s0, cnt in shard_batches(cfg.num_shuffles, cfg.deterministic_batch_size, rank, world):
+            pending = [s for s in range(s0, s0 + cnt) if s not in done]
+            tasks = make_shuffle_tasks(root, k, pending, cfg.deterministic_batch_size)
+            if tasks:
+                _run_chunk_metrics(tasks, collect_rows=True, row_dir=row_dir, manifest_path=manifest)
+        if world > 1:
+            dist.barrier()
+    eng = get_engine(state.device)
+    prof = state.game_profile
+    if prof and prof.tournament_max_rounds_overrides:
+        kw = dict(target_score=prof.default_target_score, max_rounds=prof.default_max_rounds)
+
+        def launch(root_seed, kk, s0, n, table, tallies, totals):
+            res = eng.play_tournament(root_seed, kk, s0, n, table, tallies=tallies, totals=totals,
+                                      overrides=prof.tournament_overrides_for(root_seed, kk, s0, n), **kw)
+            return res.tallies, res.totals
+    else:
+        kw = dict(target_score=prof.default_target_score, max_rounds=prof.default_max_rounds) if prof else {}
+        launch = _engine_launch(eng, kw)
+    table_dev = eng.to_device(state.table)
+    tallies, totals = run_cell(root, k, cfg.num_shuffles, table_dev,
+                               batch_size=cfg.deterministic_batch_size, launch=launch, rank=rank,
+                               world=world)
+    torch.cuda.synchronize(eng.device)
+    if rank != 0:
+        return
+    tot = totals.cpu().numpy()
+    if tot[7]:
+        raise RuntimeError("a game hit ROLL_LIMIT or overflowed an int16 row counter")
+    wins, sums, sqs = tallies_to_outcome(tallies.cpu().numpy()[0], state.ids, tuple(tot[:3]))
+    payload: Dict[str, Any] = {"win_totals": wins, "outcome_counts": wins.outcome_payload()}
+    if collect_metrics or collect_rows:
+        payload["metric_sums"] = {m: dict(v) for m, v in sums.items()}
+        payload["metric_square_sums"] = {m: dict(v) for m, v in sqs.items()}
+    if checkpoint_metadata:
+        payload["meta"] = dict(checkpoint_metadata)
+    _atomic_write(ckpt_path, lambda p: p.write_bytes(pickle.dumps(payload, protocol=pickle.HIGHEST_PROTOCOL)))
+    if write_final_metrics_artifact and (collect_metrics or collect_rows):
+        import pyarrow as pa
+        import pyarrow.parquet as pq
+
+        metric_rows = [{"metric": label, "strategy": s, "sum": float(v),
+                        "square_sum": float(sqs[label].get(s, 0.0))}
+                       for label in METRIC_LABELS for s, v in sums[label].items()]
+        schema = pa.schema([pa.field("metric", pa.string()), pa.field("strategy", pa.int32()),
+                            pa.field("sum", pa.float64()), pa.field("square_sum", pa.float64())])
+        tbl = pa.Table.from_pylist(metric_rows, schema=schema)
+        _atomic_write(ckpt_path.with_name(f"{k}p_metrics.parquet"), lambda p: pq.write_table(tbl, p))
+    LOGGER.info("Tournament run complete after %d attempted games", wins.games_attempted)

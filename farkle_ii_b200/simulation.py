@@ -147,7 +147,9 @@ def expand_rows(rows: np.ndarray, provenance: Sequence[Mapping[str, Any]] | None
         }
         if provenance is not None:
             flat.update(provenance[i])
-        for s in range(k):
+        # per-seat blocks follow the iteration order of GameMetrics.players: rank order for a
+        # completed game, seat order at the safety limit (game/engine.py:477-509)
+        for s in (range(k) if safety else (int(x) for x in order[i])):
             seat = seats[s]
             p = f"P{s + 1}_"
             flat[p + "score"] = scores[s]

@@ -1,0 +1,102 @@
+"""Test double: an ``Engine`` look-alike whose compute calls go to the CPU oracle.
+
+Only ``tests/`` may use this.  It lets the host-surface mirror (row expansion, counters,
+H2H loop, rank sharding) be checked against the reference's golden outputs on a box without
+a GPU; the ``-m gpu`` variants of the same tests run the real ``Engine``.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+import oracle
+from farkle_ii_b200.layout import STRATEGY_DTYPE, row_dtype
+
+P_H2H_PLAYER = 203
+
+
+@dataclass
+class _Result:
+    tallies: torch.Tensor | None
+    totals: torch.Tensor
+    rows: torch.Tensor | None
+    n_games: int
+    k: int
+
+    def rows_numpy(self) -> np.ndarray:
+        return self.rows.numpy().view(row_dtype(self.k)).reshape(-1)
+
+
+def _table(strategies) -> np.ndarray:
+    if isinstance(strategies, torch.Tensor):
+        return strategies.cpu().numpy().view(STRATEGY_DTYPE).reshape(-1)
+    return np.ascontiguousarray(strategies, dtype=STRATEGY_DTYPE)
+
+
+class OracleEngine:
+    device = torch.device("cpu")
+
+    def to_device(self, a: np.ndarray, dtype=None) -> torch.Tensor:
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy())
+
+    def play_tournament(self, root_seed, k, shuffle0, n_shuffles, strategies, *, strategy_ids=None,
+                        n_tally_ids=None, target_score=10_000, max_rounds=200, overrides=(),
+                        shuffles_per_slot=0, want_tallies=True, want_rows=False,
+                        want_game_seeds=False, tallies=None, totals=None):
+        t, tot, rows = oracle.play_tournament(
+            root_seed, k, shuffle0, n_shuffles, _table(strategies), strategy_ids=strategy_ids,
+            n_tally_ids=n_tally_ids, target_score=target_score, max_rounds=max_rounds,
+            overrides=list(overrides), shuffles_per_slot=shuffles_per_slot, want_rows=want_rows,
+            want_game_seeds=want_game_seeds, n_threads=2)
+        tt, to = torch.from_numpy(t), torch.from_numpy(tot)
+        if tallies is not None:
+            tallies += tt
+            tt = tallies
+        if totals is not None:
+            totals += to
+            to = totals
+        r = None if rows is None else torch.from_numpy(rows.view(np.uint8).reshape(len(rows), -1))
+        return _Result(tt if want_tallies else None, to, r, len(rows) if rows is not None else 0, k)
+
+    def play_games(self, coords, k, seat_strategies, **kw):
+        return oracle.play_games(coords, k, seat_strategies, **kw)
+
+    def play_h2h(self, root_seed, pair_id, order, seat1, seat2, attempt0, n_attempts, *,
+                 target_score=10_000, max_rounds=200, want_rows=False):
+        pair_id, order = np.asarray(pair_id), np.asarray(order)
+        attempt0, n_attempts = np.asarray(attempt0), np.asarray(n_attempts, dtype=np.uint32)
+        s1, s2 = _table(seat1), _table(seat2)
+        coords, st = [], []
+        for b in range(len(pair_id)):
+            for a in range(int(attempt0[b]), int(attempt0[b]) + int(n_attempts[b])):
+                coords.append([P_H2H_PLAYER, root_seed, 2, 0, int(pair_id[b]), int(order[b]), a])
+                st.append([tuple(s1[b]), tuple(s2[b])])
+        if not coords:
+            return torch.zeros(0, dtype=torch.uint8), torch.from_numpy(n_attempts.astype(np.int64)), None, None
+        rows, totals = oracle.play_games(np.array(coords, dtype=np.uint64), 2,
+                                         np.array(st, dtype=STRATEGY_DTYPE), target_score=target_score,
+                                         max_rounds=max_rounds)
+        oc = np.where(rows["flags"] & 1, 0, rows["winner_seat"] + 1).astype(np.uint8)
+        oc |= np.where(rows["flags"] & ~np.uint8(1), 0x80, 0).astype(np.uint8)
+        return torch.from_numpy(oc), torch.from_numpy(n_attempts.astype(np.int64)), None, torch.from_numpy(totals)
+
+    def h2h_resolve(self, d_n_attempts, outcome, required, progress):
+        na = d_n_attempts.numpy()
+        oc = outcome.numpy()
+        prog = np.array(progress, dtype=np.int32).reshape(-1, 5)
+        off = 0
+        for b in range(len(na)):
+            for o in oc[off:off + int(na[b])] & 0x7F:
+                if prog[b, 1] >= required[b]:
+                    break
+                prog[b, 0] += 1
+                if o == 0:
+                    prog[b, 2] += 1
+                else:
+                    prog[b, 1] += 1
+                    prog[b, 2 + int(o)] += 1
+            off += int(na[b])
+        return prog

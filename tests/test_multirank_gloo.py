@@ -1,0 +1,91 @@
+"""N>1 path on CPU: two `gloo` ranks shard a (root, k) cell by deterministic batch and merge the
+tally tensors with the same all-reduce the GPUs use over NCCL (run_tournament.run_cell).
+
+The per-rank launches are served by the oracle here (no GPU in this container); what is under
+test is the partition (disjoint coordinate ranges, every shuffle played exactly once), the
+ranks-without-work case and the merge.
+"""
+
+from __future__ import annotations
+
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parents[1]
+for p in (str(ROOT), str(ROOT / "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _oracle_launch(root_seed, k, shuffle0, n_shuffles, table, tallies, totals):
+    import oracle
+
+    t, tot, _ = oracle.play_tournament(root_seed, k, shuffle0, n_shuffles, table, n_threads=1)
+    tt, to = torch.from_numpy(t), torch.from_numpy(tot)
+    if tallies is not None:
+        tt += tallies
+        to += totals
+    return tt, to
+
+
+def _worker(rank: int, world: int, port: int, num_shuffles: int, batch: int, out_dir: str) -> None:
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from farkle_ii_b200 import run_tournament as frt
+        from farkle_ii_b200.strategies import generate_strategy_grid, pack_strategies
+
+        table = pack_strategies(generate_strategy_grid(
+            score_thresholds=[250, 300, 350, 400], smart_five_opts=[True], smart_one_opts=[True],
+            consider_score_opts=[True], consider_dice_opts=[True], auto_hot_dice_opts=[True],
+            run_up_score_opts=[True])[0])
+        launches = []
+
+        def launch(*a):
+            launches.append((a[2], a[3]))
+            return _oracle_launch(*a)
+
+        tallies, totals = frt.run_cell(42, 2, num_shuffles, table, batch_size=batch, launch=launch,
+                                       rank=dist.get_rank(), world=dist.get_world_size())
+        np.savez(Path(out_dir) / f"rank{rank}.npz", tallies=tallies.numpy(), totals=totals.numpy(),
+                 launches=np.array(launches, dtype=np.int64).reshape(-1, 2))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("num_shuffles,batch", [(50, 8), (5, 30)])
+def test_two_ranks_equal_one(tmp_path, num_shuffles, batch):
+    import oracle
+
+    oracle.build()
+    mp.spawn(_worker, args=(2, _free_port(), num_shuffles, batch, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (np.load(tmp_path / f"rank{r}.npz") for r in (0, 1))
+    from farkle_ii_b200.strategies import generate_strategy_grid, pack_strategies
+
+    table = pack_strategies(generate_strategy_grid(
+        score_thresholds=[250, 300, 350, 400], smart_five_opts=[True], smart_one_opts=[True],
+        consider_score_opts=[True], consider_dice_opts=[True], auto_hot_dice_opts=[True],
+        run_up_score_opts=[True])[0])
+    want_t, want_tot, _ = oracle.play_tournament(42, 2, 0, num_shuffles, table, n_threads=2)
+    for r in (r0, r1):                                   # every rank holds the merged cell
+        assert np.array_equal(r["tallies"], want_t)
+        assert np.array_equal(r["totals"], want_tot)
+    played = sorted(s for r in (r0, r1) for s0, n in r["launches"] for s in range(s0, s0 + n))
+    assert played == list(range(num_shuffles))           # disjoint and complete
+    if num_shuffles <= batch:
+        assert len(r1["launches"]) == 0                  # a rank without work still reduces
