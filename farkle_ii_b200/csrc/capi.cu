@@ -95,14 +95,15 @@ struct Workspace {
     uint32_t* header;
     uint64_t* game_seed;
     int32_t* limits;
-    unsigned int* counter;
+    unsigned int* counter;  // [0] play ordinal, [1] number of HDR_LONG games
+    uint32_t* long_list;    // [n_games] worst case
     uint8_t* extra;  // mode specific tail (perm / h2h tables)
     size_t extra_bytes;
 };
 
 size_t ws_core_bytes(int k, uint64_t n) {
     return align_up(n * (uint64_t)k * sizeof(SeatMut), 256) + align_up(n * (uint64_t)k * sizeof(SeatImm), 256) +
-           align_up(n * 4, 256) + align_up(n * 8, 256) + align_up(n * 8, 256) + 256;
+           align_up(n * 4, 256) + align_up(n * 8, 256) + align_up(n * 8, 256) + 256 + align_up(n * 4, 256);
 }
 
 bool carve(void* base, size_t bytes, int k, uint64_t n, Workspace& w) {
@@ -121,6 +122,8 @@ bool carve(void* base, size_t bytes, int k, uint64_t n, Workspace& w) {
     p += align_up(n * 8, 256);
     w.counter = reinterpret_cast<unsigned int*>(p);
     p += 256;
+    w.long_list = reinterpret_cast<uint32_t*>(p);
+    p += align_up(n * 4, 256);
     w.extra = p;
     w.extra_bytes = bytes - core;
     return true;
@@ -141,7 +144,27 @@ __device__ __forceinline__ void store_seat(SeatMut* mut, SeatImm* imm, const Pcg
     const uint2 sv = reinterpret_cast<const uint2*>(table)[strat_index];
     uint4* i = reinterpret_cast<uint4*>(imm);
     i[0] = make_uint4((uint32_t)g.ilo, (uint32_t)(g.ilo >> 32), (uint32_t)g.ihi, (uint32_t)(g.ihi >> 32));
-    i[1] = make_uint4(sv.x, sv.y, strat_index, 0u);
+    i[1] = make_uint4(sv.x, sv.y, strat_index, disc_base(sv.y));
+}
+
+// Longest-first scheduling hint: the lanes of a warp that hold a game whose seats can never
+// bank append its ordinal to the long list (one atomic per warp) and every game's header is
+// initialised.  Must be called by all 32 lanes of the warp.
+__device__ __forceinline__ void publish_game(bool owns_game, bool is_long, uint32_t g, uint32_t* header,
+                                             uint32_t* long_list, unsigned int* counter) {
+    const uint32_t m = __ballot_sync(0xffffffffu, owns_game && is_long);
+    if (owns_game) header[g] = is_long ? HDR_LONG : 0u;
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        unsigned int base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(&counter[1], (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (owns_game && is_long) long_list[base + __popc(m & ((1u << lane) - 1u))] = g;
+    }
+}
+__device__ __forceinline__ bool entry_never_banks(const fb_strategy_t* table, uint32_t index) {
+    const uint2 sv = reinterpret_cast<const uint2*>(table)[index];
+    return never_banks((int)(int16_t)(sv.y & 0xffffu), sv.y >> 16);
 }
 
 __device__ __forceinline__ uint64_t coord_fingerprint(const Coord& c, bool as_u32) {
@@ -156,35 +179,43 @@ __global__ void __launch_bounds__(256) seed_tournament_kernel(
     uint64_t root, int k, uint64_t shuffle0, uint32_t gps, uint64_t n_games, const int32_t* perm,
     int n_strategies, int32_t target, int32_t max_rounds, const uint64_t* ov_shuffle,
     const uint32_t* ov_game, const int32_t* ov_rounds, int n_ov, int want_seeds,
-    const fb_strategy_t* table, SeatMut* mut, SeatImm* imm, uint64_t* game_seed, int32_t* limits) {
+    const fb_strategy_t* table, SeatMut* mut, SeatImm* imm, uint64_t* game_seed, int32_t* limits,
+    uint32_t* header, uint32_t* long_list, unsigned int* counter) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_games * (uint64_t)k) return;
-    const uint64_t g = t / (uint64_t)k;
+    const bool live = t < n_games * (uint64_t)k;
+    const uint64_t g = live ? t / (uint64_t)k : 0;
     const uint32_t s = (uint32_t)(t - g * (uint64_t)k);
     const uint64_t sl = g / gps;
     const uint32_t gi = (uint32_t)(g - sl * gps);
-    Coord c{FB_PURPOSE_TOURNAMENT_PLAYER, root, (uint64_t)k, shuffle0 + sl, 0, 0, gi, s, 0};
-    Pcg pg;
-    pcg_seed_coord(pg, c);
-    store_seat(mut + t, imm + t, pg, table, (uint32_t)perm[sl * (uint64_t)n_strategies + (uint64_t)gi * k + s]);
-    if (s == 0) {
-        if (want_seeds) {
-            Coord gc = c;
-            gc.purpose = FB_PURPOSE_TOURNAMENT_GAME;
-            gc.seat_index = 0;
-            game_seed[g] = coord_fingerprint(gc, true);
-        }
-        if (limits) {
-            int32_t mr = max_rounds;
-            for (int o = 0; o < n_ov; o++)
-                if (ov_shuffle[o] == shuffle0 + sl && ov_game[o] == gi) {
-                    mr = ov_rounds[o];
-                    break;
-                }
-            limits[2 * g] = target;
-            limits[2 * g + 1] = mr;
+    bool is_long = false;
+    if (live) {
+        Coord c{FB_PURPOSE_TOURNAMENT_PLAYER, root, (uint64_t)k, shuffle0 + sl, 0, 0, gi, s, 0};
+        Pcg pg;
+        pcg_seed_coord(pg, c);
+        const int32_t* seats = perm + sl * (uint64_t)n_strategies + (uint64_t)gi * k;
+        store_seat(mut + t, imm + t, pg, table, (uint32_t)seats[s]);
+        if (s == 0) {
+            is_long = true;
+            for (int j = 0; j < k; j++) is_long = is_long && entry_never_banks(table, (uint32_t)seats[j]);
+            if (want_seeds) {
+                Coord gc = c;
+                gc.purpose = FB_PURPOSE_TOURNAMENT_GAME;
+                gc.seat_index = 0;
+                game_seed[g] = coord_fingerprint(gc, true);
+            }
+            if (limits) {
+                int32_t mr = max_rounds;
+                for (int o = 0; o < n_ov; o++)
+                    if (ov_shuffle[o] == shuffle0 + sl && ov_game[o] == gi) {
+                        mr = ov_rounds[o];
+                        break;
+                    }
+                limits[2 * g] = target;
+                limits[2 * g + 1] = mr;
+            }
         }
     }
+    publish_game(live && s == 0, is_long, (uint32_t)g, header, long_list, counter);
 }
 
 // Exclusive prefix sum of n_attempts (single block; n_blocks is at most ~1e5).
@@ -217,40 +248,57 @@ __global__ void __launch_bounds__(256) seed_h2h_kernel(
     uint64_t root, int n_blocks, const uint64_t* pair_id, const uint8_t* order,
     const fb_strategy_t* seat1, const fb_strategy_t* seat2, const uint32_t* attempt0,
     const uint64_t* offsets, uint64_t total, int want_seeds, SeatMut* mut, SeatImm* imm,
-    uint64_t* game_seed) {
+    uint64_t* game_seed, uint32_t* header, uint32_t* long_list, unsigned int* counter) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total * 2) return;
-    const uint64_t g = t >> 1;
+    const bool live = t < total * 2;
+    const uint64_t g = live ? t >> 1 : 0;
     const uint32_t s = (uint32_t)(t & 1);
-    int lo = 0, hi = n_blocks - 1;  // last block with offsets[b] <= g
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (offsets[mid] <= g) lo = mid; else hi = mid - 1;
+    bool is_long = false;
+    if (live) {
+        int lo = 0, hi = n_blocks - 1;  // last block with offsets[b] <= g
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (offsets[mid] <= g) lo = mid; else hi = mid - 1;
+        }
+        const int b = lo;
+        const uint64_t a = (uint64_t)attempt0[b] + (g - offsets[b]);
+        Coord c{FB_PURPOSE_H2H_PLAYER, root, 2, 0, pair_id[b], order[b], a, s, 0};
+        Pcg pg;
+        pcg_seed_coord(pg, c);
+        store_seat(mut + t, imm + t, pg, s ? seat2 : seat1, (uint32_t)b);
+        if (s == 0) {
+            is_long = entry_never_banks(seat1, (uint32_t)b) && entry_never_banks(seat2, (uint32_t)b);
+            if (want_seeds) {
+                Coord gc = c;
+                gc.purpose = FB_PURPOSE_H2H_GAME;
+                game_seed[g] = coord_fingerprint(gc, false);
+            }
+        }
     }
-    const int b = lo;
-    const uint64_t a = (uint64_t)attempt0[b] + (g - offsets[b]);
-    Coord c{FB_PURPOSE_H2H_PLAYER, root, 2, 0, pair_id[b], order[b], a, s, 0};
-    Pcg pg;
-    pcg_seed_coord(pg, c);
-    store_seat(mut + t, imm + t, pg, s ? seat2 : seat1, (uint32_t)b);
-    if (s == 0 && want_seeds) {
-        Coord gc = c;
-        gc.purpose = FB_PURPOSE_H2H_GAME;
-        game_seed[g] = coord_fingerprint(gc, false);
-    }
+    publish_game(live && s == 0, is_long, (uint32_t)g, header, long_list, counter);
 }
 
 __global__ void __launch_bounds__(256) seed_explicit_kernel(const uint64_t* coords, uint64_t n_games, int k,
                                                             const fb_strategy_t* seat_table, SeatMut* mut,
-                                                            SeatImm* imm) {
+                                                            SeatImm* imm, uint32_t* header,
+                                                            uint32_t* long_list, unsigned int* counter) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_games * (uint64_t)k) return;
-    const uint64_t g = t / (uint64_t)k;
-    const uint64_t* cc = coords + g * 7;
-    Coord c{(uint32_t)cc[0], cc[1], cc[2], cc[3], cc[4], cc[5], cc[6], t - g * (uint64_t)k, 0};
-    Pcg pg;
-    pcg_seed_coord(pg, c);
-    store_seat(mut + t, imm + t, pg, seat_table, (uint32_t)t);
+    const bool live = t < n_games * (uint64_t)k;
+    const uint64_t g = live ? t / (uint64_t)k : 0;
+    const uint32_t s = (uint32_t)(t - g * (uint64_t)k);
+    bool is_long = false;
+    if (live) {
+        const uint64_t* cc = coords + g * 7;
+        Coord c{(uint32_t)cc[0], cc[1], cc[2], cc[3], cc[4], cc[5], cc[6], s, 0};
+        Pcg pg;
+        pcg_seed_coord(pg, c);
+        store_seat(mut + t, imm + t, pg, seat_table, (uint32_t)t);
+        if (s == 0) {
+            is_long = true;
+            for (int j = 0; j < k; j++) is_long = is_long && entry_never_banks(seat_table, (uint32_t)(t + j));
+        }
+    }
+    publish_game(live && s == 0, is_long, (uint32_t)g, header, long_list, counter);
 }
 
 __global__ void pack_limits_kernel(const int32_t* tv, int32_t t0, const int32_t* mv, int32_t m0,
@@ -547,13 +595,15 @@ int launch_play(const PlayParams& P, const FinishParams& F, cudaStream_t stream)
         }
     }
     const size_t smem = (LUT_BYTES + 15) & ~15;
-    FB_CUDA(cudaMemsetAsync(P.counter, 0, sizeof(unsigned int), stream));
     if (!t_ev0) {
         FB_CUDA(cudaEventCreate(&t_ev0));
         FB_CUDA(cudaEventCreate(&t_ev1));
     }
     FB_CUDA(cudaEventRecord(t_ev0, stream));
-    play_kernel<1024><<<grid, warps * 32, smem, stream>>>(P, g_ctx.lut_dev);
+    if (P.limits)
+        play_kernel<1024, true><<<grid, warps * 32, smem, stream>>>(P, g_ctx.lut_dev);
+    else
+        play_kernel<1024, false><<<grid, warps * 32, smem, stream>>>(P, g_ctx.lut_dev);
     int rc = launch_check("play_kernel");
     if (rc) return rc;
     FB_CUDA(cudaEventRecord(t_ev1, stream));
@@ -725,10 +775,11 @@ int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuff
     int rc = fb_permute_shuffles(root_seed, k, shuffle0, n_shuffles, n_strategies, perm, stream);
     if (rc) return rc;
     int32_t* limits = n_overrides > 0 ? w.limits : nullptr;
+    FB_CUDA(cudaMemsetAsync(w.counter, 0, 2 * sizeof(unsigned int), stream));
     seed_tournament_kernel<<<blocks_for(n_games * k, 256), 256, 0, stream>>>(
         root_seed, k, shuffle0, gps, n_games, perm, n_strategies, target_score, max_rounds,
         override_shuffle_dev, override_game_dev, override_max_rounds_dev, n_overrides, want_game_seeds,
-        strategies_dev, w.mut, w.imm, w.game_seed, limits);
+        strategies_dev, w.mut, w.imm, w.game_seed, limits, w.header, w.long_list, w.counter);
     rc = launch_check("seed_tournament_kernel");
     if (rc) return rc;
     PlayParams P{};
@@ -742,6 +793,7 @@ int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuff
     P.k = k;
     P.totals = reinterpret_cast<unsigned long long*>(totals_dev);
     P.counter = w.counter;
+    P.long_list = w.long_list;
     FinishParams F{};
     F.mut = w.mut;
     F.imm = w.imm;
@@ -780,9 +832,10 @@ int fb_play_h2h(uint64_t root_seed, int n_blocks, const uint64_t* pair_id_dev, c
     int rc = launch_check("h2h_offsets_kernel");
     if (rc) return rc;
     const int want_seeds = rows_dev != nullptr;
+    FB_CUDA(cudaMemsetAsync(w.counter, 0, 2 * sizeof(unsigned int), stream));
     seed_h2h_kernel<<<blocks_for(total_attempts * 2, 256), 256, 0, stream>>>(
         root_seed, n_blocks, pair_id_dev, order_dev, seat1_dev, seat2_dev, attempt0_dev, offsets,
-        total_attempts, want_seeds, w.mut, w.imm, w.game_seed);
+        total_attempts, want_seeds, w.mut, w.imm, w.game_seed, w.header, w.long_list, w.counter);
     rc = launch_check("seed_h2h_kernel");
     if (rc) return rc;
     PlayParams P{};
@@ -795,6 +848,7 @@ int fb_play_h2h(uint64_t root_seed, int n_blocks, const uint64_t* pair_id_dev, c
     P.k = 2;
     P.totals = reinterpret_cast<unsigned long long*>(totals_dev);
     P.counter = w.counter;
+    P.long_list = w.long_list;
     FinishParams F{};
     F.mut = w.mut;
     F.imm = w.imm;
@@ -841,8 +895,9 @@ int fb_play_games(const uint64_t* coords_dev, uint64_t n_games, int k,
     Workspace w;
     if (!carve(workspace_dev, workspace_bytes, k, n_games, w))
         return fail(FB_ERR_WORKSPACE, "workspace too small: need %zu bytes", ws_core_bytes(k, n_games));
-    seed_explicit_kernel<<<blocks_for(n_games * k, 256), 256, 0, stream>>>(coords_dev, n_games, k,
-                                                                          seat_strategies_dev, w.mut, w.imm);
+    FB_CUDA(cudaMemsetAsync(w.counter, 0, 2 * sizeof(unsigned int), stream));
+    seed_explicit_kernel<<<blocks_for(n_games * k, 256), 256, 0, stream>>>(
+        coords_dev, n_games, k, seat_strategies_dev, w.mut, w.imm, w.header, w.long_list, w.counter);
     int rc = launch_check("seed_explicit_kernel");
     if (rc) return rc;
     int32_t* limits = nullptr;
@@ -864,6 +919,7 @@ int fb_play_games(const uint64_t* coords_dev, uint64_t n_games, int k,
     P.k = k;
     P.totals = reinterpret_cast<unsigned long long*>(totals_dev);
     P.counter = w.counter;
+    P.long_list = w.long_list;
     FinishParams F{};
     F.mut = w.mut;
     F.imm = w.imm;

@@ -14,7 +14,9 @@
 //                  turns|hot, sf uses|dice, so uses|dice, pad
 //   SeatImm  32 B  PCG increment (16 B) | score_threshold, dice_threshold|flags,
 //                  strategy table index, pad
-//   game header 4 B  n_rounds | flags << 16, written when the game ends
+//   game header 4 B  n_rounds | flags << 16 | HDR_LONG, written when the game ends; the seed
+//                    kernels pre-set HDR_LONG on games that are certain to run to the safety
+//                    limit so that play_kernel starts them first (longest-first scheduling)
 // The active seat lives in registers; a turn switch is three 16-byte stores of the
 // outgoing SeatMut and five 16-byte loads of the incoming seat.  The records of all
 // games in flight (148 SMs x 1,024 lanes x k seats x 80 B) stay L2-resident, so the
@@ -41,6 +43,7 @@ constexpr uint32_t HIGH_MASK = 0x3fffffffu;
 constexpr uint32_t HW_HAS32 = 1u << 30;
 constexpr uint32_t HW_SCORED = 1u << 31;
 constexpr uint32_t FULL = 0xffffffffu;
+constexpr uint32_t HDR_LONG = 1u << 31;
 
 struct __align__(16) SeatMut {
     uint32_t lo0, lo1, hi0, hi1;    // PCG state
@@ -49,7 +52,8 @@ struct __align__(16) SeatMut {
 };
 struct __align__(16) SeatImm {
     uint32_t ilo0, ilo1, ihi0, ihi1;  // PCG increment
-    uint32_t st, p1, strat, pad;      // score_threshold | (u16)dice_threshold|flags<<16 | table index
+    uint32_t st, p1, strat, dbase;    // score_threshold | (u16)dice_threshold|flags<<16 | table index |
+                                      // discard-table base of the strategy (disc_base)
 };
 static_assert(sizeof(SeatMut) == 48 && sizeof(SeatImm) == 32, "seat record layout");
 
@@ -62,12 +66,13 @@ struct PlayParams {
     uint32_t n_games;
     int k;
     unsigned long long* totals;  // [FB_TOTALS_WIDTH] or nullptr (dice / rng words only)
-    unsigned int* counter;
+    unsigned int* counter;       // [0] next ordinal (zeroed per launch), [1] number of HDR_LONG games
+    const uint32_t* long_list;   // [counter[1]] ordinals of the HDR_LONG games
 };
 
 enum LaneStatus { ST_NEED = 0, ST_LOAD = 1, ST_PLAY = 2, ST_DEAD = 3 };
 
-template <int MAXT>
+template <int MAXT, bool LIMITS>
 __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const ScoreLut* __restrict__ lut_g) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ unsigned long long s_tot[2];
@@ -80,11 +85,16 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
     const int lane = threadIdx.x & 31;
     const int k = P.k;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    // Ordinals [0, n_long) walk the long list, [n_long, n_long + n_games) walk every game and
+    // skip the ones the long list already covered.
+    const uint32_t n_long = P.counter[1];
+    const uint32_t n_ordinals = P.n_games + n_long;
 
     // ---- per-lane game state ------------------------------------------------
     int status = ST_NEED;
     uint32_t g = 0, err = 0;
-    int seat = 0, round = 0, trigger = -1, stb = 0, target = 0, max_rounds = 0;
+    int seat = 0, round = 0, trigger = -1, stb = 0;
+    int target = P.target_score, max_rounds = P.max_rounds;
     // active seat (SeatMut / SeatImm in registers)
     Pcg rng{0, 0, 0, 0};
     uint32_t saved = 0, hw = 0;
@@ -103,19 +113,30 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
             base = __shfl_sync(FULL, base, 0);
             if (status == ST_NEED) {
                 const uint32_t ng = base + (uint32_t)__popc(need & lt_mask);
-                if (ng < P.n_games) {
-                    g = ng;
-                    seat = 0;
-                    round = 0;
-                    trigger = -1;
-                    err = 0;
-                    target = P.limits ? P.limits[2 * (size_t)g] : P.target_score;
-                    max_rounds = P.limits ? P.limits[2 * (size_t)g + 1] : P.max_rounds;
-                    stb = target;
-                    if (max_rounds <= 0) {  // `while rounds < max_rounds` never runs (engine.py:455)
-                        P.header[g] = (uint32_t)FB_ROW_SAFETY_LIMIT << 16;
+                if (ng < n_ordinals) {
+                    bool take = true;
+                    if (ng < n_long) {
+                        g = P.long_list[ng];
+                        err = HDR_LONG;  // carried into the header (bit 31), not a row flag
                     } else {
-                        status = ST_LOAD;
+                        g = ng - n_long;
+                        err = 0;
+                        take = !(__ldcg(&P.header[g]) & HDR_LONG);  // already played from the list
+                    }
+                    if (take) {
+                        seat = 0;
+                        round = 0;
+                        trigger = -1;
+                        if (LIMITS) {
+                            target = P.limits[2 * (size_t)g];
+                            max_rounds = P.limits[2 * (size_t)g + 1];
+                        }
+                        stb = target;
+                        if (max_rounds <= 0) {  // `while rounds < max_rounds` never runs (engine.py:455)
+                            P.header[g] = ((uint32_t)FB_ROW_SAFETY_LIMIT << 16) | err;
+                        } else {
+                            status = ST_LOAD;
+                        }
                     }
                 } else {
                     status = ST_DEAD;
@@ -132,7 +153,7 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
             const uint4* ip = reinterpret_cast<const uint4*>(P.imm + rec);
             const uint4 m0 = __ldcg(mp), m1 = __ldcg(mp + 1), m2 = __ldcg(mp + 2);
             const uint4 i0 = __ldcg(ip);
-            const uint2 i1 = __ldcg(reinterpret_cast<const uint2*>(ip + 1));
+            const uint4 i1 = __ldcg(ip + 1);
             rng.lo = (uint64_t)m0.x | ((uint64_t)m0.y << 32);
             rng.hi = (uint64_t)m0.z | ((uint64_t)m0.w << 32);
             rng.ilo = (uint64_t)i0.x | ((uint64_t)i0.y << 32);
@@ -146,7 +167,7 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
             c_so = m2.z;
             st = (int)i1.x;
             p1 = i1.y;
-            dbase = disc_base(p1);
+            dbase = i1.w;
             dice = 6;
             ts = 0;
             rolls_turn = 0;
@@ -259,7 +280,7 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
             ts = farkle ? 0 : ts2;
             dice = ndice;
             if (!turn_over && rolls_turn >= ROLL_LIMIT) {  // engine.py:242-243 raises
-                err = FB_ROW_ROLL_LIMIT;
+                err |= FB_ROW_ROLL_LIMIT;
                 turn_over = true;
             }
 
@@ -297,10 +318,10 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
                     if (seat == trigger) seat++;
                     over = seat >= k;
                 }
-                if (err) over = true;
+                if (err & FB_ROW_ROLL_LIMIT) over = true;
                 if (over) {
-                    P.header[g] = (uint32_t)round |
-                                  (((trigger < 0 ? FB_ROW_SAFETY_LIMIT : 0u) | err) << 16);
+                    P.header[g] = (uint32_t)round | (err & HDR_LONG) |
+                                  (((trigger < 0 ? FB_ROW_SAFETY_LIMIT : 0u) | (err & 0xffu)) << 16);
                     status = ST_NEED;
                 } else {
                     status = ST_LOAD;
@@ -355,7 +376,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
     if (g < F.n_games) {
         const uint32_t hdr = F.header[g];
         const uint32_t rounds = hdr & 0xffffu;
-        uint32_t flags = hdr >> 16;
+        uint32_t flags = (hdr >> 16) & 0xffu;
         const bool safety = flags & FB_ROW_SAFETY_LIMIT;
         const SeatMut* mut = F.mut + (size_t)g * k;
         const SeatImm* imm = F.imm + (size_t)g * k;

@@ -127,6 +127,19 @@ inline void host_build_lut(ScoreLut& lut) {
                             }
 }
 
+// A strategy whose keep/bank rule can never say "bank": dice_left >= 1 always exceeds a
+// dice threshold <= 0, and that alone keeps it rolling when dice are the only criterion or
+// when both criteria must be met to stop (strategies.py:125-162).  Its turns end only in a
+// farkle, so a table of such strategies always runs to the safety limit.  Scheduling hint only.
+inline
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+bool never_banks(int dice_threshold, uint32_t flags) {
+    const bool cs = flags & FB_SF_CONSIDER_SCORE, cd = flags & FB_SF_CONSIDER_DICE;
+    return cd && dice_threshold <= 0 && (!cs || (flags & FB_SF_REQUIRE_BOTH));
+}
+
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t lut_lookup(const ScoreLut* lut, uint32_t hist) {
     const uint32_t a = lut->idxA[hist & 511u];
