@@ -142,9 +142,11 @@ __device__ __forceinline__ void store_seat(SeatMut* mut, SeatImm* imm, const Pcg
     m[1] = make_uint4(0u, 0u, 0u, 0u);
     m[2] = make_uint4(0u, 0u, 0u, 0u);
     const uint2 sv = reinterpret_cast<const uint2*>(table)[strat_index];
+    const SeatConsts sc = seat_consts((int)sv.x, (int)(int16_t)(sv.y & 0xffffu), sv.y >> 16);
     uint4* i = reinterpret_cast<uint4*>(imm);
     i[0] = make_uint4((uint32_t)g.ilo, (uint32_t)(g.ilo >> 32), (uint32_t)g.ihi, (uint32_t)(g.ihi >> 32));
-    i[1] = make_uint4(sv.x, sv.y, strat_index, disc_base(sv.y));
+    i[1] = make_uint4((uint32_t)sc.st_d, ((uint32_t)sc.dt_d & 0xffffu) | (sc.kf << IMM_KF_SHIFT), strat_index,
+                      sc.dbase | (sc.tab_off << 16));
 }
 
 // Longest-first scheduling hint: the lanes of a warp that hold a game whose seats can never
@@ -533,13 +535,12 @@ __global__ void default_score_kernel(const ScoreLut* lut, const uint8_t* faces, 
         const uint32_t f = faces[i * 6 + d];
         if (f) { hist += 1u << (3u * (f - 1u)); nd++; }
     }
-    const uint32_t e = lut_lookup(lut, hist);
+    const uint2 sv = reinterpret_cast<const uint2*>(strat)[i];
+    const SeatConsts sc = seat_consts((int)sv.x, (int)(int16_t)(sv.y & 0xffffu), sv.y >> 16);
+    const uint32_t e = lut_lookup(lut, sc.tab_off, hist);
     const int rscore = (int)(e & 127u) * 50;
     int used = (int)((e >> 7) & 7u);
-    const int sf = (int)((e >> 10) & 3u), so = (int)((e >> 12) & 3u);
-    const uint2 sv = reinterpret_cast<const uint2*>(strat)[i];
-    const uint32_t dd =
-        rscore ? smart_discards(lut, disc_base(sv.y), rscore, used, sf, so, nd, ts_pre[i], (int)sv.x, sv.y) : 0u;
+    const uint32_t dd = rscore ? smart_discards(lut, sc.dbase, e, nd, ts_pre[i], sc.st_d, sc.dt_d) : 0u;
     const int d5 = (int)(dd & 3u), d1 = (int)(dd >> 2);
     used -= d5 + d1;
     out[i * 5 + 0] = rscore - 50 * d5 - 100 * d1;
@@ -595,6 +596,12 @@ int launch_play(const PlayParams& P, const FinishParams& F, cudaStream_t stream)
         }
     }
     const size_t smem = (LUT_BYTES + 15) & ~15;
+    static bool smem_opted = false;
+    if (!smem_opted) {
+        FB_CUDA(cudaFuncSetAttribute(play_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FB_CUDA(cudaFuncSetAttribute(play_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_opted = true;
+    }
     if (!t_ev0) {
         FB_CUDA(cudaEventCreate(&t_ev0));
         FB_CUDA(cudaEventCreate(&t_ev1));

@@ -52,8 +52,8 @@ struct __align__(16) SeatMut {
 };
 struct __align__(16) SeatImm {
     uint32_t ilo0, ilo1, ihi0, ihi1;  // PCG increment
-    uint32_t st, p1, strat, dbase;    // score_threshold | (u16)dice_threshold|flags<<16 | table index |
-                                      // discard-table base of the strategy (disc_base)
+    uint32_t st_d, dtkf, strat, tabs;  // seat_consts(): st_d | (u16)dt_d | kf << 16 | table index |
+                                       // dbase | tab_off << 16
 };
 static_assert(sizeof(SeatMut) == 48 && sizeof(SeatImm) == 32, "seat record layout");
 
@@ -70,15 +70,18 @@ struct PlayParams {
     const uint32_t* long_list;   // [counter[1]] ordinals of the HDR_LONG games
 };
 
-enum LaneStatus { ST_NEED = 0, ST_LOAD = 1, ST_PLAY = 2, ST_DEAD = 3 };
+enum LaneStatus { ST_NEED = 0, ST_PLAY = 1, ST_DEAD = 2 };
+
+// kernel-side view of SeatImm's second line
+constexpr uint32_t IMM_KF_SHIFT = 16;  // w1 = (u16)dt_d | kf << 16,  w3 = dbase | tab_off << 16
 
 template <int MAXT, bool LIMITS>
 __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const ScoreLut* __restrict__ lut_g) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ unsigned long long s_tot[2];
     ScoreLut* lut = reinterpret_cast<ScoreLut*>(smem_raw);
-    for (int i = threadIdx.x; i < LUT_BYTES / 4; i += blockDim.x)
-        reinterpret_cast<uint32_t*>(lut)[i] = reinterpret_cast<const uint32_t*>(lut_g)[i];
+    for (int i = threadIdx.x; i < LUT_BYTES / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(lut)[i] = reinterpret_cast<const uint4*>(lut_g)[i];
     if (threadIdx.x < 2) s_tot[threadIdx.x] = 0ull;
     __syncthreads();
 
@@ -98,11 +101,39 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
     // active seat (SeatMut / SeatImm in registers)
     Pcg rng{0, 0, 0, 0};
     uint32_t saved = 0, hw = 0;
-    int score = 0, st = 0;
-    uint32_t c_fr = 0, c_th = 0, c_sf = 0, c_so = 0, p1 = 0, dbase = 0;
+    int score = 0, st_d = 0, dt_d = 0;
+    uint32_t c_fr = 0, c_th = 0, c_sf = 0, c_so = 0, kf = 0, dbase = 0, tab_off = 0;
     // active turn
     int ts = 0, dice = 6, rolls_turn = 0;
     uint32_t a_dice = 0, a_words = 0;
+
+    // Seat player `seat` of game g and start the turn (engine.py:229-240): five 16-byte loads.
+    auto seat_player = [&]() {
+        const uint32_t rec = g * (uint32_t)k + (uint32_t)seat;  // n_games * k < 2^32 (checked on the host)
+        const uint4* mp = reinterpret_cast<const uint4*>(P.mut + rec);
+        const uint4* ip = reinterpret_cast<const uint4*>(P.imm + rec);
+        const uint4 m0 = __ldcg(mp), m1 = __ldcg(mp + 1), m2 = __ldcg(mp + 2);
+        const uint4 i0 = __ldcg(ip), i1 = __ldcg(ip + 1);
+        rng.lo = (uint64_t)m0.x | ((uint64_t)m0.y << 32);
+        rng.hi = (uint64_t)m0.z | ((uint64_t)m0.w << 32);
+        rng.ilo = (uint64_t)i0.x | ((uint64_t)i0.y << 32);
+        rng.ihi = (uint64_t)i0.z | ((uint64_t)i0.w << 32);
+        saved = m1.x;
+        score = (int)m1.y;
+        hw = m1.z;
+        c_fr = m1.w;
+        c_th = m2.x + 1u;  // n_turns += 1 (engine.py:237)
+        c_sf = m2.y;
+        c_so = m2.z;
+        st_d = (int)i1.x;
+        dt_d = (int)(int16_t)(i1.y & 0xffffu);
+        kf = i1.y >> IMM_KF_SHIFT;
+        dbase = i1.w & 0xffffu;
+        tab_off = i1.w >> 16;
+        dice = 6;
+        ts = 0;
+        rolls_turn = 0;
+    };
 
     for (;;) {
         // ================= R: lane refill =====================================
@@ -125,7 +156,7 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
                     }
                     if (take) {
                         seat = 0;
-                        round = 0;
+                        round = 1;
                         trigger = -1;
                         if (LIMITS) {
                             target = P.limits[2 * (size_t)g];
@@ -135,7 +166,8 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
                         if (max_rounds <= 0) {  // `while rounds < max_rounds` never runs (engine.py:455)
                             P.header[g] = ((uint32_t)FB_ROW_SAFETY_LIMIT << 16) | err;
                         } else {
-                            status = ST_LOAD;
+                            seat_player();
+                            status = ST_PLAY;
                         }
                     }
                 } else {
@@ -144,35 +176,6 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
             }
         }
         if (__all_sync(FULL, status == ST_DEAD)) break;
-
-        // ================= L: seat the next player, start the turn ==============
-        if (status == ST_LOAD) {
-            if (trigger < 0 && seat == 0) round++;
-            const uint32_t rec = g * (uint32_t)k + (uint32_t)seat;  // n_games * k < 2^32 (checked on the host)
-            const uint4* mp = reinterpret_cast<const uint4*>(P.mut + rec);
-            const uint4* ip = reinterpret_cast<const uint4*>(P.imm + rec);
-            const uint4 m0 = __ldcg(mp), m1 = __ldcg(mp + 1), m2 = __ldcg(mp + 2);
-            const uint4 i0 = __ldcg(ip);
-            const uint4 i1 = __ldcg(ip + 1);
-            rng.lo = (uint64_t)m0.x | ((uint64_t)m0.y << 32);
-            rng.hi = (uint64_t)m0.z | ((uint64_t)m0.w << 32);
-            rng.ilo = (uint64_t)i0.x | ((uint64_t)i0.y << 32);
-            rng.ihi = (uint64_t)i0.z | ((uint64_t)i0.w << 32);
-            saved = m1.x;
-            score = (int)m1.y;
-            hw = m1.z;
-            c_fr = m1.w;
-            c_th = m2.x + 1u;  // n_turns += 1 (engine.py:237)
-            c_sf = m2.y;
-            c_so = m2.z;
-            st = (int)i1.x;
-            p1 = i1.y;
-            dbase = i1.w;
-            dice = 6;
-            ts = 0;
-            rolls_turn = 0;
-            status = ST_PLAY;
-        }
 
         // ================= P: one roll (straight-line, no divergent branches) =====
         if (status == ST_PLAY) {
@@ -213,12 +216,11 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
             const uint32_t H5 = (uint32_t)o3, H6 = (uint32_t)(o3 >> 32);
             uint32_t hist = 0;
             uint32_t minlo = 0xffffffffu;  // Lemire leftover; < 4 means NumPy redraws
-#define FB_DIE(i_, Ha_, Hb_)                                       \
-    {                                                              \
-        const uint32_t u_ = p ? (Hb_) : (Ha_);                     \
-        const uint64_t m_ = (uint64_t)u_ * 6u;                     \
-        minlo = min(minlo, (uint32_t)m_);                          \
-        if ((i_) < n) hist += 1u << (3u * (uint32_t)(m_ >> 32));   \
+#define FB_DIE(i_, Ha_, Hb_)                                               \
+    {                                                                      \
+        const uint32_t u_ = p ? (Hb_) : (Ha_);                             \
+        minlo = min(minlo, u_ * 6u);                                       \
+        if ((i_) < n) hist += 1u << (3u * __umulhi(u_, 6u));               \
     }
             FB_DIE(0, saved, H1)
             FB_DIE(1, H1, H2)
@@ -251,12 +253,11 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
             a_words += words;
 
             // -- score the roll (engine.py:103-147), discards, counters
-            const uint32_t e = lut_lookup(lut, hist);
+            const uint32_t e = lut_lookup(lut, tab_off, hist);
             const int rscore = (int)(e & 127u) * 50;
             const int used0 = (int)((e >> 7) & 7u);
-            const int sf = (int)((e >> 10) & 3u), so = (int)((e >> 12) & 3u);
             const bool farkle = rscore == 0;
-            const uint32_t dd = smart_discards(lut, dbase, rscore, used0, sf, so, n, ts, st, p1);
+            const uint32_t dd = smart_discards(lut, dbase, e, n, ts, st_d, dt_d);
             const uint32_t d5 = dd & 3u, d1 = dd >> 2;  // both 0 on a farkle
             const int pts = rscore - 50 * (int)d5 - 100 * (int)d1;
             const int used = used0 - (int)d5 - (int)d1;
@@ -268,14 +269,14 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
             const int ts2 = ts + pts;
             // -- hot dice (engine.py:149-154), then _should_continue (engine.py:156-205) and
             //    ThresholdStrategy.decide (strategies.py:212-275)
-            const bool hot = !farkle && ndice == 6 && strat_flag(p1, FB_SF_AUTO_HOT_DICE);
+            const bool hot = !farkle && ndice == 6 && (kf & KF_AUTO_HOT);
             c_th += hot ? 0x10000u : 0u;
             const bool fin = trigger >= 0;
             const int rt = score + ts2;
             const bool behind = fin && rt <= stb;
-            const bool stop_ahead = fin && rt > stb && !strat_flag(p1, FB_SF_RUN_UP_SCORE);
+            const bool stop_ahead = fin && rt > stb && !(kf & KF_RUN_UP);
             const bool gate = !(hw & HW_SCORED) && ts2 < 500;
-            const bool keep = !stop_ahead && (gate || behind || decide_continue(ts2, ndice, st, p1));
+            const bool keep = !stop_ahead && (gate || behind || decide_continue(ts2, ndice, st_d, dt_d, kf));
             bool turn_over = farkle || (!hot && !keep);
             ts = farkle ? 0 : ts2;
             dice = ndice;
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
                 turn_over = true;
             }
 
-            // ================= T: bank, park the seat, pick the next one ========
+            // ================= T: bank, park the seat, seat the next one ========
             if (turn_over) {
                 if (ts >= 500) hw |= HW_SCORED;  // entry turn (engine.py:266-267)
                 if (hw & HW_SCORED) {
@@ -297,34 +298,33 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
                                       (uint32_t)(rng.hi >> 32)));
                 __stcg(mp + 1, make_uint4(saved, (uint32_t)score, hw, c_fr));
                 __stcg(mp + 2, make_uint4(c_th, c_sf, c_so, 0u));
-                bool over;
+                bool over = (err & FB_ROW_ROLL_LIMIT) != 0u;
                 if (trigger < 0) {
                     if (score >= target) {  // first trigger starts the final round (engine.py:466-471)
                         trigger = seat;
                         stb = score;
                         seat = seat == 0 ? 1 : 0;
-                        over = seat >= k;
+                        over |= seat >= k;
                     } else {
                         seat++;
-                        over = false;
-                        if (seat == k) {
+                        if (seat == k) {  // next round, unless the safety limit is reached (engine.py:455)
                             seat = 0;
-                            over = round >= max_rounds;
+                            over |= round >= max_rounds;
+                            if (!over) round++;
                         }
                     }
                 } else {
                     if (score > stb) stb = score;  // engine.py:547-548
                     seat++;
                     if (seat == trigger) seat++;
-                    over = seat >= k;
+                    over |= seat >= k;
                 }
-                if (err & FB_ROW_ROLL_LIMIT) over = true;
                 if (over) {
                     P.header[g] = (uint32_t)round | (err & HDR_LONG) |
                                   (((trigger < 0 ? FB_ROW_SAFETY_LIMIT : 0u) | (err & 0xffu)) << 16);
                     status = ST_NEED;
                 } else {
-                    status = ST_LOAD;
+                    seat_player();
                 }
             }
         }

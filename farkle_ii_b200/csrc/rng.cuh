@@ -154,11 +154,37 @@ __host__ __device__ __forceinline__ uint64_t pcg_output(uint64_t hi, uint64_t lo
 // state = state * CHEAP_MULT + inc (mod 2^128)
 __host__ __device__ __forceinline__ void pcg_step(uint64_t& hi, uint64_t& lo, uint64_t ihi,
                                                   uint64_t ilo) {
+#ifdef __CUDA_ARCH__
+    // 128 x 64 -> 128 multiply-add as one carry chain over 32-bit limbs: seven multiplies
+    // (ptxas fuses the lo/hi pairs into IMAD.WIDE) and no compare/select carry fix-ups,
+    // which moves the step from the ALU pipe to the FMA pipe.
+    const uint32_t s0 = (uint32_t)lo, s1 = (uint32_t)(lo >> 32), s2 = (uint32_t)hi, s3 = (uint32_t)(hi >> 32);
+    const uint32_t i0 = (uint32_t)ilo, i1 = (uint32_t)(ilo >> 32), i2 = (uint32_t)ihi, i3 = (uint32_t)(ihi >> 32);
+    const uint32_t m0 = (uint32_t)PCG_CHEAP_MULT, m1 = (uint32_t)(PCG_CHEAP_MULT >> 32);
+    uint32_t r0, r1, r2, r3;
+    asm("mad.lo.cc.u32   %0, %4, %8, %10;\n\t"   // r0  = lo(s0 m0) + i0
+        "madc.hi.cc.u32  %1, %4, %8, %11;\n\t"   // r1  = hi(s0 m0) + i1 + c
+        "madc.lo.cc.u32  %2, %5, %9, %12;\n\t"   // r2  = lo(s1 m1) + i2 + c
+        "madc.hi.u32     %3, %5, %9, %13;\n\t"   // r3  = hi(s1 m1) + i3 + c
+        "mad.lo.cc.u32   %1, %4, %9, %1;\n\t"    // r1 += lo(s0 m1)
+        "madc.hi.cc.u32  %2, %4, %9, %2;\n\t"    // r2 += hi(s0 m1) + c
+        "madc.lo.u32     %3, %6, %9, %3;\n\t"    // r3 += lo(s2 m1) + c
+        "mad.lo.cc.u32   %1, %5, %8, %1;\n\t"    // r1 += lo(s1 m0)
+        "madc.hi.cc.u32  %2, %5, %8, %2;\n\t"    // r2 += hi(s1 m0) + c
+        "madc.lo.u32     %3, %7, %8, %3;\n\t"    // r3 += lo(s3 m0) + c
+        "mad.lo.cc.u32   %2, %6, %8, %2;\n\t"    // r2 += lo(s2 m0)
+        "madc.hi.u32     %3, %6, %8, %3;\n\t"    // r3 += hi(s2 m0) + c
+        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3)
+        : "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(m0), "r"(m1), "r"(i0), "r"(i1), "r"(i2), "r"(i3));
+    lo = (uint64_t)r0 | ((uint64_t)r1 << 32);
+    hi = (uint64_t)r2 | ((uint64_t)r3 << 32);
+#else
     uint64_t plo = lo * PCG_CHEAP_MULT;
     uint64_t phi = FB_UMULHI(lo, PCG_CHEAP_MULT) + hi * PCG_CHEAP_MULT;
     uint64_t nlo = plo + ilo;
     hi = phi + ihi + (nlo < plo ? 1u : 0u);
     lo = nlo;
+#endif
 }
 
 // Sequential view with NumPy's persistent 32-bit half buffer (pcg64_cm_next32).

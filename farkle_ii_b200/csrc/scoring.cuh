@@ -6,13 +6,16 @@
 //   apply_discards                 src/farkle/game/scoring.py:548-578
 //   _decide_continue               src/farkle/simulation/strategies.py:125-162
 //
-// Layout of the lookup in shared memory (18,592 bytes per CTA):
-//   idxA[512] u8   packed 3-bit counts of faces 1,2,3 -> combo index 0..83
-//   idxB[512] u8   packed 3-bit counts of faces 4,5,6 -> combo index 0..83
-//   tab[84*84] u16 score/50 (7 bits) | used (3) | single_fives (2) | single_ones (2)
-//   disc[3456] u8  smart-discard decision, see disc_index()
+// Layout of the lookup in shared memory (99,520 bytes per CTA):
+//   idxA[512] u8      packed 3-bit counts of faces 1,2,3 -> combo index 0..83
+//   idxB[512] u8      packed 3-bit counts of faces 4,5,6 -> combo index 0..83
+//   tab[3][84*84] u32 one copy per smart-discard variant of the strategy (0 none, 1 smart five,
+//                     2 smart five + one): score/50 (7 bits) | used (3) | single_fives (2) |
+//                     single_ones (2) | bits 16..25 the roll-dependent part of the discard-table
+//                     index, premultiplied (see disc_index)
+//   disc[16*864] u8   smart-discard decision
 // A roll's histogram h = sum 1 << 3*(face-1) indexes it as
-//   tab[idxA[h & 511] * 84 + idxB[h >> 9]].
+//   tab[variant][idxA[h & 511] * 84 + idxB[h >> 9]].
 #pragma once
 #include <cstdint>
 
@@ -23,18 +26,56 @@ namespace fb {
 constexpr int LUT_COMBOS = 84;  // multisets of <= 6 dice over 3 faces = C(9,3)
 constexpr int LUT_IDX = 512;
 constexpr int LUT_TAB = LUT_COMBOS * LUT_COMBOS;
-// discard table: [favor_score 2][require_both 2][all_singles 2][sf 3][bmax 3][xs 8][yd 6]
-constexpr int DISC_INNER = 2 * 3 * 3 * 8 * 6;  // entries per (favor, both) pair = 864
-constexpr int LUT_DISC = 4 * DISC_INNER;       // 3,456
-constexpr int LUT_BYTES = 2 * LUT_IDX + 2 * LUT_TAB + LUT_DISC;  // 18,592
+constexpr int LUT_VARIANTS = 3;
+// discard table: [consider_score 2][consider_dice 2][favor_score 2][require_both 2] x
+//                [all_singles 2][sf 3][bm 3][xs 8][yd 6]
+constexpr int DISC_INNER = 2 * 3 * 3 * 8 * 6;  // entries per strategy class = 864
+constexpr int LUT_DISC = 16 * DISC_INNER;      // 13,824
+constexpr int LUT_BYTES = 2 * LUT_IDX + 4 * LUT_VARIANTS * LUT_TAB + LUT_DISC;  // 99,520
 
 struct ScoreLut {
     uint8_t idxA[LUT_IDX];
     uint8_t idxB[LUT_IDX];
-    uint16_t tab[LUT_TAB];
+    uint32_t tab[LUT_VARIANTS * LUT_TAB];
     uint8_t disc[LUT_DISC];
 };
 static_assert(sizeof(ScoreLut) == LUT_BYTES, "lut layout");
+
+// Strategy constants as the kernels keep them per seat (SeatImm, written at seeding):
+//   st_d  score threshold for BOTH the keep/bank rule and the discard search, -2^30 when the
+//         strategy does not consider score ("turn_score < st_d" is then never true; the discard
+//         sub-table of such a strategy ignores the score axis)
+//   dt_d  dice threshold, 127 when the strategy does not consider dice
+//   kf    KF_* flags
+//   dbase discard sub-table offset, tab_off score-table variant offset (elements)
+constexpr uint32_t KF_AND_MODE = 1u;  // both considered and NOT require_both: stop unless both say go
+constexpr uint32_t KF_AUTO_HOT = 2u;
+constexpr uint32_t KF_RUN_UP = 4u;
+constexpr int ST_NOT_CONSIDERED = -(1 << 30);
+constexpr int DT_NOT_CONSIDERED = 127;
+
+struct SeatConsts {
+    int st_d, dt_d;
+    uint32_t kf, dbase, tab_off;
+};
+inline
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+SeatConsts seat_consts(int score_threshold, int dice_threshold, uint32_t flags) {
+    const bool cs = flags & FB_SF_CONSIDER_SCORE, cd = flags & FB_SF_CONSIDER_DICE;
+    const bool rb = flags & FB_SF_REQUIRE_BOTH, fav = flags & FB_SF_FAVOR_SCORE;
+    const bool both = cs && cd && rb;
+    SeatConsts c;
+    c.st_d = cs ? score_threshold : ST_NOT_CONSIDERED;
+    c.dt_d = cd ? dice_threshold : DT_NOT_CONSIDERED;
+    c.kf = ((cs && cd && !rb) ? KF_AND_MODE : 0u) | ((flags & FB_SF_AUTO_HOT_DICE) ? KF_AUTO_HOT : 0u) |
+           ((flags & FB_SF_RUN_UP_SCORE) ? KF_RUN_UP : 0u);
+    c.dbase = (uint32_t)((((cs ? 2 : 0) + (cd ? 1 : 0)) * 2 + (fav ? 1 : 0)) * 2 + (both ? 1 : 0)) * DISC_INNER;
+    const int variant = (flags & FB_SF_SMART_FIVE) ? ((flags & FB_SF_SMART_ONE) ? 2 : 1) : 0;
+    c.tab_off = (uint32_t)variant * LUT_TAB;
+    return c;
+}
 
 struct RollScore {
     int score, used, sf, so;
@@ -83,21 +124,31 @@ inline void host_build_lut(ScoreLut& lut) {
                 lut.idxB[a | (b << 3) | (c << 6)] = (uint8_t)n;
                 n++;
             }
-    for (int i = 0; i < LUT_COMBOS; i++)
-        for (int j = 0; j < LUT_COMBOS; j++) {
-            int c[6] = {combo[i][0], combo[i][1], combo[i][2], combo[j][0], combo[j][1], combo[j][2]};
-            uint16_t e = 0;
-            if (c[0] + c[1] + c[2] + c[3] + c[4] + c[5] <= 6) {
-                RollScore r = host_evaluate_counts(c);
-                e = (uint16_t)((r.score / 50) | (r.used << 7) | (r.sf << 10) | (r.so << 12));
+    for (int v = 0; v < LUT_VARIANTS; v++)
+        for (int i = 0; i < LUT_COMBOS; i++)
+            for (int j = 0; j < LUT_COMBOS; j++) {
+                int c[6] = {combo[i][0], combo[i][1], combo[i][2], combo[j][0], combo[j][1], combo[j][2]};
+                const int nd = c[0] + c[1] + c[2] + c[3] + c[4] + c[5];
+                uint32_t e = 0;
+                if (nd <= 6) {
+                    RollScore r = host_evaluate_counts(c);
+                    e = (uint32_t)((r.score / 50) | (r.used << 7) | (r.sf << 10) | (r.so << 12));
+                    // decide_smart_discards (scoring.py:369-467): candidates exist only with
+                    // smart_five, unused dice left over and lone fives/ones to give back
+                    const bool on = v >= 1 && r.used != nd;
+                    const int sfi = on ? r.sf : 0, bm = (on && v == 2) ? r.so : 0;
+                    const int excl = r.score == 50 * sfi + 100 * bm ? 1 : 0;  // all-discard scores 0
+                    e |= (uint32_t)(((excl * 3 + sfi) * 3 + bm) * 48) << 16;
+                }
+                lut.tab[v * LUT_TAB + i * LUT_COMBOS + j] = e;
             }
-            lut.tab[i * LUT_COMBOS + j] = e;
-        }
     // Smart-discard table.  A candidate "drop a lone fives and b lone ones" loses
     // u = a + 2b units of 50 points and frees D = a + b dice; whether it must bank depends
     // only on u < xs (score threshold still met) and D < yd (dice threshold still met),
     // and the preference key is (-u, D) or (D, -u).  So the whole search of
-    // decide_smart_discards (scoring.py:303-467) is a function of seven small integers.
+    // decide_smart_discards (scoring.py:303-467) is a function of nine small integers.
+    for (int cs = 0; cs < 2; cs++)
+    for (int cd = 0; cd < 2; cd++)
     for (int fav = 0; fav < 2; fav++)
         for (int both = 0; both < 2; both++)
             for (int excl = 0; excl < 2; excl++)
@@ -111,7 +162,7 @@ inline void host_build_lut(ScoreLut& lut) {
                                     for (int b = 0; b <= bm; b++) {
                                         if (excl && a == sf && b == bm) continue;  // candidate scores 0
                                         const int u = a + 2 * b, D = a + b;
-                                        const bool hit_s = u < xs, hit_d = D < yd;
+                                        const bool hit_s = cs && u < xs, hit_d = cd && D < yd;
                                         if (both ? (hit_s && hit_d) : (hit_s || hit_d)) continue;
                                         const int k1 = fav ? -u : D, k2 = fav ? D : -u;
                                         if (!have || k1 > best_k1 || (k1 == best_k1 && k2 > best_k2)) {
@@ -121,7 +172,7 @@ inline void host_build_lut(ScoreLut& lut) {
                                             pick = a | (b << 2);
                                         }
                                     }
-                                const int idx = (fav * 2 + both) * DISC_INNER +
+                                const int idx = ((((cs * 2 + cd) * 2 + fav) * 2 + both) * DISC_INNER) +
                                                 ((excl * 3 + sf) * 3 + bm) * 48 + xs * 6 + yd;
                                 lut.disc[idx] = (uint8_t)pick;
                             }
@@ -141,22 +192,10 @@ bool never_banks(int dice_threshold, uint32_t flags) {
 }
 
 #ifdef __CUDACC__
-__device__ __forceinline__ uint32_t lut_lookup(const ScoreLut* lut, uint32_t hist) {
+__device__ __forceinline__ uint32_t lut_lookup(const ScoreLut* lut, uint32_t tab_off, uint32_t hist) {
     const uint32_t a = lut->idxA[hist & 511u];
     const uint32_t b = lut->idxB[hist >> 9];
-    return lut->tab[a * LUT_COMBOS + b];
-}
-
-// Strategy parameters as the kernels keep them: p0 = score_threshold,
-// p1 = (uint16)dice_threshold | flags << 16.
-__device__ __forceinline__ int strat_dice_threshold(uint32_t p1) { return (int)(int16_t)(p1 & 0xffffu); }
-__device__ __forceinline__ bool strat_flag(uint32_t p1, uint32_t f) { return (p1 >> 16) & f; }
-
-// Per-strategy part of the discard-table index: (favor_score * 2 + require_both) * 864.
-__device__ __forceinline__ uint32_t disc_base(uint32_t p1) {
-    const bool both = strat_flag(p1, FB_SF_CONSIDER_SCORE) && strat_flag(p1, FB_SF_CONSIDER_DICE) &&
-                      strat_flag(p1, FB_SF_REQUIRE_BOTH);
-    return ((strat_flag(p1, FB_SF_FAVOR_SCORE) ? 2u : 0u) + (both ? 1u : 0u)) * DISC_INNER;
+    return lut->tab[tab_off + a * LUT_COMBOS + b];
 }
 
 // decide_smart_discards (scoring.py:369-467) as ONE table lookup, branch free.
@@ -165,32 +204,25 @@ __device__ __forceinline__ uint32_t disc_base(uint32_t p1) {
 // the table gives score-50a-100b with used-a-b dice (no special 6-dice pattern can appear
 // because used != n).  With X = ts + score - score_threshold and Y = dice_threshold -
 // (n - used):  hit_score <=> consider_score and 50(a+2b) <= X,  hit_dice <=>
-// consider_dice and a+b <= Y.  xs / yd below count how many values of a+2b / a+b hit.
+// consider_dice and a+b <= Y.  xs / yd below count how many values of a+2b / a+b hit; the
+// (sf, so, all-singles) part of the index comes premultiplied from the score-table entry e
+// of the strategy's variant, the consider/favor/both part from the seat's dbase.
 // Returns d5 | d1 << 2.
-__device__ __forceinline__ uint32_t smart_discards(const ScoreLut* lut, uint32_t dbase, int score,
-                                                   int used, int sf, int so, int n, int ts,
-                                                   int st, uint32_t p1) {
-    const bool on = strat_flag(p1, FB_SF_SMART_FIVE) && used != n;
-    const int sfi = on ? sf : 0;
-    const int bm = (on && strat_flag(p1, FB_SF_SMART_ONE)) ? so : 0;
-    int xs = min(max(ts + score - st + 50, 0), 399);
+__device__ __forceinline__ uint32_t smart_discards(const ScoreLut* lut, uint32_t dbase, uint32_t e, int n,
+                                                   int ts, int st_d, int dt_d) {
+    const int score = (int)(e & 127u) * 50, used = (int)((e >> 7) & 7u);
+    int xs = min(max(ts + score - st_d + 50, 0), 399);
     xs = (xs * 1311) >> 16;  // floor(xs / 50) for 0 <= xs <= 399
-    xs = strat_flag(p1, FB_SF_CONSIDER_SCORE) ? xs : 0;
-    int yd = min(max(strat_dice_threshold(p1) - (n - used) + 1, 0), 5);
-    yd = strat_flag(p1, FB_SF_CONSIDER_DICE) ? yd : 0;
-    const int excl = score == 50 * sfi + 100 * bm ? 1 : 0;  // the all-discard candidate scores 0
-    return lut->disc[dbase + ((excl * 3 + sfi) * 3 + bm) * 48 + xs * 6 + yd];
+    const int yd = min(max(dt_d - (n - used) + 1, 0), 5);
+    return lut->disc[dbase + (e >> 16) + (uint32_t)(xs * 6 + yd)];
 }
 
-// _decide_continue (strategies.py:125-162), branch free: with only one threshold
-// considered the other "want" is false, so OR gives the single-threshold answer.
-__device__ __forceinline__ bool decide_continue(int ts, int dice, int st, uint32_t p1) {
-    const bool cs = strat_flag(p1, FB_SF_CONSIDER_SCORE);
-    const bool cd = strat_flag(p1, FB_SF_CONSIDER_DICE);
-    const bool want_s = cs && ts < st;
-    const bool want_d = cd && dice > strat_dice_threshold(p1);
-    const bool and_mode = cs && cd && !strat_flag(p1, FB_SF_REQUIRE_BOTH);
-    return and_mode ? (want_s && want_d) : (want_s || want_d);
+// _decide_continue (strategies.py:125-162), branch free on the seat constants: a threshold
+// that is not considered can never "want" to go on, so OR gives the single-threshold answer.
+__device__ __forceinline__ bool decide_continue(int ts, int dice, int st_d, int dt_d, uint32_t kf) {
+    const bool want_s = ts < st_d;
+    const bool want_d = dice > dt_d;
+    return (kf & KF_AND_MODE) ? (want_s && want_d) : (want_s || want_d);
 }
 #endif  // __CUDACC__
 
