@@ -90,8 +90,7 @@ inline int launch_check(const char* what) {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Workspace {
-    SeatMut* mut;
-    SeatImm* imm;
+    Seat* seats;
     uint32_t* header;
     uint64_t* game_seed;
     int32_t* limits;
@@ -102,7 +101,7 @@ struct Workspace {
 };
 
 size_t ws_core_bytes(int k, uint64_t n) {
-    return align_up(n * (uint64_t)k * sizeof(SeatMut), 256) + align_up(n * (uint64_t)k * sizeof(SeatImm), 256) +
+    return align_up(n * (uint64_t)k * sizeof(Seat), 256) +
            align_up(n * 4, 256) + align_up(n * 8, 256) + align_up(n * 8, 256) + 256 + align_up(n * 4, 256);
 }
 
@@ -110,10 +109,8 @@ bool carve(void* base, size_t bytes, int k, uint64_t n, Workspace& w) {
     uint8_t* p = static_cast<uint8_t*>(base);
     const size_t core = ws_core_bytes(k, n);
     if (bytes < core) return false;
-    w.mut = reinterpret_cast<SeatMut*>(p);
-    p += align_up(n * (uint64_t)k * sizeof(SeatMut), 256);
-    w.imm = reinterpret_cast<SeatImm*>(p);
-    p += align_up(n * (uint64_t)k * sizeof(SeatImm), 256);
+    w.seats = reinterpret_cast<Seat*>(p);
+    p += align_up(n * (uint64_t)k * sizeof(Seat), 256);
     w.header = reinterpret_cast<uint32_t*>(p);
     p += align_up(n * 4, 256);
     w.game_seed = reinterpret_cast<uint64_t*>(p);
@@ -135,18 +132,16 @@ bool carve(void* base, size_t bytes, int k, uint64_t n, Workspace& w) {
 // device helpers / kernels
 // ---------------------------------------------------------------------------
 // Fresh seat records: seeded stream, zero score / counters, the seat's strategy.
-__device__ __forceinline__ void store_seat(SeatMut* mut, SeatImm* imm, const Pcg& g, const fb_strategy_t* table,
+__device__ __forceinline__ void store_seat(Seat* seat, const Pcg& g, const fb_strategy_t* table,
                                            uint32_t strat_index) {
-    uint4* m = reinterpret_cast<uint4*>(mut);
-    m[0] = make_uint4((uint32_t)g.lo, (uint32_t)(g.lo >> 32), (uint32_t)g.hi, (uint32_t)(g.hi >> 32));
-    m[1] = make_uint4(0u, 0u, 0u, 0u);
-    m[2] = make_uint4(0u, 0u, 0u, 0u);
     const uint2 sv = reinterpret_cast<const uint2*>(table)[strat_index];
     const SeatConsts sc = seat_consts((int)sv.x, (int)(int16_t)(sv.y & 0xffffu), sv.y >> 16);
-    uint4* i = reinterpret_cast<uint4*>(imm);
-    i[0] = make_uint4((uint32_t)g.ilo, (uint32_t)(g.ilo >> 32), (uint32_t)g.ihi, (uint32_t)(g.ihi >> 32));
-    i[1] = make_uint4((uint32_t)sc.st_d, ((uint32_t)sc.dt_d & 0xffffu) | (sc.kf << IMM_KF_SHIFT), strat_index,
-                      sc.dbase | (sc.tab_off << 16));
+    seat->state = make_uint4((uint32_t)g.lo, (uint32_t)(g.lo >> 32), (uint32_t)g.hi, (uint32_t)(g.hi >> 32));
+    seat->a = make_uint4(0u, 0u, 0u, 0u);
+    seat->b = make_uint4(0u, 0u, 0u, 0u);
+    seat->inc = make_uint4((uint32_t)g.ilo, (uint32_t)(g.ilo >> 32), (uint32_t)g.ihi, (uint32_t)(g.ihi >> 32));
+    seat->cst = make_uint4((uint32_t)sc.st_d, sc.kf | ((uint32_t)sc.dt_d << CST_DT_SHIFT),
+                           sc.dbase | (sc.tab_off << 16), strat_index);
 }
 
 // Longest-first scheduling hint: the lanes of a warp that hold a game whose seats can never
@@ -181,7 +176,7 @@ __global__ void __launch_bounds__(256) seed_tournament_kernel(
     uint64_t root, int k, uint64_t shuffle0, uint32_t gps, uint64_t n_games, const int32_t* perm,
     int n_strategies, int32_t target, int32_t max_rounds, const uint64_t* ov_shuffle,
     const uint32_t* ov_game, const int32_t* ov_rounds, int n_ov, int want_seeds,
-    const fb_strategy_t* table, SeatMut* mut, SeatImm* imm, uint64_t* game_seed, int32_t* limits,
+    const fb_strategy_t* table, Seat* seats, uint64_t* game_seed, int32_t* limits,
     uint32_t* header, uint32_t* long_list, unsigned int* counter) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t < n_games * (uint64_t)k;
@@ -194,11 +189,11 @@ __global__ void __launch_bounds__(256) seed_tournament_kernel(
         Coord c{FB_PURPOSE_TOURNAMENT_PLAYER, root, (uint64_t)k, shuffle0 + sl, 0, 0, gi, s, 0};
         Pcg pg;
         pcg_seed_coord(pg, c);
-        const int32_t* seats = perm + sl * (uint64_t)n_strategies + (uint64_t)gi * k;
-        store_seat(mut + t, imm + t, pg, table, (uint32_t)seats[s]);
+        const int32_t* seat_ids = perm + sl * (uint64_t)n_strategies + (uint64_t)gi * k;
+        store_seat(seats + t, pg, table, (uint32_t)seat_ids[s]);
         if (s == 0) {
             is_long = true;
-            for (int j = 0; j < k; j++) is_long = is_long && entry_never_banks(table, (uint32_t)seats[j]);
+            for (int j = 0; j < k; j++) is_long = is_long && entry_never_banks(table, (uint32_t)seat_ids[j]);
             if (want_seeds) {
                 Coord gc = c;
                 gc.purpose = FB_PURPOSE_TOURNAMENT_GAME;
@@ -249,7 +244,7 @@ __global__ void h2h_offsets_kernel(const uint32_t* n_attempts, int n_blocks, uin
 __global__ void __launch_bounds__(256) seed_h2h_kernel(
     uint64_t root, int n_blocks, const uint64_t* pair_id, const uint8_t* order,
     const fb_strategy_t* seat1, const fb_strategy_t* seat2, const uint32_t* attempt0,
-    const uint64_t* offsets, uint64_t total, int want_seeds, SeatMut* mut, SeatImm* imm,
+    const uint64_t* offsets, uint64_t total, int want_seeds, Seat* seats,
     uint64_t* game_seed, uint32_t* header, uint32_t* long_list, unsigned int* counter) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t < total * 2;
@@ -267,7 +262,7 @@ __global__ void __launch_bounds__(256) seed_h2h_kernel(
         Coord c{FB_PURPOSE_H2H_PLAYER, root, 2, 0, pair_id[b], order[b], a, s, 0};
         Pcg pg;
         pcg_seed_coord(pg, c);
-        store_seat(mut + t, imm + t, pg, s ? seat2 : seat1, (uint32_t)b);
+        store_seat(seats + t, pg, s ? seat2 : seat1, (uint32_t)b);
         if (s == 0) {
             is_long = entry_never_banks(seat1, (uint32_t)b) && entry_never_banks(seat2, (uint32_t)b);
             if (want_seeds) {
@@ -281,8 +276,8 @@ __global__ void __launch_bounds__(256) seed_h2h_kernel(
 }
 
 __global__ void __launch_bounds__(256) seed_explicit_kernel(const uint64_t* coords, uint64_t n_games, int k,
-                                                            const fb_strategy_t* seat_table, SeatMut* mut,
-                                                            SeatImm* imm, uint32_t* header,
+                                                            const fb_strategy_t* seat_table, Seat* seats,
+                                                            uint32_t* header,
                                                             uint32_t* long_list, unsigned int* counter) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t < n_games * (uint64_t)k;
@@ -294,7 +289,7 @@ __global__ void __launch_bounds__(256) seed_explicit_kernel(const uint64_t* coor
         Coord c{(uint32_t)cc[0], cc[1], cc[2], cc[3], cc[4], cc[5], cc[6], s, 0};
         Pcg pg;
         pcg_seed_coord(pg, c);
-        store_seat(mut + t, imm + t, pg, seat_table, (uint32_t)t);
+        store_seat(seats + t, pg, seat_table, (uint32_t)t);
         if (s == 0) {
             is_long = true;
             for (int j = 0; j < k; j++) is_long = is_long && entry_never_banks(seat_table, (uint32_t)(t + j));
@@ -595,11 +590,11 @@ int launch_play(const PlayParams& P, const FinishParams& F, cudaStream_t stream)
             if (warps < 1) warps = 1;
         }
     }
-    const size_t smem = (LUT_BYTES + 15) & ~15;
+    const size_t smem = PLAY_SMEM_BYTES;
     static bool smem_opted = false;
     if (!smem_opted) {
-        FB_CUDA(cudaFuncSetAttribute(play_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        FB_CUDA(cudaFuncSetAttribute(play_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FB_CUDA(cudaFuncSetAttribute(play_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FB_CUDA(cudaFuncSetAttribute(play_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_opted = true;
     }
     if (!t_ev0) {
@@ -608,9 +603,9 @@ int launch_play(const PlayParams& P, const FinishParams& F, cudaStream_t stream)
     }
     FB_CUDA(cudaEventRecord(t_ev0, stream));
     if (P.limits)
-        play_kernel<1024, true><<<grid, warps * 32, smem, stream>>>(P, g_ctx.lut_dev);
+        play_kernel<true><<<grid, warps * 32, smem, stream>>>(P, g_ctx.lut_dev);
     else
-        play_kernel<1024, false><<<grid, warps * 32, smem, stream>>>(P, g_ctx.lut_dev);
+        play_kernel<false><<<grid, warps * 32, smem, stream>>>(P, g_ctx.lut_dev);
     int rc = launch_check("play_kernel");
     if (rc) return rc;
     FB_CUDA(cudaEventRecord(t_ev1, stream));
@@ -786,12 +781,11 @@ int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuff
     seed_tournament_kernel<<<blocks_for(n_games * k, 256), 256, 0, stream>>>(
         root_seed, k, shuffle0, gps, n_games, perm, n_strategies, target_score, max_rounds,
         override_shuffle_dev, override_game_dev, override_max_rounds_dev, n_overrides, want_game_seeds,
-        strategies_dev, w.mut, w.imm, w.game_seed, limits, w.header, w.long_list, w.counter);
+        strategies_dev, w.seats, w.game_seed, limits, w.header, w.long_list, w.counter);
     rc = launch_check("seed_tournament_kernel");
     if (rc) return rc;
     PlayParams P{};
-    P.mut = w.mut;
-    P.imm = w.imm;
+    P.seats = w.seats;
     P.header = w.header;
     P.limits = limits;
     P.target_score = target_score;
@@ -802,8 +796,7 @@ int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuff
     P.counter = w.counter;
     P.long_list = w.long_list;
     FinishParams F{};
-    F.mut = w.mut;
-    F.imm = w.imm;
+    F.seats = w.seats;
     F.header = w.header;
     F.strategy_ids = strategy_ids_dev;
     F.ids_mode = strategy_ids_dev ? 1 : 0;
@@ -842,12 +835,11 @@ int fb_play_h2h(uint64_t root_seed, int n_blocks, const uint64_t* pair_id_dev, c
     FB_CUDA(cudaMemsetAsync(w.counter, 0, 2 * sizeof(unsigned int), stream));
     seed_h2h_kernel<<<blocks_for(total_attempts * 2, 256), 256, 0, stream>>>(
         root_seed, n_blocks, pair_id_dev, order_dev, seat1_dev, seat2_dev, attempt0_dev, offsets,
-        total_attempts, want_seeds, w.mut, w.imm, w.game_seed, w.header, w.long_list, w.counter);
+        total_attempts, want_seeds, w.seats, w.game_seed, w.header, w.long_list, w.counter);
     rc = launch_check("seed_h2h_kernel");
     if (rc) return rc;
     PlayParams P{};
-    P.mut = w.mut;
-    P.imm = w.imm;
+    P.seats = w.seats;
     P.header = w.header;
     P.target_score = target_score;
     P.max_rounds = max_rounds;
@@ -857,8 +849,7 @@ int fb_play_h2h(uint64_t root_seed, int n_blocks, const uint64_t* pair_id_dev, c
     P.counter = w.counter;
     P.long_list = w.long_list;
     FinishParams F{};
-    F.mut = w.mut;
-    F.imm = w.imm;
+    F.seats = w.seats;
     F.header = w.header;
     F.ids_mode = 2;
     F.game_seed = want_seeds ? w.game_seed : nullptr;
@@ -904,7 +895,7 @@ int fb_play_games(const uint64_t* coords_dev, uint64_t n_games, int k,
         return fail(FB_ERR_WORKSPACE, "workspace too small: need %zu bytes", ws_core_bytes(k, n_games));
     FB_CUDA(cudaMemsetAsync(w.counter, 0, 2 * sizeof(unsigned int), stream));
     seed_explicit_kernel<<<blocks_for(n_games * k, 256), 256, 0, stream>>>(
-        coords_dev, n_games, k, seat_strategies_dev, w.mut, w.imm, w.header, w.long_list, w.counter);
+        coords_dev, n_games, k, seat_strategies_dev, w.seats, w.header, w.long_list, w.counter);
     int rc = launch_check("seed_explicit_kernel");
     if (rc) return rc;
     int32_t* limits = nullptr;
@@ -916,8 +907,7 @@ int fb_play_games(const uint64_t* coords_dev, uint64_t n_games, int k,
         if (rc) return rc;
     }
     PlayParams P{};
-    P.mut = w.mut;
-    P.imm = w.imm;
+    P.seats = w.seats;
     P.header = w.header;
     P.limits = limits;
     P.target_score = target_score;
@@ -928,8 +918,7 @@ int fb_play_games(const uint64_t* coords_dev, uint64_t n_games, int k,
     P.counter = w.counter;
     P.long_list = w.long_list;
     FinishParams F{};
-    F.mut = w.mut;
-    F.imm = w.imm;
+    F.seats = w.seats;
     F.header = w.header;
     F.strategy_ids = seat_strategy_ids_dev;
     F.ids_mode = seat_strategy_ids_dev ? 1 : 2;

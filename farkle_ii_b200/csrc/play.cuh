@@ -9,19 +9,19 @@
 //   OutcomeCounter.record_row + winner metric sums
 //                                         src/farkle/simulation/run_tournament.py:177-195,375-391
 //
-// Data layout in HBM (per (game, seat), written by the seed kernels)
-//   SeatMut  48 B  PCG state (16 B) | saved half, score, highest|flags, farkles|rolls |
-//                  turns|hot, sf uses|dice, so uses|dice, pad
-//   SeatImm  32 B  PCG increment (16 B) | score_threshold, dice_threshold|flags,
-//                  strategy table index, pad
+// Data layout in HBM: one 80-byte Seat record per (game, seat), written by the seed kernels
+//   line 0  PCG state (16 B)
+//   line 1  saved half | score | highest_turn|has32<<30|has_scored<<31 | farkles|rolls<<16
+//   line 2  turns|hot<<16 | smart-five uses|dice<<16 | smart-one uses|dice<<16 | pad
+//   line 3  PCG increment (16 B)
+//   line 4  st_d | kf|dt_d<<16 | dbase|tab_off<<16 | strategy table index   (seat_consts())
 //   game header 4 B  n_rounds | flags << 16 | HDR_LONG, written when the game ends; the seed
 //                    kernels pre-set HDR_LONG on games that are certain to run to the safety
 //                    limit so that play_kernel starts them first (longest-first scheduling)
-// The active seat lives in registers; a turn switch is three 16-byte stores of the
-// outgoing SeatMut and five 16-byte loads of the incoming seat.  The records of all
-// games in flight (148 SMs x 1,024 lanes x k seats x 80 B) stay L2-resident, so the
-// traffic is L2 traffic; shared memory holds only the lookup tables, which leaves the
-// SM at full occupancy for every k.
+// The active seat lives in registers.  A turn switch stores lines 0-2 of the outgoing seat
+// (three 16-byte st.cg) and takes the incoming seat from this lane's shared-memory staging
+// slots, which a cp.async prefetch filled during the turn that just ended; the records of the
+// games in flight stay L2 resident.
 //
 // play_kernel   one game per lane, loop body = ONE ROLL, straight-line; persistent CTAs
 //               (one per SM); a lane whose game ended takes the next ordinal from a
@@ -45,21 +45,18 @@ constexpr uint32_t HW_SCORED = 1u << 31;
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr uint32_t HDR_LONG = 1u << 31;
 
-struct __align__(16) SeatMut {
-    uint32_t lo0, lo1, hi0, hi1;    // PCG state
-    uint32_t saved, score, hw, fr;  // buffered half | score | highest|has32<<30|has_scored<<31 | farkles|rolls<<16
-    uint32_t th, sf, so, pad;       // turns|hot<<16 | sf uses|dice<<16 | so uses|dice<<16
+struct __align__(16) Seat {
+    uint4 state;  // PCG state lo0, lo1, hi0, hi1
+    uint4 a;      // saved | score | hw | farkles|rolls<<16
+    uint4 b;      // turns|hot<<16 | sf uses|dice<<16 | so uses|dice<<16 | pad
+    uint4 inc;    // PCG increment
+    uint4 cst;    // st_d | kf|dt_d<<16 | dbase|tab_off<<16 | strategy table index
 };
-struct __align__(16) SeatImm {
-    uint32_t ilo0, ilo1, ihi0, ihi1;  // PCG increment
-    uint32_t st_d, dtkf, strat, tabs;  // seat_consts(): st_d | (u16)dt_d | kf << 16 | table index |
-                                       // dbase | tab_off << 16
-};
-static_assert(sizeof(SeatMut) == 48 && sizeof(SeatImm) == 32, "seat record layout");
+static_assert(sizeof(Seat) == 80, "seat record layout");
+constexpr uint32_t CST_DT_SHIFT = 16;  // cst.y: kf in the low half, dt_d (signed) in the high half
 
 struct PlayParams {
-    SeatMut* mut;           // [n_games*k]
-    const SeatImm* imm;     // [n_games*k]
+    Seat* seats;            // [n_games*k]
     uint32_t* header;       // [n_games]
     const int32_t* limits;  // [n_games][2] {target, max_rounds} or nullptr
     int32_t target_score, max_rounds;
@@ -72,14 +69,33 @@ struct PlayParams {
 
 enum LaneStatus { ST_NEED = 0, ST_PLAY = 1, ST_DEAD = 2 };
 
-// kernel-side view of SeatImm's second line
-constexpr uint32_t IMM_KF_SHIFT = 16;  // w1 = (u16)dt_d | kf << 16,  w3 = dbase | tab_off << 16
+// 16-byte asynchronous global -> shared copy (LDGSTS) and its completion wait.
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t smem_addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(smem_addr)
+                 : "memory");
+    return v;
+}
+// Staging area behind the tables: line f of lane t at stage0 + f * STAGE_STRIDE + t * 16, so a
+// warp's 16-byte accesses to one line are contiguous (conflict free) and the five lines of a
+// lane are immediate offsets from one address register.
+constexpr int PLAY_THREADS = 1024;
+constexpr uint32_t STAGE_STRIDE = PLAY_THREADS * 16u;
+constexpr size_t PLAY_SMEM_BYTES = (size_t)((LUT_BYTES + 15) & ~15) + 5u * STAGE_STRIDE;
 
-template <int MAXT, bool LIMITS>
-__global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const ScoreLut* __restrict__ lut_g) {
+template <bool LIMITS>
+__global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams P, const ScoreLut* __restrict__ lut_g) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ unsigned long long s_tot[2];
     ScoreLut* lut = reinterpret_cast<ScoreLut*>(smem_raw);
+    const uint32_t stage = (uint32_t)__cvta_generic_to_shared(smem_raw) + (uint32_t)((LUT_BYTES + 15) & ~15) +
+                           threadIdx.x * 16u;
     for (int i = threadIdx.x; i < LUT_BYTES / 16; i += blockDim.x)
         reinterpret_cast<uint4*>(lut)[i] = reinterpret_cast<const uint4*>(lut_g)[i];
     if (threadIdx.x < 2) s_tot[threadIdx.x] = 0ull;
@@ -96,9 +112,9 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
     // ---- per-lane game state ------------------------------------------------
     int status = ST_NEED;
     uint32_t g = 0, err = 0;
-    int seat = 0, round = 0, trigger = -1, stb = 0;
+    int seat = 0, nseat = 0, round = 0, trigger = -1, stb = 0;
     int target = P.target_score, max_rounds = P.max_rounds;
-    // active seat (SeatMut / SeatImm in registers)
+    // active seat in registers
     Pcg rng{0, 0, 0, 0};
     uint32_t saved = 0, hw = 0;
     int score = 0, st_d = 0, dt_d = 0;
@@ -107,13 +123,13 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
     int ts = 0, dice = 6, rolls_turn = 0;
     uint32_t a_dice = 0, a_words = 0;
 
-    // Seat player `seat` of game g and start the turn (engine.py:229-240): five 16-byte loads.
-    auto seat_player = [&]() {
-        const uint32_t rec = g * (uint32_t)k + (uint32_t)seat;  // n_games * k < 2^32 (checked on the host)
-        const uint4* mp = reinterpret_cast<const uint4*>(P.mut + rec);
-        const uint4* ip = reinterpret_cast<const uint4*>(P.imm + rec);
-        const uint4 m0 = __ldcg(mp), m1 = __ldcg(mp + 1), m2 = __ldcg(mp + 2);
-        const uint4 i0 = __ldcg(ip), i1 = __ldcg(ip + 1);
+    // Start the turn of player `seat` from its record lines (engine.py:229-240), then predict
+    // who plays next if this turn neither triggers the final round nor ends the game — seat
+    // order within a round, or the final-round order that skips the trigger seat
+    // (engine.py:459-471,533-548); >= k means nobody — and prefetch that record into the
+    // staging slots so its L2 latency overlaps this whole turn instead of stalling the warp.
+    // (The predicted record was last written by this lane, earlier in program order.)
+    auto start_turn = [&](const uint4 m0, const uint4 m1, const uint4 m2, const uint4 i0, const uint4 i1) {
         rng.lo = (uint64_t)m0.x | ((uint64_t)m0.y << 32);
         rng.hi = (uint64_t)m0.z | ((uint64_t)m0.w << 32);
         rng.ilo = (uint64_t)i0.x | ((uint64_t)i0.y << 32);
@@ -126,13 +142,30 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
         c_sf = m2.y;
         c_so = m2.z;
         st_d = (int)i1.x;
-        dt_d = (int)(int16_t)(i1.y & 0xffffu);
-        kf = i1.y >> IMM_KF_SHIFT;
-        dbase = i1.w & 0xffffu;
-        tab_off = i1.w >> 16;
+        kf = i1.y;  // KF_* bits live in the low half; the high half is never tested
+        dt_d = (int)i1.y >> CST_DT_SHIFT;
+        dbase = i1.z & 0xffffu;
+        tab_off = i1.z >> 16;
         dice = 6;
         ts = 0;
         rolls_turn = 0;
+        int ns = seat + 1;
+        if (trigger < 0) ns = ns == k ? 0 : ns;
+        else if (ns == trigger) ns++;
+        nseat = ns;
+        if (ns < k && k > 1) {
+            const uint4* np = reinterpret_cast<const uint4*>(P.seats + (g * (uint32_t)k + (uint32_t)ns));
+            cp_async16(stage, np);
+            cp_async16(stage + STAGE_STRIDE, np + 1);
+            cp_async16(stage + 2u * STAGE_STRIDE, np + 2);
+            cp_async16(stage + 3u * STAGE_STRIDE, np + 3);
+            cp_async16(stage + 4u * STAGE_STRIDE, np + 4);
+        }
+    };
+    auto start_turn_from_l2 = [&]() {
+        const uint4* sp = reinterpret_cast<const uint4*>(P.seats + (g * (uint32_t)k + (uint32_t)seat));
+        const uint4 m0 = __ldcg(sp), m1 = __ldcg(sp + 1), m2 = __ldcg(sp + 2), i0 = __ldcg(sp + 3), i1 = __ldcg(sp + 4);
+        start_turn(m0, m1, m2, i0, i1);
     };
 
     for (;;) {
@@ -166,7 +199,7 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
                         if (max_rounds <= 0) {  // `while rounds < max_rounds` never runs (engine.py:455)
                             P.header[g] = ((uint32_t)FB_ROW_SAFETY_LIMIT << 16) | err;
                         } else {
-                            seat_player();
+                            start_turn_from_l2();
                             status = ST_PLAY;
                         }
                     }
@@ -186,30 +219,28 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
             // advances past the nw words this roll really consumes.
             const uint32_t p = (hw & HW_HAS32) ? 0u : 1u;
             const int nw = (n + (int)p) >> 1;
+            const bool c1 = nw > 0, c2 = nw > 1, c3 = nw > 2;
             uint64_t shi = rng.hi, slo = rng.lo;
             const uint64_t o1 = pcg_output(shi, slo);
             {
                 uint64_t th = shi, tl = slo;
                 pcg_step(th, tl, rng.ihi, rng.ilo);
-                const bool c = nw > 0;
-                shi = c ? th : shi;
-                slo = c ? tl : slo;
+                shi = c1 ? th : shi;
+                slo = c1 ? tl : slo;
             }
             const uint64_t o2 = pcg_output(shi, slo);
             {
                 uint64_t th = shi, tl = slo;
                 pcg_step(th, tl, rng.ihi, rng.ilo);
-                const bool c = nw > 1;
-                shi = c ? th : shi;
-                slo = c ? tl : slo;
+                shi = c2 ? th : shi;
+                slo = c2 ? tl : slo;
             }
             const uint64_t o3 = pcg_output(shi, slo);
             {
                 uint64_t th = shi, tl = slo;
                 pcg_step(th, tl, rng.ihi, rng.ilo);
-                const bool c = nw > 2;
-                shi = c ? th : shi;
-                slo = c ? tl : slo;
+                shi = c3 ? th : shi;
+                slo = c3 ? tl : slo;
             }
             const uint32_t H1 = (uint32_t)o1, H2 = (uint32_t)(o1 >> 32);
             const uint32_t H3 = (uint32_t)o2, H4 = (uint32_t)(o2 >> 32);
@@ -229,9 +260,10 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
             FB_DIE(4, H4, H5)
             FB_DIE(5, H5, H6)
 #undef FB_DIE
-            const uint32_t q = p + (uint32_t)n;  // index of the first unread half
-            bool nhas = (q & 1u) == 0u;
-            uint32_t nsaved = q == 2u ? H2 : (q == 4u ? H4 : H6);
+            // The buffered half afterwards is the high half of the last word consumed (only
+            // meaningful when an odd number of halves remains unread); has32 flips with odd n.
+            uint32_t nsaved = c3 ? H6 : (c2 ? H4 : H2);
+            uint32_t nhw = hw ^ (((uint32_t)n << 30) & HW_HAS32);
             uint32_t words = (uint32_t)nw;
             if (minlo < 4u) {
                 // A draw with leftover < 4 somewhere in the window (4 in 2^32 per die; unused
@@ -242,12 +274,12 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
                 for (int i = 0; i < n; i++) hist += 1u << (3u * s.die0(words));
                 shi = s.g.hi;
                 slo = s.g.lo;
-                nhas = s.has32;
+                nhw = s.has32 ? (hw | HW_HAS32) : (hw & ~HW_HAS32);
                 nsaved = s.saved;
             }
             rng.hi = shi;
             rng.lo = slo;
-            hw = nhas ? (hw | HW_HAS32) : (hw & ~HW_HAS32);
+            hw = nhw;
             saved = nsaved;
             a_dice += (uint32_t)n;
             a_words += words;
@@ -293,38 +325,46 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
                     const uint32_t hi_turn = max(hw & HIGH_MASK, (uint32_t)ts);
                     hw = (hw & ~HIGH_MASK) | hi_turn;
                 }
-                uint4* mp = reinterpret_cast<uint4*>(P.mut + (g * (uint32_t)k + (uint32_t)seat));
-                __stcg(mp, make_uint4((uint32_t)rng.lo, (uint32_t)(rng.lo >> 32), (uint32_t)rng.hi,
+                uint4* sp = reinterpret_cast<uint4*>(P.seats + (g * (uint32_t)k + (uint32_t)seat));
+                __stcg(sp, make_uint4((uint32_t)rng.lo, (uint32_t)(rng.lo >> 32), (uint32_t)rng.hi,
                                       (uint32_t)(rng.hi >> 32)));
-                __stcg(mp + 1, make_uint4(saved, (uint32_t)score, hw, c_fr));
-                __stcg(mp + 2, make_uint4(c_th, c_sf, c_so, 0u));
-                bool over = (err & FB_ROW_ROLL_LIMIT) != 0u;
-                if (trigger < 0) {
-                    if (score >= target) {  // first trigger starts the final round (engine.py:466-471)
-                        trigger = seat;
-                        stb = score;
-                        seat = seat == 0 ? 1 : 0;
-                        over |= seat >= k;
-                    } else {
-                        seat++;
-                        if (seat == k) {  // next round, unless the safety limit is reached (engine.py:455)
-                            seat = 0;
-                            over |= round >= max_rounds;
-                            if (!over) round++;
-                        }
+                __stcg(sp + 1, make_uint4(saved, (uint32_t)score, hw, c_fr));
+                __stcg(sp + 2, make_uint4(c_th, c_sf, c_so, 0u));
+                // Who plays next.  Without a trigger event it is the seat predicted (and
+                // prefetched) at the start of this turn.
+                int next = nseat;
+                bool over;
+                if (fin) {                       // final round (engine.py:533-548)
+                    stb = max(stb, score);
+                    over = next >= k;
+                } else if (score >= target) {    // this turn triggers it (engine.py:466-471)
+                    trigger = seat;
+                    stb = score;
+                    next = seat == 0 ? 1 : 0;
+                    over = next >= k;
+                } else {                         // next seat, or next round unless the safety
+                    over = false;                // limit is reached (engine.py:455)
+                    if (next == 0) {
+                        over = round >= max_rounds;
+                        if (!over) round++;
                     }
-                } else {
-                    if (score > stb) stb = score;  // engine.py:547-548
-                    seat++;
-                    if (seat == trigger) seat++;
-                    over |= seat >= k;
                 }
-                if (over) {
+                if (over || (err & FB_ROW_ROLL_LIMIT)) {
                     P.header[g] = (uint32_t)round | (err & HDR_LONG) |
                                   (((trigger < 0 ? FB_ROW_SAFETY_LIMIT : 0u) | (err & 0xffu)) << 16);
                     status = ST_NEED;
                 } else {
-                    seat_player();
+                    const bool staged = next == nseat && k > 1;
+                    seat = next;
+                    if (staged) {
+                        cp_async_wait_all();
+                        const uint4 m0 = lds128(stage), m1 = lds128(stage + STAGE_STRIDE);
+                        const uint4 m2 = lds128(stage + 2u * STAGE_STRIDE), i0 = lds128(stage + 3u * STAGE_STRIDE);
+                        const uint4 i1 = lds128(stage + 4u * STAGE_STRIDE);
+                        start_turn(m0, m1, m2, i0, i1);
+                    } else {
+                        start_turn_from_l2();
+                    }
                 }
             }
         }
@@ -347,8 +387,7 @@ __global__ void __launch_bounds__(MAXT, 1) play_kernel(const PlayParams P, const
 // finish pass
 // ---------------------------------------------------------------------------
 struct FinishParams {
-    const SeatMut* mut;
-    const SeatImm* imm;
+    const Seat* seats;
     const uint32_t* header;
     const int32_t* strategy_ids;  // id of table entry (ids_mode 1)
     int ids_mode;                 // 0 id = table index, 1 id = strategy_ids[index], 2 id = seat
@@ -378,13 +417,12 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
         const uint32_t rounds = hdr & 0xffffu;
         uint32_t flags = (hdr >> 16) & 0xffu;
         const bool safety = flags & FB_ROW_SAFETY_LIMIT;
-        const SeatMut* mut = F.mut + (size_t)g * k;
-        const SeatImm* imm = F.imm + (size_t)g * k;
+        const Seat* seats = F.seats + (size_t)g * k;
         // pass 1: winner = highest score, ties to the lower seat (stable sort, engine.py:483)
         int best = -1;
         for (int s = 0; s < k; s++) {
-            const uint4 a = __ldcg(reinterpret_cast<const uint4*>(mut + s) + 1);
-            const uint4 b = __ldcg(reinterpret_cast<const uint4*>(mut + s) + 2);
+            const uint4 a = __ldcg(&seats[s].a);
+            const uint4 b = __ldcg(&seats[s].b);
             const int sc = (int)a.y;
             if (sc > best) {
                 best = sc;
@@ -416,9 +454,9 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
         }
         // pass 2: rows, exposures, winner metrics
         for (int s = 0; s < k; s++) {
-            const uint4 a = __ldcg(reinterpret_cast<const uint4*>(mut + s) + 1);
-            const uint4 b = __ldcg(reinterpret_cast<const uint4*>(mut + s) + 2);
-            const uint32_t idx = __ldcg(&imm[s].strat);
+            const uint4 a = __ldcg(&seats[s].a);
+            const uint4 b = __ldcg(&seats[s].b);
+            const uint32_t idx = __ldcg(&seats[s].cst.w);
             const int sid = F.ids_mode == 0 ? (int)idx : (F.ids_mode == 1 ? F.strategy_ids[idx] : s);
             if (row) {
                 uint32_t* w = row + 4 + s * 7;
