@@ -809,6 +809,14 @@ int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuff
     F.totals = reinterpret_cast<unsigned long long*>(totals_dev);
     F.rows = reinterpret_cast<uint32_t*>(rows_dev);
     F.row_words = (int)(fb_row_stride(k) / 4);
+    if (F.tallies) {
+        F.dense_exposure = 1;
+        const int n_slots = shuffles_per_slot > 0 ? (n_shuffles + shuffles_per_slot - 1) / shuffles_per_slot : 1;
+        exposure_kernel<<<dim3(blocks_for((uint64_t)n_strategies, 256), (unsigned)n_slots), 256, 0, stream>>>(
+            F.tallies, strategy_ids_dev, n_strategies, n_tally_ids, n_shuffles, shuffles_per_slot);
+        rc = launch_check("exposure_kernel");
+        if (rc) return rc;
+    }
     return launch_play(P, F, stream);
 }
 

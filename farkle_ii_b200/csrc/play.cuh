@@ -396,6 +396,9 @@ struct FinishParams {
     int k;
     uint32_t games_per_slot;  // 0 = one tally slot
     int n_tally_ids;
+    int dense_exposure;           // 1: every id is seated exactly once per shuffle, so attempted /
+                                  // completed exposures are added per slot by exposure_kernel and
+                                  // only safety-limit games touch them here
     unsigned long long* tallies;  // [slots][ids][26] or nullptr
     unsigned long long* totals;   // [FB_TOTALS_WIDTH] or nullptr
     uint32_t* rows;               // or nullptr
@@ -470,19 +473,26 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
             }
             if (T) {
                 unsigned long long* Ts = T + (size_t)sid * FB_TALLY_WIDTH;
-                atomicAdd(&Ts[1], 1ull);
-                atomicAdd(&Ts[safety ? 3 : 2], 1ull);
+                if (!F.dense_exposure) {
+                    atomicAdd(&Ts[1], 1ull);
+                    atomicAdd(&Ts[safety ? 3 : 2], 1ull);
+                } else if (safety) {  // move one exposure from "completed" to "safety limit"
+                    atomicAdd(&Ts[3], 1ull);
+                    atomicAdd(&Ts[2], ~0ull);
+                }
                 if (s == winner) {
                     // METRIC_LABELS order, run_tournament.py:109-121; winner_hit_max_rounds is
-                    // False for every completed game, so its sums stay 0.
+                    // False for every completed game, so its sums stay 0.  Zero addends are skipped.
                     const unsigned long long m[10] = {a.y, rounds, a.w & 0xffffu, a.w >> 16,
                                                       a.z & HIGH_MASK, b.y & 0xffffu, b.y >> 16,
                                                       b.z & 0xffffu, b.z >> 16, b.x >> 16};
                     atomicAdd(&Ts[0], 1ull);
 #pragma unroll
                     for (int j = 0; j < 10; j++) {
-                        atomicAdd(&Ts[4 + j], m[j]);
-                        atomicAdd(&Ts[4 + FB_N_METRICS + j], m[j] * m[j]);
+                        if (m[j]) {
+                            atomicAdd(&Ts[4 + j], m[j]);
+                            atomicAdd(&Ts[4 + FB_N_METRICS + j], m[j] * m[j]);
+                        }
                     }
                 }
             }
@@ -513,6 +523,21 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
         if (threadIdx.x < FB_TOTALS_WIDTH && s_tot[threadIdx.x])
             atomicAdd(&F.totals[threadIdx.x], s_tot[threadIdx.x]);
     }
+}
+
+// attempted / completed exposures of a tournament launch: strategy i is seated exactly once in
+// every shuffle (run_tournament.py:336-353), so slot j adds its shuffle count to both columns.
+__global__ void exposure_kernel(unsigned long long* tallies, const int32_t* strategy_ids, int n_strategies,
+                                int n_tally_ids, int n_shuffles, int shuffles_per_slot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int slot = blockIdx.y;
+    if (i >= n_strategies) return;
+    const int per = shuffles_per_slot > 0 ? shuffles_per_slot : n_shuffles;
+    const int cnt = min(per, n_shuffles - slot * per);
+    const int sid = strategy_ids ? strategy_ids[i] : i;
+    unsigned long long* Ts = tallies + ((size_t)slot * n_tally_ids + sid) * FB_TALLY_WIDTH;
+    atomicAdd(&Ts[1], (unsigned long long)cnt);
+    atomicAdd(&Ts[2], (unsigned long long)cnt);
 }
 
 }  // namespace fb
