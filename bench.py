@@ -307,7 +307,9 @@ def main() -> None:
     dom = max(CELLS_K, key=lambda k_: kern[k_]["ms"])
     achieved = kern[dom]["ops"] / (kern[dom]["ms"] * 1e-3)
     tot = kern[dom]["totals"]
-    row_bytes_alg = kern[dom]["games"] * (dom * 36 + 0)  # seat state + strategy index reads
+    # algorithmic HBM bytes of play_kernel per game: every 80-byte seat record is read once and
+    # its 48 mutable bytes written back once, plus the 4-byte game header
+    row_bytes_alg = kern[dom]["games"] * (dom * (80 + 48) + 4)
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -357,6 +359,8 @@ def main() -> None:
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roofline,
+        "roofline_hbm": {**roofline["hbm"], "traffic": traffic,
+                         "note": "same kernel against the HBM roofline: it is not the binding one"},
         "cpu_baseline": cpu,
         "published_reference": {"games_per_s_1_worker": 279.1, "games_per_s_12_workers": 1142.9,
                                 "hardware": "Ryzen 7 3700X, fast grid k=2 (BASELINE.md §1)"},
