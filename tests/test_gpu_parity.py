@@ -371,3 +371,84 @@ def test_h2h_many_blocks_vs_oracle(eng, golden_dir):
         P_H2H_GAME, root_seed=77, k=2, pair_id=int(pair[0]), order=int(order[0]),
         game_index=int(att0[0]))
     assert totals.cpu().numpy()[0] == n_att.sum()
+
+
+@pytest.mark.parametrize("k", [2, 4])
+def test_full_size_cell_properties(eng, golden_dir, k):
+    """BASELINE.json configs[1] at full size (4,300 shuffles of the 5,160 grid): size-independent
+    invariants on the whole cell, bit-exact per-batch tallies against the oracle on three of
+    the 100 deterministic batches, and the sum of the batch slots equal to a single-slot run."""
+    table = np.load(golden_dir / "games_full_0_2.npz")["strategies"]
+    n, nsh, spb = len(table), 4300, 43
+    res = eng.play_tournament(42, k, 0, nsh, table, shuffles_per_slot=spb)
+    t = res.tallies.cpu().numpy()
+    tot = res.totals.cpu().numpy()
+    games = nsh * (n // k)
+    assert t.shape == (100, n, 26) and tot[0] == games and tot[1] + tot[2] == games and tot[7] == 0
+    assert (t[:, :, 1] == spb).all()                              # one seat per strategy per shuffle
+    assert (t[:, :, 2] + t[:, :, 3] == t[:, :, 1]).all()          # completed + safety = attempted
+    assert t[:, :, 0].sum() == tot[1] and t[:, :, 3].sum() == k * tot[2]
+    assert tot[8:8 + k].sum() == tot[1] and not tot[8 + k:].any()  # seat wins
+    assert (t[:, :, 14] == 0).all() and (t[:, :, 25] == 0).all()  # winner_hit_max_rounds
+    assert (t[:, :, 4] >= 10_000 * t[:, :, 0]).all()              # every winner reached the target
+    assert (t[:, :, 15] >= t[:, :, 4] * 10_000).all()             # sum v^2 >= 10,000 * sum v
+    for slot in (0, 57, 99):
+        want, _, _ = fo.play_tournament(42, k, slot * spb, spb, table, n_threads=8)
+        assert np.array_equal(t[slot], want[0]), slot
+    one = eng.play_tournament(42, k, 0, nsh, table)
+    assert np.array_equal(one.tallies.cpu().numpy()[0], t.sum(axis=0))
+    assert np.array_equal(one.totals.cpu().numpy(), tot)
+
+
+def test_run_tournament_end_to_end(eng, golden_dir, tmp_path):
+    """run_tournament(): checkpoint payload, {k}p_metrics.parquet and per-shuffle row shards for
+    the fast grid, seed 42, k=2 — the cell the reference's `farkle run` digest was taken on."""
+    import pickle
+
+    import pyarrow.parquet as pq
+
+    from farkle_ii_b200 import run_tournament as frt
+    from farkle_ii_b200.strategies import generate_strategy_grid
+
+    z = np.load(golden_dir / "fast42.npz")
+    strategies, _ = generate_strategy_grid(
+        score_thresholds=[250, 300, 350, 400], smart_five_opts=[True], smart_one_opts=[True],
+        consider_score_opts=[True], consider_dice_opts=[True], auto_hot_dice_opts=[True],
+        run_up_score_opts=[True])
+    cfg = frt.TournamentConfig(n_players=2, num_shuffles=600, deterministic_batch_size=30)
+    ckpt = tmp_path / "2p_checkpoint.pkl"
+    frt.run_tournament(config=cfg, global_seed=42, checkpoint_path=ckpt, collect_metrics=True,
+                       num_shuffles=600, strategies=strategies, checkpoint_metadata={"seed": 42})
+    payload = pickle.loads(ckpt.read_bytes())
+    wins = payload["win_totals"]
+    assert isinstance(wins, frt.OutcomeCounter) and payload["meta"] == {"seed": 42}
+    assert (wins.games_attempted, wins.games_completed, wins.games_safety_limit) == (24000, 23801, 199)
+    assert [wins[i] for i in (42, 46, 51, 37, 25)] == [330, 322, 407, 386, 140]
+    want = z["tallies"]
+    for sid in range(80):
+        assert wins[sid] == want[sid, 0] and wins.attempted_exposures[sid] == want[sid, 1]
+        assert wins.completed_exposures[sid] == want[sid, 2]
+        assert wins.safety_limit_exposures[sid] == want[sid, 3]
+        for m, label in enumerate(frt.METRIC_LABELS):
+            assert payload["metric_sums"][label].get(sid, 0.0) == float(want[sid, 4 + m])
+            assert payload["metric_square_sums"][label].get(sid, 0.0) == float(want[sid, 15 + m])
+    metrics = pq.read_table(tmp_path / "2p_metrics.parquet").to_pandas()
+    assert len(metrics) == 11 * int((want[:, 0] > 0).sum())
+    ws = metrics[metrics.metric == "winning_score"].set_index("strategy")["sum"]
+    assert ws.sum() == 252_520_900
+    # rows mode on a slice: one shard + one manifest line per shuffle, resumable
+    cfg2 = frt.TournamentConfig(n_players=2, num_shuffles=4, deterministic_batch_size=2)
+    row_dir = tmp_path / "rows"
+    frt.run_tournament(config=cfg2, global_seed=42, checkpoint_path=tmp_path / "c2.pkl",
+                       row_output_directory=row_dir, num_shuffles=4, strategies=strategies)
+    shards = sorted(row_dir.glob("rows_42_2p_*.parquet"))
+    assert len(shards) == 4 and len((row_dir / "manifest.jsonl").read_text().splitlines()) == 4
+    first = pq.read_table(shards[0]).to_pylist()[0]
+    assert (first["P1_strategy"], first["P2_strategy"]) == (42, 9)        # SURVEY.md §8c first row
+    assert (first["winner_seat"], first["P1_score"], first["P2_score"], first["n_rounds"]) == ("P1", 10800, 6900, 17)
+    assert (first["P1_rolls"], first["P1_farkles"], first["P1_highest_turn"], first["P1_hot_dice"]) == (36, 6, 2750, 5)
+    assert (first["P2_rolls"], first["P2_farkles"], first["P2_smart_five_uses"]) == (52, 8, 20)
+    assert first["shuffle_seed"] == 1_998_876_487 and first["game_seed"] == 1_433_242_307
+    frt.run_tournament(config=cfg2, global_seed=42, checkpoint_path=tmp_path / "c2.pkl",
+                       row_output_directory=row_dir, num_shuffles=4, strategies=strategies)
+    assert len((row_dir / "manifest.jsonl").read_text().splitlines()) == 4  # resume skipped all
