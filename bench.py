@@ -200,6 +200,10 @@ def main() -> None:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # Libraries (NCCL prints its version banner) write to fd 1: keep the real stdout for the one
+    # JSON line and send everything else to stderr.
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: farkle_ii_b200 has no CPU fallback")
     torch.cuda.set_device(local)
@@ -365,7 +369,8 @@ def main() -> None:
         "published_reference": {"games_per_s_1_worker": 279.1, "games_per_s_12_workers": 1142.9,
                                 "hardware": "Ryzen 7 3700X, fast grid k=2 (BASELINE.md §1)"},
     }
-    print(json.dumps(line))
+    json_out.write(json.dumps(line) + "\n")
+    json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 

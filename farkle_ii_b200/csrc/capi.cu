@@ -593,8 +593,10 @@ int launch_play(const PlayParams& P, const FinishParams& F, cudaStream_t stream)
     const size_t smem = PLAY_SMEM_BYTES;
     static bool smem_opted = false;
     if (!smem_opted) {
-        FB_CUDA(cudaFuncSetAttribute(play_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        FB_CUDA(cudaFuncSetAttribute(play_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FB_CUDA(cudaFuncSetAttribute(play_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FB_CUDA(cudaFuncSetAttribute(play_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FB_CUDA(cudaFuncSetAttribute(play_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FB_CUDA(cudaFuncSetAttribute(play_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_opted = true;
     }
     if (!t_ev0) {
@@ -602,10 +604,14 @@ int launch_play(const PlayParams& P, const FinishParams& F, cudaStream_t stream)
         FB_CUDA(cudaEventCreate(&t_ev1));
     }
     FB_CUDA(cudaEventRecord(t_ev0, stream));
-    if (P.limits)
-        play_kernel<true><<<grid, warps * 32, smem, stream>>>(P, g_ctx.lut_dev);
-    else
-        play_kernel<false><<<grid, warps * 32, smem, stream>>>(P, g_ctx.lut_dev);
+    const dim3 block((unsigned)warps * 32u);
+    if (P.k == 2) {
+        if (P.limits) play_kernel<true, true><<<grid, block, smem, stream>>>(P, g_ctx.lut_dev);
+        else play_kernel<false, true><<<grid, block, smem, stream>>>(P, g_ctx.lut_dev);
+    } else {
+        if (P.limits) play_kernel<true, false><<<grid, block, smem, stream>>>(P, g_ctx.lut_dev);
+        else play_kernel<false, false><<<grid, block, smem, stream>>>(P, g_ctx.lut_dev);
+    }
     int rc = launch_check("play_kernel");
     if (rc) return rc;
     FB_CUDA(cudaEventRecord(t_ev1, stream));

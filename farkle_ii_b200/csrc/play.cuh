@@ -89,20 +89,24 @@ constexpr int PLAY_THREADS = 1024;
 constexpr uint32_t STAGE_STRIDE = PLAY_THREADS * 16u;
 constexpr size_t PLAY_SMEM_BYTES = (size_t)((LUT_BYTES + 15) & ~15) + 5u * STAGE_STRIDE;
 
-template <bool LIMITS>
+// K2: two-seat games (every H2H block and the k=2 tournament cells).  The other seat always plays
+// next, so the turn switch needs no seat-order logic, the staged record is always the right one
+// and the record just parked is the one to prefetch.
+template <bool LIMITS, bool K2>
 __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams P, const ScoreLut* __restrict__ lut_g) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ unsigned long long s_tot[2];
     ScoreLut* lut = reinterpret_cast<ScoreLut*>(smem_raw);
-    const uint32_t stage = (uint32_t)__cvta_generic_to_shared(smem_raw) + (uint32_t)((LUT_BYTES + 15) & ~15) +
-                           threadIdx.x * 16u;
+    uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    asm volatile("" : "+r"(lut_s));  // opaque: keep it in a register instead of recomputing it
+    const uint32_t stage = lut_s + (uint32_t)((LUT_BYTES + 15) & ~15) + threadIdx.x * 16u;
     for (int i = threadIdx.x; i < LUT_BYTES / 16; i += blockDim.x)
         reinterpret_cast<uint4*>(lut)[i] = reinterpret_cast<const uint4*>(lut_g)[i];
     if (threadIdx.x < 2) s_tot[threadIdx.x] = 0ull;
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
-    const int k = P.k;
+    const int k = K2 ? 2 : P.k;
     const uint32_t lt_mask = (1u << lane) - 1u;
     // Ordinals [0, n_long) walk the long list, [n_long, n_long + n_games) walk every game and
     // skip the ones the long list already covered.
@@ -129,7 +133,8 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
     // (engine.py:459-471,533-548); >= k means nobody — and prefetch that record into the
     // staging slots so its L2 latency overlaps this whole turn instead of stalling the warp.
     // (The predicted record was last written by this lane, earlier in program order.)
-    auto start_turn = [&](const uint4 m0, const uint4 m1, const uint4 m2, const uint4 i0, const uint4 i1) {
+    auto start_turn = [&](const uint4 m0, const uint4 m1, const uint4 m2, const uint4 i0, const uint4 i1,
+                          const uint4* k2_next) {
         rng.lo = (uint64_t)m0.x | ((uint64_t)m0.y << 32);
         rng.hi = (uint64_t)m0.z | ((uint64_t)m0.w << 32);
         rng.ilo = (uint64_t)i0.x | ((uint64_t)i0.y << 32);
@@ -149,12 +154,17 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
         dice = 6;
         ts = 0;
         rolls_turn = 0;
-        int ns = seat + 1;
-        if (trigger < 0) ns = ns == k ? 0 : ns;
-        else if (ns == trigger) ns++;
-        nseat = ns;
-        if (ns < k && k > 1) {
-            const uint4* np = reinterpret_cast<const uint4*>(P.seats + (g * (uint32_t)k + (uint32_t)ns));
+        const uint4* np = k2_next;
+        bool prefetch = true;
+        if (!K2) {
+            int ns = seat + 1;
+            if (trigger < 0) ns = ns == k ? 0 : ns;
+            else if (ns == trigger) ns++;
+            nseat = ns;
+            prefetch = ns < k && k > 1;
+            np = reinterpret_cast<const uint4*>(P.seats + (g * (uint32_t)k + (uint32_t)ns));
+        }
+        if (prefetch) {
             cp_async16(stage, np);
             cp_async16(stage + STAGE_STRIDE, np + 1);
             cp_async16(stage + 2u * STAGE_STRIDE, np + 2);
@@ -165,10 +175,18 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
     auto start_turn_from_l2 = [&]() {
         const uint4* sp = reinterpret_cast<const uint4*>(P.seats + (g * (uint32_t)k + (uint32_t)seat));
         const uint4 m0 = __ldcg(sp), m1 = __ldcg(sp + 1), m2 = __ldcg(sp + 2), i0 = __ldcg(sp + 3), i1 = __ldcg(sp + 4);
-        start_turn(m0, m1, m2, i0, i1);
+        start_turn(m0, m1, m2, i0, i1, sp + 5);  // K2: a game starts with seat 0, seat 1 is the next record
+    };
+    auto start_turn_staged = [&](const uint4* k2_next) {
+        cp_async_wait_all();
+        const uint4 m0 = lds128(stage), m1 = lds128(stage + STAGE_STRIDE);
+        const uint4 m2 = lds128(stage + 2u * STAGE_STRIDE), i0 = lds128(stage + 3u * STAGE_STRIDE);
+        const uint4 i1 = lds128(stage + 4u * STAGE_STRIDE);
+        start_turn(m0, m1, m2, i0, i1, k2_next);
     };
 
-    for (;;) {
+    // One loop iteration; returns true when every lane of the warp is out of work.
+    auto roll_step = [&]() -> bool {
         // ================= R: lane refill =====================================
         const uint32_t need = __ballot_sync(FULL, status == ST_NEED);
         if (need) {
@@ -208,7 +226,7 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                 }
             }
         }
-        if (__all_sync(FULL, status == ST_DEAD)) break;
+        if (__all_sync(FULL, status == ST_DEAD)) return true;
 
         // ================= P: one roll (straight-line, no divergent branches) =====
         if (status == ST_PLAY) {
@@ -285,11 +303,11 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
             a_words += words;
 
             // -- score the roll (engine.py:103-147), discards, counters
-            const uint32_t e = lut_lookup(lut, tab_off, hist);
+            const uint32_t e = lut_lookup_s(lut_s, tab_off, hist);
             const int rscore = (int)(e & 127u) * 50;
             const int used0 = (int)((e >> 7) & 7u);
             const bool farkle = rscore == 0;
-            const uint32_t dd = smart_discards(lut, dbase, e, n, ts, st_d, dt_d);
+            const uint32_t dd = smart_discards_s(lut_s, dbase, e, n, ts, st_d, dt_d);
             const uint32_t d5 = dd & 3u, d1 = dd >> 2;  // both 0 on a farkle
             const int pts = rscore - 50 * (int)d5 - 100 * (int)d1;
             const int used = used0 - (int)d5 - (int)d1;
@@ -330,44 +348,65 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                                       (uint32_t)(rng.hi >> 32)));
                 __stcg(sp + 1, make_uint4(saved, (uint32_t)score, hw, c_fr));
                 __stcg(sp + 2, make_uint4(c_th, c_sf, c_so, 0u));
-                // Who plays next.  Without a trigger event it is the seat predicted (and
-                // prefetched) at the start of this turn.
-                int next = nseat;
-                bool over;
-                if (fin) {                       // final round (engine.py:533-548)
-                    stb = max(stb, score);
-                    over = next >= k;
-                } else if (score >= target) {    // this turn triggers it (engine.py:466-471)
-                    trigger = seat;
-                    stb = score;
-                    next = seat == 0 ? 1 : 0;
-                    over = next >= k;
-                } else {                         // next seat, or next round unless the safety
-                    over = false;                // limit is reached (engine.py:455)
-                    if (next == 0) {
-                        over = round >= max_rounds;
-                        if (!over) round++;
+                if (K2) {
+                    bool over = fin;  // the seat that did not trigger has had its final turn
+                    if (!fin) {
+                        if (score >= target) {  // this turn triggers the final round (engine.py:466-471)
+                            trigger = seat;
+                            stb = score;
+                        } else if (seat == 1) {  // next round unless the safety limit is reached
+                            over = round >= max_rounds;
+                            if (!over) round++;
+                        }
                     }
-                }
-                if (over || (err & FB_ROW_ROLL_LIMIT)) {
-                    P.header[g] = (uint32_t)round | (err & HDR_LONG) |
-                                  (((trigger < 0 ? FB_ROW_SAFETY_LIMIT : 0u) | (err & 0xffu)) << 16);
-                    status = ST_NEED;
-                } else {
-                    const bool staged = next == nseat && k > 1;
-                    seat = next;
-                    if (staged) {
-                        cp_async_wait_all();
-                        const uint4 m0 = lds128(stage), m1 = lds128(stage + STAGE_STRIDE);
-                        const uint4 m2 = lds128(stage + 2u * STAGE_STRIDE), i0 = lds128(stage + 3u * STAGE_STRIDE);
-                        const uint4 i1 = lds128(stage + 4u * STAGE_STRIDE);
-                        start_turn(m0, m1, m2, i0, i1);
+                    if (over || (err & FB_ROW_ROLL_LIMIT)) {
+                        P.header[g] = (uint32_t)round | (err & HDR_LONG) |
+                                      (((trigger < 0 ? FB_ROW_SAFETY_LIMIT : 0u) | (err & 0xffu)) << 16);
+                        status = ST_NEED;
                     } else {
-                        start_turn_from_l2();
+                        seat ^= 1;
+                        start_turn_staged(sp);  // the record parked above is the one that plays after next
+                    }
+                } else {
+                    // Who plays next.  Without a trigger event it is the seat predicted (and
+                    // prefetched) at the start of this turn.
+                    int next = nseat;
+                    bool over;
+                    if (fin) {                       // final round (engine.py:533-548)
+                        stb = max(stb, score);
+                        over = next >= k;
+                    } else if (score >= target) {    // this turn triggers it (engine.py:466-471)
+                        trigger = seat;
+                        stb = score;
+                        next = seat == 0 ? 1 : 0;
+                        over = next >= k;
+                    } else {                         // next seat, or next round unless the safety
+                        over = false;                // limit is reached (engine.py:455)
+                        if (next == 0) {
+                            over = round >= max_rounds;
+                            if (!over) round++;
+                        }
+                    }
+                    if (over || (err & FB_ROW_ROLL_LIMIT)) {
+                        P.header[g] = (uint32_t)round | (err & HDR_LONG) |
+                                      (((trigger < 0 ? FB_ROW_SAFETY_LIMIT : 0u) | (err & 0xffu)) << 16);
+                        status = ST_NEED;
+                    } else {
+                        const bool staged = next == nseat && k > 1;
+                        seat = next;
+                        if (staged) start_turn_staged(nullptr);
+                        else start_turn_from_l2();
                     }
                 }
             }
         }
+        return false;
+    };
+    // Two copies of the body per trip: the loop-carried seat state then alternates between two
+    // register sets instead of being moved back at the end of every iteration.
+    for (;;) {
+        if (roll_step()) break;
+        if (roll_step()) break;
     }
 
     // ---- work counters: warp shuffle -> shared memory -> one global RED per CTA ----

@@ -217,6 +217,33 @@ __device__ __forceinline__ uint32_t smart_discards(const ScoreLut* lut, uint32_t
     return lut->disc[dbase + (e >> 16) + (uint32_t)(xs * 6 + yd)];
 }
 
+// Shared-memory twins of the two lookups above for play_kernel: `lut_s` is the 32-bit
+// shared-space address of the ScoreLut copy, kept in one register for the whole kernel (taking the
+// generic pointer instead makes ptxas rebuild the shared-window base from SR_CgaCtaId every roll).
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lut_lookup_s(uint32_t lut_s, uint32_t tab_off, uint32_t hist) {
+    const uint32_t a = lds_u8(lut_s + (hist & 511u));
+    const uint32_t b = lds_u8(lut_s + LUT_IDX + (hist >> 9));
+    return lds_u32(lut_s + 2 * LUT_IDX + 4u * (tab_off + a * LUT_COMBOS + b));
+}
+__device__ __forceinline__ uint32_t smart_discards_s(uint32_t lut_s, uint32_t dbase, uint32_t e, int n, int ts,
+                                                     int st_d, int dt_d) {
+    const int score = (int)(e & 127u) * 50, used = (int)((e >> 7) & 7u);
+    int xs = min(max(ts + score - st_d + 50, 0), 399);
+    xs = (xs * 1311) >> 16;  // floor(xs / 50) for 0 <= xs <= 399
+    const int yd = min(max(dt_d - (n - used) + 1, 0), 5);
+    return lds_u8(lut_s + (2 * LUT_IDX + 4 * LUT_VARIANTS * LUT_TAB) + dbase + (e >> 16) + (uint32_t)(xs * 6 + yd));
+}
+
 // _decide_continue (strategies.py:125-162), branch free on the seat constants: a threshold
 // that is not considered can never "want" to go on, so OR gives the single-threshold answer.
 __device__ __forceinline__ bool decide_continue(int ts, int dice, int st_d, int dt_d, uint32_t kf) {
