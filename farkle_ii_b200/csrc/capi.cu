@@ -324,7 +324,7 @@ constexpr int PERM_WARPS = 4;
 __global__ void __launch_bounds__(PERM_WARPS * 32) permute_warp_kernel(uint64_t root, int k, uint64_t shuffle0,
                                                                       int n_shuffles, int n,
                                                                       const JumpTable* __restrict__ jt,
-                                                                      int32_t* out) {
+                                                                      int32_t* out, int32_t* inv) {
     extern __shared__ __align__(16) uint8_t perm_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = blockIdx.x * PERM_WARPS + warp;  // shuffle handled by this warp
@@ -380,11 +380,15 @@ __global__ void __launch_bounds__(PERM_WARPS * 32) permute_warp_kernel(uint64_t 
     __syncwarp();
     int32_t* dst = out + (size_t)j * n;
     for (int t = lane; t < n; t += 32) dst[t] = (int32_t)a[t];
+    if (inv) {  // inverse permutation: position of every strategy in this shuffle
+        int32_t* idst = inv + (size_t)j * n;
+        for (int t = lane; t < n; t += 32) idst[a[t]] = t;
+    }
 }
 
 // Fallback for grids too large for shared memory: the array lives in global memory.
 __global__ void __launch_bounds__(128) permute_kernel(uint64_t root, int k, uint64_t shuffle0,
-                                                      int n_shuffles, int n, int32_t* out) {
+                                                      int n_shuffles, int n, int32_t* out, int32_t* inv) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_shuffles) return;
     Coord c{FB_PURPOSE_SHUFFLE_PERMUTATION, root, (uint64_t)k, shuffle0 + (uint64_t)j, 0, 0, 0, 0, 0};
@@ -400,6 +404,10 @@ __global__ void __launch_bounds__(128) permute_kernel(uint64_t root, int k, uint
         const int32_t t = a[i];
         a[i] = a[v];
         a[v] = t;
+    }
+    if (inv) {
+        int32_t* ia = inv + (size_t)j * n;
+        for (int i = 0; i < n; i++) ia[a[i]] = i;
     }
 }
 
@@ -738,8 +746,8 @@ int fb_default_score(const uint8_t* faces_dev, const int32_t* turn_score_pre_dev
     return launch_check("default_score_kernel");
 }
 
-int fb_permute_shuffles(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles, int n_strategies,
-                        int32_t* perm_out_dev, void* stream) {
+static int permute_shuffles(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles, int n_strategies,
+                            int32_t* perm_out_dev, int32_t* inv_out_dev, void* stream) {
     FB_REQUIRE_INIT();
     if (n_shuffles < 0 || n_strategies < 1) return fail(FB_ERR_BAD_ARG, "bad shuffle or strategy count");
     if (n_shuffles == 0) return FB_OK;
@@ -749,12 +757,17 @@ int fb_permute_shuffles(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuf
         FB_CUDA(cudaFuncSetAttribute(permute_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         permute_warp_kernel<<<(n_shuffles + PERM_WARPS - 1) / PERM_WARPS, PERM_WARPS * 32, smem,
                               (cudaStream_t)stream>>>(root_seed, k, shuffle0, n_shuffles, n_strategies,
-                                                      g_ctx.jump_dev, perm_out_dev);
+                                                      g_ctx.jump_dev, perm_out_dev, inv_out_dev);
         return launch_check("permute_warp_kernel");
     }
     permute_kernel<<<blocks_for((uint64_t)n_shuffles, 128), 128, 0, (cudaStream_t)stream>>>(
-        root_seed, k, shuffle0, n_shuffles, n_strategies, perm_out_dev);
+        root_seed, k, shuffle0, n_shuffles, n_strategies, perm_out_dev, inv_out_dev);
     return launch_check("permute_kernel");
+}
+
+int fb_permute_shuffles(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles, int n_strategies,
+                        int32_t* perm_out_dev, void* stream) {
+    return permute_shuffles(root_seed, k, shuffle0, n_shuffles, n_strategies, perm_out_dev, nullptr, stream);
 }
 
 int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
@@ -776,11 +789,12 @@ int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuff
     if (n_games * (uint64_t)k > 0xfffffff0ull) return fail(FB_ERR_BAD_ARG, "more than 2^32 seats in one launch");
     Workspace w;
     const size_t perm_bytes = align_up((size_t)n_shuffles * n_strategies * 4, 256);
-    if (!carve(workspace_dev, workspace_bytes, k, n_games, w) || w.extra_bytes < perm_bytes)
+    if (!carve(workspace_dev, workspace_bytes, k, n_games, w) || w.extra_bytes < 2 * perm_bytes)
         return fail(FB_ERR_WORKSPACE, "workspace too small: need %zu bytes",
-                    ws_core_bytes(k, n_games) + perm_bytes);
+                    ws_core_bytes(k, n_games) + 2 * perm_bytes);
     int32_t* perm = reinterpret_cast<int32_t*>(w.extra);
-    int rc = fb_permute_shuffles(root_seed, k, shuffle0, n_shuffles, n_strategies, perm, stream);
+    int32_t* inv = tallies_dev ? reinterpret_cast<int32_t*>(w.extra + perm_bytes) : nullptr;
+    int rc = permute_shuffles(root_seed, k, shuffle0, n_shuffles, n_strategies, perm, inv, stream);
     if (rc) return rc;
     int32_t* limits = n_overrides > 0 ? w.limits : nullptr;
     FB_CUDA(cudaMemsetAsync(w.counter, 0, 2 * sizeof(unsigned int), stream));
@@ -815,15 +829,32 @@ int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuff
     F.totals = reinterpret_cast<unsigned long long*>(totals_dev);
     F.rows = reinterpret_cast<uint32_t*>(rows_dev);
     F.row_words = (int)(fb_row_stride(k) / 4);
-    if (F.tallies) {
-        F.dense_exposure = 1;
-        const int n_slots = shuffles_per_slot > 0 ? (n_shuffles + shuffles_per_slot - 1) / shuffles_per_slot : 1;
-        exposure_kernel<<<dim3(blocks_for((uint64_t)n_strategies, 256), (unsigned)n_slots), 256, 0, stream>>>(
-            F.tallies, strategy_ids_dev, n_strategies, n_tally_ids, n_shuffles, shuffles_per_slot);
-        rc = launch_check("exposure_kernel");
-        if (rc) return rc;
-    }
-    return launch_play(P, F, stream);
+    if (!F.tallies) return launch_play(P, F, stream);
+    // tallies: exposures per slot now, winner metrics by gather after the finish pass
+    const int n_slots = shuffles_per_slot > 0 ? (n_shuffles + shuffles_per_slot - 1) / shuffles_per_slot : 1;
+    exposure_kernel<<<dim3(blocks_for((uint64_t)n_strategies, 256), (unsigned)n_slots), 256, 0, stream>>>(
+        F.tallies, strategy_ids_dev, n_strategies, n_tally_ids, n_shuffles, shuffles_per_slot);
+    rc = launch_check("exposure_kernel");
+    if (rc) return rc;
+    F.mark_winner = 1;
+    rc = launch_play(P, F, stream);
+    if (rc) return rc;
+    GatherParams G{};
+    G.seats = w.seats;
+    G.header = w.header;
+    G.inv = inv;
+    G.strategy_ids = strategy_ids_dev;
+    G.n_strategies = n_strategies;
+    G.n_tally_ids = n_tally_ids;
+    G.n_shuffles = n_shuffles;
+    G.k = k;
+    G.gps = gps;
+    G.chunk = shuffles_per_slot > 0 ? shuffles_per_slot : 43;
+    G.slotted = shuffles_per_slot > 0;
+    G.tallies = F.tallies;
+    const int n_chunks = (n_shuffles + G.chunk - 1) / G.chunk;
+    tally_gather_kernel<<<dim3(blocks_for((uint64_t)n_strategies, 128), (unsigned)n_chunks), 128, 0, stream>>>(G);
+    return launch_check("tally_gather_kernel");
 }
 
 int fb_play_h2h(uint64_t root_seed, int n_blocks, const uint64_t* pair_id_dev, const uint8_t* order_dev,
@@ -960,7 +991,7 @@ int fb_run_tournament_host(uint64_t root_seed, int k, uint64_t shuffle0, int n_s
     const size_t tally_b = align_up((size_t)n_slots * n_tally_ids * FB_TALLY_WIDTH * 8, 256);
     const size_t totals_b = 256;
     const size_t rows_b = rows_host ? align_up(n_games * fb_row_stride(k), 256) : 0;
-    const size_t ws_b = fb_workspace_bytes(k, n_games) + align_up((size_t)n_shuffles * n_strategies * 4, 256);
+    const size_t ws_b = fb_workspace_bytes(k, n_games) + 2 * align_up((size_t)n_shuffles * n_strategies * 4, 256);
     const size_t total = strat_b + ids_b + tally_b + totals_b + rows_b + ws_b;
     std::lock_guard<std::mutex> lock(g_mu);
     if (g_ctx.host_ws_bytes < total) {

@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
 // ---------------------------------------------------------------------------
 struct FinishParams {
     const Seat* seats;
-    const uint32_t* header;
+    uint32_t* header;
     const int32_t* strategy_ids;  // id of table entry (ids_mode 1)
     int ids_mode;                 // 0 id = table index, 1 id = strategy_ids[index], 2 id = seat
     const uint64_t* game_seed;    // [n_games] or nullptr
@@ -435,10 +435,8 @@ struct FinishParams {
     int k;
     uint32_t games_per_slot;  // 0 = one tally slot
     int n_tally_ids;
-    int dense_exposure;           // 1: every id is seated exactly once per shuffle, so attempted /
-                                  // completed exposures are added per slot by exposure_kernel and
-                                  // only safety-limit games touch them here
-    unsigned long long* tallies;  // [slots][ids][26] or nullptr
+    int mark_winner;              // 1: write winner seat + 1 into header bits 24..27 for the gather pass
+    unsigned long long* tallies;  // [slots][ids][26] or nullptr (filled by tally_gather_kernel)
     unsigned long long* totals;   // [FB_TOTALS_WIDTH] or nullptr
     uint32_t* rows;               // or nullptr
     int row_words;
@@ -482,11 +480,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
         t_err = (flags & (FB_ROW_ROLL_LIMIT | FB_ROW_I16_OVERFLOW)) ? 1u : 0u;
         if (F.outcome)
             F.outcome[g] = (uint8_t)((safety ? 0 : winner + 1) | ((flags & ~FB_ROW_SAFETY_LIMIT) ? 0x80 : 0));
-        unsigned long long* T = nullptr;
-        if (F.tallies) {
-            const uint32_t slot = F.games_per_slot ? g / F.games_per_slot : 0u;
-            T = F.tallies + (size_t)slot * (size_t)F.n_tally_ids * FB_TALLY_WIDTH;
-        }
+        if (F.mark_winner) F.header[g] = hdr | ((uint32_t)(winner + 1) << 24);
         uint32_t* row = F.rows ? F.rows + (size_t)g * F.row_words : nullptr;
         if (row) {
             const uint64_t gs = F.game_seed ? F.game_seed[g] : 0ull;
@@ -494,47 +488,20 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
                 make_uint4((uint32_t)gs, (uint32_t)(gs >> 32), g,
                            rounds | ((uint32_t)(safety ? 0xFF : winner) << 16) | (flags << 24));
         }
-        // pass 2: rows, exposures, winner metrics
-        for (int s = 0; s < k; s++) {
+        // pass 2: the compact row
+        for (int s = 0; row && s < k; s++) {
             const uint4 a = __ldcg(&seats[s].a);
             const uint4 b = __ldcg(&seats[s].b);
             const uint32_t idx = __ldcg(&seats[s].cst.w);
             const int sid = F.ids_mode == 0 ? (int)idx : (F.ids_mode == 1 ? F.strategy_ids[idx] : s);
-            if (row) {
-                uint32_t* w = row + 4 + s * 7;
-                w[0] = a.y;
-                w[1] = (uint32_t)sid;
-                w[2] = a.z & HIGH_MASK;
-                w[3] = a.w;
-                w[4] = b.x;
-                w[5] = b.y;
-                w[6] = b.z;
-            }
-            if (T) {
-                unsigned long long* Ts = T + (size_t)sid * FB_TALLY_WIDTH;
-                if (!F.dense_exposure) {
-                    atomicAdd(&Ts[1], 1ull);
-                    atomicAdd(&Ts[safety ? 3 : 2], 1ull);
-                } else if (safety) {  // move one exposure from "completed" to "safety limit"
-                    atomicAdd(&Ts[3], 1ull);
-                    atomicAdd(&Ts[2], ~0ull);
-                }
-                if (s == winner) {
-                    // METRIC_LABELS order, run_tournament.py:109-121; winner_hit_max_rounds is
-                    // False for every completed game, so its sums stay 0.  Zero addends are skipped.
-                    const unsigned long long m[10] = {a.y, rounds, a.w & 0xffffu, a.w >> 16,
-                                                      a.z & HIGH_MASK, b.y & 0xffffu, b.y >> 16,
-                                                      b.z & 0xffffu, b.z >> 16, b.x >> 16};
-                    atomicAdd(&Ts[0], 1ull);
-#pragma unroll
-                    for (int j = 0; j < 10; j++) {
-                        if (m[j]) {
-                            atomicAdd(&Ts[4 + j], m[j]);
-                            atomicAdd(&Ts[4 + FB_N_METRICS + j], m[j] * m[j]);
-                        }
-                    }
-                }
-            }
+            uint32_t* w = row + 4 + s * 7;
+            w[0] = a.y;
+            w[1] = (uint32_t)sid;
+            w[2] = a.z & HIGH_MASK;
+            w[3] = a.w;
+            w[4] = b.x;
+            w[5] = b.y;
+            w[6] = b.z;
         }
         if (row) {
             for (int w = 4 + 7 * k; w < F.row_words; w++) row[w] = 0u;  // padding
@@ -577,6 +544,67 @@ __global__ void exposure_kernel(unsigned long long* tallies, const int32_t* stra
     unsigned long long* Ts = tallies + ((size_t)slot * n_tally_ids + sid) * FB_TALLY_WIDTH;
     atomicAdd(&Ts[1], (unsigned long long)cnt);
     atomicAdd(&Ts[2], (unsigned long long)cnt);
+}
+
+// Winner tallies by gather (run_tournament.py:375-391).  Every strategy is seated exactly once per
+// shuffle, so thread (strategy i, chunk c) walks the chunk's shuffles, finds its game through the
+// inverse permutation, and — if it won — adds the winner metrics from its seat record into
+// registers; one RED per non-zero column at the end.  ~25x fewer L2 atomics than adding per game.
+struct GatherParams {
+    const Seat* seats;
+    const uint32_t* header;  // rounds | flags << 16 | (winner seat + 1) << 24
+    const int32_t* inv;      // [n_shuffles][n_strategies] position of strategy i in shuffle j
+    const int32_t* strategy_ids;
+    int n_strategies, n_tally_ids, n_shuffles, k;
+    uint32_t gps;
+    int chunk;    // shuffles per thread
+    int slotted;  // 1: chunk c -> tally slot c, 0: single slot
+    unsigned long long* tallies;
+};
+
+__global__ void __launch_bounds__(128) tally_gather_kernel(const GatherParams G) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G.n_strategies) return;
+    const int c = blockIdx.y;
+    const int j0 = c * G.chunk, j1 = min(j0 + G.chunk, G.n_shuffles);
+    unsigned long long wins = 0, safety = 0, sum[10], sq[10];
+#pragma unroll
+    for (int m = 0; m < 10; m++) sum[m] = sq[m] = 0ull;
+    for (int j = j0; j < j1; j++) {
+        const uint32_t pos = (uint32_t)G.inv[(size_t)j * G.n_strategies + i];
+        const uint32_t gi = pos / (uint32_t)G.k, seat = pos - gi * (uint32_t)G.k;
+        const uint32_t game = (uint32_t)j * G.gps + gi;
+        const uint32_t hdr = __ldg(&G.header[game]);
+        if ((hdr >> 16) & FB_ROW_SAFETY_LIMIT) {
+            safety++;
+        } else if (((hdr >> 24) & 15u) == seat + 1u) {
+            const Seat* s = G.seats + ((size_t)game * G.k + seat);
+            const uint4 a = __ldg(&s->a), b = __ldg(&s->b);
+            // METRIC_LABELS order, run_tournament.py:109-121 (winner_hit_max_rounds stays 0)
+            const unsigned long long v[10] = {a.y, hdr & 0xffffu, a.w & 0xffffu, a.w >> 16, a.z & HIGH_MASK,
+                                              b.y & 0xffffu, b.y >> 16, b.z & 0xffffu, b.z >> 16, b.x >> 16};
+            wins++;
+#pragma unroll
+            for (int m = 0; m < 10; m++) {
+                sum[m] += v[m];
+                sq[m] += v[m] * v[m];
+            }
+        }
+    }
+    const int sid = G.strategy_ids ? G.strategy_ids[i] : i;
+    unsigned long long* T = G.tallies + ((size_t)(G.slotted ? c : 0) * G.n_tally_ids + sid) * FB_TALLY_WIDTH;
+    if (wins) atomicAdd(&T[0], wins);
+    if (safety) {  // move exposures from "completed" (added by exposure_kernel) to "safety limit"
+        atomicAdd(&T[3], safety);
+        atomicAdd(&T[2], 0ull - safety);
+    }
+#pragma unroll
+    for (int m = 0; m < 10; m++) {
+        if (sum[m]) {
+            atomicAdd(&T[4 + m], sum[m]);
+            atomicAdd(&T[4 + FB_N_METRICS + m], sq[m]);
+        }
+    }
 }
 
 }  // namespace fb

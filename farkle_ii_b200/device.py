@@ -246,7 +246,7 @@ class Engine:
             d_os = self.to_device(np.array([o[0] for o in ov], dtype=np.uint64))
             d_og = self.to_device(np.array([o[1] for o in ov], dtype=np.uint32))
             d_om = self.to_device(np.array([o[2] for o in ov], dtype=np.int32))
-        ws_bytes = self.workspace_bytes(max(k, 1), n_games) + n_shuffles * n_strategies * 4 + 512
+        ws_bytes = self.workspace_bytes(max(k, 1), n_games) + 2 * (n_shuffles * n_strategies * 4 + 256)
         ws = self.workspace(ws_bytes)
         _native.check(self.lib.fb_play_tournament(
             root_seed, k, shuffle0, n_shuffles, _ptr(strategies), _ptr(d_ids), n_strategies,

@@ -208,7 +208,8 @@ int fb_permute_shuffles(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuf
  *                    bytes in (shuffle, game) order; may be NULL.
  *  want_game_seeds   also compute the purpose-102 fingerprints for rows.
  *  workspace_dev     >= fb_workspace_bytes(k, n_shuffles * (n_strategies/k))
- *                    + n_shuffles * n_strategies * 4 bytes.
+ *                    + 2 * align256(n_shuffles * n_strategies * 4) bytes (the
+ *                    permutations and their inverses).
  */
 int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
                        const fb_strategy_t* strategies_dev, const int32_t* strategy_ids_dev,
