@@ -47,6 +47,7 @@ struct Ctx {
     // cached buffers of fb_run_tournament_host
     void* host_ws = nullptr;
     size_t host_ws_bytes = 0;
+    bool smem_opted = false;  // play_kernel dynamic shared memory opt-in done on this device
 };
 Ctx g_ctx;
 std::mutex g_mu;
@@ -96,13 +97,15 @@ struct Workspace {
     int32_t* limits;
     unsigned int* counter;  // [0] play ordinal, [1] number of HDR_LONG games
     uint32_t* long_list;    // [n_games] worst case
+    uint8_t* prefix;        // [n_shuffles or n_blocks] uint4 stream-prefix pools (<= n_games entries)
     uint8_t* extra;  // mode specific tail (perm / h2h tables)
     size_t extra_bytes;
 };
 
 size_t ws_core_bytes(int k, uint64_t n) {
     return align_up(n * (uint64_t)k * sizeof(Seat), 256) +
-           align_up(n * 4, 256) + align_up(n * 8, 256) + align_up(n * 8, 256) + 256 + align_up(n * 4, 256);
+           align_up(n * 4, 256) + align_up(n * 8, 256) + align_up(n * 8, 256) + 256 + align_up(n * 4, 256) +
+           align_up(n * 16, 256);
 }
 
 bool carve(void* base, size_t bytes, int k, uint64_t n, Workspace& w) {
@@ -121,6 +124,8 @@ bool carve(void* base, size_t bytes, int k, uint64_t n, Workspace& w) {
     p += 256;
     w.long_list = reinterpret_cast<uint32_t*>(p);
     p += align_up(n * 4, 256);
+    w.prefix = p;
+    p += align_up(n * 16, 256);
     w.extra = p;
     w.extra_bytes = bytes - core;
     return true;
@@ -177,7 +182,7 @@ __global__ void __launch_bounds__(256) seed_tournament_kernel(
     int n_strategies, int32_t target, int32_t max_rounds, const uint64_t* ov_shuffle,
     const uint32_t* ov_game, const int32_t* ov_rounds, int n_ov, int want_seeds,
     const fb_strategy_t* table, Seat* seats, uint64_t* game_seed, int32_t* limits,
-    uint32_t* header, uint32_t* long_list, unsigned int* counter) {
+    uint32_t* header, uint32_t* long_list, unsigned int* counter, const uint4* prefix) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t < n_games * (uint64_t)k;
     const uint64_t g = live ? t / (uint64_t)k : 0;
@@ -188,7 +193,10 @@ __global__ void __launch_bounds__(256) seed_tournament_kernel(
     if (live) {
         Coord c{FB_PURPOSE_TOURNAMENT_PLAYER, root, (uint64_t)k, shuffle0 + sl, 0, 0, gi, s, 0};
         Pcg pg;
-        pcg_seed_coord(pg, c);
+        const uint4 pre = prefix[sl];  // hash of the 12 coordinate words shared by the shuffle
+        uint32_t pool[4] = {pre.x, pre.y, pre.z, pre.w};
+        ss_pool_suffix(pool, gi, s, 0);
+        pcg_seed_pool(pg, pool);
         const int32_t* seat_ids = perm + sl * (uint64_t)n_strategies + (uint64_t)gi * k;
         store_seat(seats + t, pg, table, (uint32_t)seat_ids[s]);
         if (s == 0) {
@@ -240,12 +248,23 @@ __global__ void h2h_offsets_kernel(const uint32_t* n_attempts, int n_blocks, uin
     if (threadIdx.x == 0) offsets[n_blocks] = carry;
 }
 
+// Shared 12-word stream prefix of every H2H block (root, k = 2, pair_id, order).
+__global__ void h2h_prefix_kernel(uint64_t root, int n_blocks, const uint64_t* pair_id, const uint8_t* order,
+                                  uint4* prefix) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    Coord pc{FB_PURPOSE_H2H_PLAYER, root, 2, 0, pair_id[b], order[b], 0, 0, 0};
+    uint32_t pool[4];
+    ss_pool_prefix(pc, pool);
+    prefix[b] = make_uint4(pool[0], pool[1], pool[2], pool[3]);
+}
+
 // One thread per (attempt, seat) (h2h_schedule.py:1169-1202).
 __global__ void __launch_bounds__(256) seed_h2h_kernel(
     uint64_t root, int n_blocks, const uint64_t* pair_id, const uint8_t* order,
     const fb_strategy_t* seat1, const fb_strategy_t* seat2, const uint32_t* attempt0,
     const uint64_t* offsets, uint64_t total, int want_seeds, Seat* seats,
-    uint64_t* game_seed, uint32_t* header, uint32_t* long_list, unsigned int* counter) {
+    uint64_t* game_seed, uint32_t* header, uint32_t* long_list, unsigned int* counter, const uint4* prefix) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t < total * 2;
     const uint64_t g = live ? t >> 1 : 0;
@@ -261,7 +280,10 @@ __global__ void __launch_bounds__(256) seed_h2h_kernel(
         const uint64_t a = (uint64_t)attempt0[b] + (g - offsets[b]);
         Coord c{FB_PURPOSE_H2H_PLAYER, root, 2, 0, pair_id[b], order[b], a, s, 0};
         Pcg pg;
-        pcg_seed_coord(pg, c);
+        const uint4 pre = prefix[b];
+        uint32_t pool[4] = {pre.x, pre.y, pre.z, pre.w};
+        ss_pool_suffix(pool, a, s, 0);
+        pcg_seed_pool(pg, pool);
         store_seat(seats + t, pg, s ? seat2 : seat1, (uint32_t)b);
         if (s == 0) {
             is_long = entry_never_banks(seat1, (uint32_t)b) && entry_never_banks(seat2, (uint32_t)b);
@@ -324,7 +346,7 @@ constexpr int PERM_WARPS = 4;
 __global__ void __launch_bounds__(PERM_WARPS * 32) permute_warp_kernel(uint64_t root, int k, uint64_t shuffle0,
                                                                       int n_shuffles, int n,
                                                                       const JumpTable* __restrict__ jt,
-                                                                      int32_t* out, int32_t* inv) {
+                                                                      int32_t* out, int32_t* inv, uint4* prefix) {
     extern __shared__ __align__(16) uint8_t perm_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = blockIdx.x * PERM_WARPS + warp;  // shuffle handled by this warp
@@ -384,11 +406,18 @@ __global__ void __launch_bounds__(PERM_WARPS * 32) permute_warp_kernel(uint64_t 
         int32_t* idst = inv + (size_t)j * n;
         for (int t = lane; t < n; t += 32) idst[a[t]] = t;
     }
+    if (prefix && lane == 0) {  // shared 12-word prefix of this shuffle's seat streams (ss_pool_prefix)
+        Coord pc{FB_PURPOSE_TOURNAMENT_PLAYER, root, (uint64_t)k, shuffle0 + (uint64_t)j, 0, 0, 0, 0, 0};
+        uint32_t pool[4];
+        ss_pool_prefix(pc, pool);
+        prefix[j] = make_uint4(pool[0], pool[1], pool[2], pool[3]);
+    }
 }
 
 // Fallback for grids too large for shared memory: the array lives in global memory.
 __global__ void __launch_bounds__(128) permute_kernel(uint64_t root, int k, uint64_t shuffle0,
-                                                      int n_shuffles, int n, int32_t* out, int32_t* inv) {
+                                                      int n_shuffles, int n, int32_t* out, int32_t* inv,
+                                                      uint4* prefix) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_shuffles) return;
     Coord c{FB_PURPOSE_SHUFFLE_PERMUTATION, root, (uint64_t)k, shuffle0 + (uint64_t)j, 0, 0, 0, 0, 0};
@@ -408,6 +437,12 @@ __global__ void __launch_bounds__(128) permute_kernel(uint64_t root, int k, uint
     if (inv) {
         int32_t* ia = inv + (size_t)j * n;
         for (int i = 0; i < n; i++) ia[a[i]] = i;
+    }
+    if (prefix) {
+        Coord pc{FB_PURPOSE_TOURNAMENT_PLAYER, root, (uint64_t)k, shuffle0 + (uint64_t)j, 0, 0, 0, 0, 0};
+        uint32_t pool[4];
+        ss_pool_prefix(pc, pool);
+        prefix[j] = make_uint4(pool[0], pool[1], pool[2], pool[3]);
     }
 }
 
@@ -599,13 +634,12 @@ int launch_play(const PlayParams& P, const FinishParams& F, cudaStream_t stream)
         }
     }
     const size_t smem = PLAY_SMEM_BYTES;
-    static bool smem_opted = false;
-    if (!smem_opted) {
+    if (!g_ctx.smem_opted) {
         FB_CUDA(cudaFuncSetAttribute(play_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         FB_CUDA(cudaFuncSetAttribute(play_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         FB_CUDA(cudaFuncSetAttribute(play_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         FB_CUDA(cudaFuncSetAttribute(play_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_opted = true;
+        g_ctx.smem_opted = true;
     }
     if (!t_ev0) {
         FB_CUDA(cudaEventCreate(&t_ev0));
@@ -678,6 +712,7 @@ int fb_init(int device) {
         FB_CUDA(cudaMemcpy(g_ctx.jump_dev, &jt, sizeof(JumpTable), cudaMemcpyHostToDevice));
     }
     g_ctx.device = device;
+    g_ctx.smem_opted = false;
     return FB_OK;
 }
 
@@ -747,7 +782,7 @@ int fb_default_score(const uint8_t* faces_dev, const int32_t* turn_score_pre_dev
 }
 
 static int permute_shuffles(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles, int n_strategies,
-                            int32_t* perm_out_dev, int32_t* inv_out_dev, void* stream) {
+                            int32_t* perm_out_dev, int32_t* inv_out_dev, uint4* prefix_out_dev, void* stream) {
     FB_REQUIRE_INIT();
     if (n_shuffles < 0 || n_strategies < 1) return fail(FB_ERR_BAD_ARG, "bad shuffle or strategy count");
     if (n_shuffles == 0) return FB_OK;
@@ -757,17 +792,17 @@ static int permute_shuffles(uint64_t root_seed, int k, uint64_t shuffle0, int n_
         FB_CUDA(cudaFuncSetAttribute(permute_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         permute_warp_kernel<<<(n_shuffles + PERM_WARPS - 1) / PERM_WARPS, PERM_WARPS * 32, smem,
                               (cudaStream_t)stream>>>(root_seed, k, shuffle0, n_shuffles, n_strategies,
-                                                      g_ctx.jump_dev, perm_out_dev, inv_out_dev);
+                                                      g_ctx.jump_dev, perm_out_dev, inv_out_dev, prefix_out_dev);
         return launch_check("permute_warp_kernel");
     }
     permute_kernel<<<blocks_for((uint64_t)n_shuffles, 128), 128, 0, (cudaStream_t)stream>>>(
-        root_seed, k, shuffle0, n_shuffles, n_strategies, perm_out_dev, inv_out_dev);
+        root_seed, k, shuffle0, n_shuffles, n_strategies, perm_out_dev, inv_out_dev, prefix_out_dev);
     return launch_check("permute_kernel");
 }
 
 int fb_permute_shuffles(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles, int n_strategies,
                         int32_t* perm_out_dev, void* stream) {
-    return permute_shuffles(root_seed, k, shuffle0, n_shuffles, n_strategies, perm_out_dev, nullptr, stream);
+    return permute_shuffles(root_seed, k, shuffle0, n_shuffles, n_strategies, perm_out_dev, nullptr, nullptr, stream);
 }
 
 int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
@@ -794,14 +829,15 @@ int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuff
                     ws_core_bytes(k, n_games) + 2 * perm_bytes);
     int32_t* perm = reinterpret_cast<int32_t*>(w.extra);
     int32_t* inv = tallies_dev ? reinterpret_cast<int32_t*>(w.extra + perm_bytes) : nullptr;
-    int rc = permute_shuffles(root_seed, k, shuffle0, n_shuffles, n_strategies, perm, inv, stream);
+    uint4* prefix = reinterpret_cast<uint4*>(w.prefix);
+    int rc = permute_shuffles(root_seed, k, shuffle0, n_shuffles, n_strategies, perm, inv, prefix, stream);
     if (rc) return rc;
     int32_t* limits = n_overrides > 0 ? w.limits : nullptr;
     FB_CUDA(cudaMemsetAsync(w.counter, 0, 2 * sizeof(unsigned int), stream));
     seed_tournament_kernel<<<blocks_for(n_games * k, 256), 256, 0, stream>>>(
         root_seed, k, shuffle0, gps, n_games, perm, n_strategies, target_score, max_rounds,
         override_shuffle_dev, override_game_dev, override_max_rounds_dev, n_overrides, want_game_seeds,
-        strategies_dev, w.seats, w.game_seed, limits, w.header, w.long_list, w.counter);
+        strategies_dev, w.seats, w.game_seed, limits, w.header, w.long_list, w.counter, prefix);
     rc = launch_check("seed_tournament_kernel");
     if (rc) return rc;
     PlayParams P{};
@@ -869,18 +905,24 @@ int fb_play_h2h(uint64_t root_seed, int n_blocks, const uint64_t* pair_id_dev, c
     if (total_attempts * 2 > 0xfffffff0ull) return fail(FB_ERR_BAD_ARG, "more than 2^31 attempts in one launch");
     Workspace w;
     const size_t off_bytes = align_up((size_t)(n_blocks + 1) * 8, 256);
-    if (!carve(workspace_dev, workspace_bytes, 2, total_attempts, w) || w.extra_bytes < off_bytes)
+    const size_t pre_bytes = align_up((size_t)n_blocks * 16, 256);
+    if (!carve(workspace_dev, workspace_bytes, 2, total_attempts, w) || w.extra_bytes < off_bytes + pre_bytes)
         return fail(FB_ERR_WORKSPACE, "workspace too small: need %zu bytes",
-                    ws_core_bytes(2, total_attempts) + off_bytes);
+                    ws_core_bytes(2, total_attempts) + off_bytes + pre_bytes);
     uint64_t* offsets = reinterpret_cast<uint64_t*>(w.extra);
     h2h_offsets_kernel<<<1, 1024, 0, stream>>>(n_attempts_dev, n_blocks, offsets);
     int rc = launch_check("h2h_offsets_kernel");
     if (rc) return rc;
     const int want_seeds = rows_dev != nullptr;
     FB_CUDA(cudaMemsetAsync(w.counter, 0, 2 * sizeof(unsigned int), stream));
+    uint4* prefix = reinterpret_cast<uint4*>(w.extra + off_bytes);
+    h2h_prefix_kernel<<<blocks_for((uint64_t)n_blocks, 128), 128, 0, stream>>>(root_seed, n_blocks, pair_id_dev,
+                                                                               order_dev, prefix);
+    rc = launch_check("h2h_prefix_kernel");
+    if (rc) return rc;
     seed_h2h_kernel<<<blocks_for(total_attempts * 2, 256), 256, 0, stream>>>(
         root_seed, n_blocks, pair_id_dev, order_dev, seat1_dev, seat2_dev, attempt0_dev, offsets,
-        total_attempts, want_seeds, w.seats, w.game_seed, w.header, w.long_list, w.counter);
+        total_attempts, want_seeds, w.seats, w.game_seed, w.header, w.long_list, w.counter, prefix);
     rc = launch_check("seed_h2h_kernel");
     if (rc) return rc;
     PlayParams P{};

@@ -65,6 +65,47 @@ __host__ __device__ __forceinline__ void ss_pool_coord(const Coord& c, uint32_t 
         for (int d = 0; d < 4; d++) pool[d] = ss_mix(pool[d], ss_hashmix(e[s], hc));
 }
 
+// The same pool in two stages.  Words 0..11 (scheme, purpose, root_seed, k, shuffle_index, pair_id,
+// order) are shared by every seat of a shuffle / H2H block, so the seed kernels hash them once
+// per shuffle and every (game, seat) thread only absorbs the last six words.  The hash-constant
+// chain is data independent: after n hashmix calls it is INIT_A * MULT_A^n.
+__host__ __device__ constexpr uint32_t ss_hash_const_after(int calls) {
+    uint32_t h = SS_INIT_A;
+    for (int i = 0; i < calls; i++) h *= SS_MULT_A;
+    return h;
+}
+constexpr int SS_PREFIX_WORDS = 12;
+constexpr int SS_PREFIX_CALLS = 4 + 12 + 4 * (SS_PREFIX_WORDS - 4);  // 48
+__host__ __device__ __forceinline__ void ss_pool_prefix(const Coord& c, uint32_t pool[4]) {
+    const uint32_t e[SS_PREFIX_WORDS] = {2u, c.purpose, (uint32_t)c.root_seed, (uint32_t)(c.root_seed >> 32),
+                                         (uint32_t)c.k, (uint32_t)(c.k >> 32), (uint32_t)c.shuffle_index,
+                                         (uint32_t)(c.shuffle_index >> 32), (uint32_t)c.pair_id,
+                                         (uint32_t)(c.pair_id >> 32), (uint32_t)c.order, (uint32_t)(c.order >> 32)};
+    uint32_t hc = SS_INIT_A;
+#pragma unroll
+    for (int i = 0; i < 4; i++) pool[i] = ss_hashmix(e[i], hc);
+#pragma unroll
+    for (int s = 0; s < 4; s++)
+#pragma unroll
+        for (int d = 0; d < 4; d++)
+            if (s != d) pool[d] = ss_mix(pool[d], ss_hashmix(pool[s], hc));
+#pragma unroll
+    for (int s = 4; s < SS_PREFIX_WORDS; s++)
+#pragma unroll
+        for (int d = 0; d < 4; d++) pool[d] = ss_mix(pool[d], ss_hashmix(e[s], hc));
+}
+__host__ __device__ __forceinline__ void ss_pool_suffix(uint32_t pool[4], uint64_t game_index, uint64_t seat_index,
+                                                        uint64_t replicate_index) {
+    const uint32_t e[6] = {(uint32_t)game_index, (uint32_t)(game_index >> 32), (uint32_t)seat_index,
+                           (uint32_t)(seat_index >> 32), (uint32_t)replicate_index,
+                           (uint32_t)(replicate_index >> 32)};
+    uint32_t hc = ss_hash_const_after(SS_PREFIX_CALLS);
+#pragma unroll
+    for (int s = 0; s < 6; s++)
+#pragma unroll
+        for (int d = 0; d < 4; d++) pool[d] = ss_mix(pool[d], ss_hashmix(e[s], hc));
+}
+
 // Generic pool for arbitrary entropy (fb_seedseq_generate).
 __host__ __device__ inline void ss_pool_generic(const uint32_t* e, int n, uint32_t pool[4]) {
     uint32_t hc = SS_INIT_A;
@@ -132,6 +173,12 @@ __host__ __device__ __forceinline__ void pcg_seed_words(Pcg& g, const uint32_t w
     g.hi = g.hi + w0 + (nlo < g.lo ? 1u : 0u);
     g.lo = nlo;
     pcg_step_full(g);
+}
+
+__host__ __device__ __forceinline__ void pcg_seed_pool(Pcg& g, const uint32_t pool[4]) {
+    uint32_t w[8];
+    ss_generate<8>(pool, w);
+    pcg_seed_words(g, w);
 }
 
 __host__ __device__ __forceinline__ void pcg_seed_coord(Pcg& g, const Coord& c) {

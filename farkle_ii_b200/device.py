@@ -299,7 +299,7 @@ class Engine:
             rows = torch.empty((max(total, 1), row_stride(2)), dtype=torch.uint8,
                                device=self.device)[:total]
         totals = torch.zeros(TOTALS_WIDTH, dtype=torch.int64, device=self.device)
-        ws = self.workspace(self.workspace_bytes(2, total) + (nb + 1) * 8 + nb * 16 + 1024)
+        ws = self.workspace(self.workspace_bytes(2, total) + (nb + 1) * 8 + nb * 16 + 1024 + 512)
         _native.check(self.lib.fb_play_h2h(root_seed, nb, _ptr(d_pair), _ptr(d_order), _ptr(d_s1),
                                            _ptr(d_s2), _ptr(d_a0), _ptr(d_na), total, target_score,
                                            max_rounds, _ptr(outcome), _ptr(rows), _ptr(totals),

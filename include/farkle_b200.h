@@ -228,6 +228,8 @@ int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuff
  * 0 safety limit, 1 P1 won, 2 P2 won, |0x80 if the row carries an error flag.
  * The reference's early stop ("break once games_completed >= target") is a
  * prefix property of this sequence; fb_h2h_resolve applies it.
+ * workspace_dev >= fb_workspace_bytes(2, total_attempts)
+ *                  + align256((n_blocks + 1) * 8) + align256(n_blocks * 16) bytes.
  */
 int fb_play_h2h(uint64_t root_seed, int n_blocks, const uint64_t* pair_id_dev,
                 const uint8_t* order_dev, const fb_strategy_t* seat1_dev,
