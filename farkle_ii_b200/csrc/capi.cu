@@ -341,32 +341,45 @@ __device__ __forceinline__ void mul128(uint64_t ahi, uint64_t alo, uint64_t bhi,
     rhi = __umul64hi(alo, blo) + alo * bhi + ahi * blo;
 }
 
-constexpr int PERM_WARPS = 4;
+// Sub-warp layout: PERM_LANES lanes share one shuffle (they execute the identical walk on the same
+// array, which is what keeps the array consistent without locks), so a warp carries
+// PERM_SHUFFLES different shuffles through the same instruction stream.  The swap chain is
+// latency bound; running four chains per warp cuts the issue slots per shuffle by four.
+constexpr int PERM_LANES = 8;
+constexpr int PERM_SHUFFLES = 32 / PERM_LANES;  // per warp (= per CTA: one warp per CTA)
+constexpr int PERM_RING = 2 * PERM_LANES;       // 32-bit draws per batch and shuffle
 
-__global__ void __launch_bounds__(PERM_WARPS * 32) permute_warp_kernel(uint64_t root, int k, uint64_t shuffle0,
-                                                                      int n_shuffles, int n,
-                                                                      const JumpTable* __restrict__ jt,
-                                                                      int32_t* out, int32_t* inv, uint4* prefix) {
+__host__ __device__ inline size_t perm_bytes_per_shuffle(int n) {
+    return (((size_t)n * 2 + 15) & ~(size_t)15) + PERM_RING * 4;
+}
+
+__global__ void __launch_bounds__(32) permute_warp_kernel(uint64_t root, int k, uint64_t shuffle0,
+                                                          int n_shuffles, int n,
+                                                          const JumpTable* __restrict__ jt,
+                                                          int32_t* out, int32_t* inv, uint4* prefix) {
     extern __shared__ __align__(16) uint8_t perm_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j = blockIdx.x * PERM_WARPS + warp;  // shuffle handled by this warp
-    const size_t per_warp = (((size_t)n * 2 + 15) & ~(size_t)15) + 64 * 4;
-    uint16_t* a = reinterpret_cast<uint16_t*>(perm_smem + warp * per_warp);
-    uint32_t* ring = reinterpret_cast<uint32_t*>(perm_smem + warp * per_warp + (per_warp - 64 * 4));
-    if (j >= n_shuffles) return;
-    for (int i = lane; i < n; i += 32) a[i] = (uint16_t)i;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / PERM_LANES, sl = lane % PERM_LANES;
+    const int j = blockIdx.x * PERM_SHUFFLES + sub;  // shuffle handled by this lane group
+    const bool valid = j < n_shuffles;
+    const size_t per = perm_bytes_per_shuffle(n);
+    uint16_t* a = reinterpret_cast<uint16_t*>(perm_smem + sub * per);
+    uint32_t* ring = reinterpret_cast<uint32_t*>(perm_smem + sub * per + (per - PERM_RING * 4));
+    for (int i = sl; i < n; i += PERM_LANES) a[i] = (uint16_t)i;
     Coord c{FB_PURPOSE_SHUFFLE_PERMUTATION, root, (uint64_t)k, shuffle0 + (uint64_t)j, 0, 0, 0, 0, 0};
     Pcg g;
-    pcg_seed_coord(g, c);  // every lane derives the same stream
-    const uint64_t ahi = jt->a_hi[lane], alo = jt->a_lo[lane], ghi = jt->g_hi[lane], glo = jt->g_lo[lane];
-    const uint64_t nahi = jt->a_hi[32], nalo = jt->a_lo[32], nghi = jt->g_hi[32], nglo = jt->g_lo[32];
-    int grp = 16;  // ring = 16 groups of four 32-bit draws
-    int i = n - 1;
+    pcg_seed_coord(g, c);  // every lane of the group derives the same stream
+    const uint64_t ahi = jt->a_hi[sl], alo = jt->a_lo[sl], ghi = jt->g_hi[sl], glo = jt->g_lo[sl];
+    const uint64_t nahi = jt->a_hi[PERM_LANES], nalo = jt->a_lo[PERM_LANES];
+    const uint64_t nghi = jt->g_hi[PERM_LANES], nglo = jt->g_lo[PERM_LANES];
+    constexpr int GROUPS = PERM_RING / 4;  // ring = GROUPS groups of four 32-bit draws
+    int grp = GROUPS;
+    int i = valid ? n - 1 : 0;
     uint32_t mask = 0xffffffffu >> __clz(i | 1);
     __syncwarp();
-    while (i >= 1) {
-        if (grp == 16) {
-            // batch: lane's state S_lane, its output -> halves 2*lane, 2*lane+1; then S += 32 steps
+    while (__any_sync(0xffffffffu, i >= 1)) {
+        if (grp == GROUPS) {
+            // batch: the lane's state S_sl, its output -> halves 2*sl, 2*sl+1; then S += PERM_LANES steps
             uint64_t thi, tlo, uhi, ulo;
             mul128(ahi, alo, g.hi, g.lo, thi, tlo);
             mul128(ghi, glo, g.ihi, g.ilo, uhi, ulo);
@@ -374,7 +387,7 @@ __global__ void __launch_bounds__(PERM_WARPS * 32) permute_warp_kernel(uint64_t 
             uint64_t shi = thi + uhi + (slo < tlo ? 1u : 0u);
             const uint64_t o = pcg_output(shi, slo);
             __syncwarp();
-            reinterpret_cast<uint2*>(ring)[lane] = make_uint2((uint32_t)o, (uint32_t)(o >> 32));
+            reinterpret_cast<uint2*>(ring)[sl] = make_uint2((uint32_t)o, (uint32_t)(o >> 32));
             mul128(nahi, nalo, g.hi, g.lo, thi, tlo);
             mul128(nghi, nglo, g.ihi, g.ilo, uhi, ulo);
             g.lo = tlo + ulo;
@@ -382,8 +395,8 @@ __global__ void __launch_bounds__(PERM_WARPS * 32) permute_warp_kernel(uint64_t 
             grp = 0;
             __syncwarp();
         }
-        // Every lane performs the identical walk and the identical swaps (same values to the
-        // same addresses), so each lane's own program order keeps the array consistent.
+        // Every lane of a group performs the identical walk and the identical swaps (same values
+        // to the same addresses), so each lane's own program order keeps the array consistent.
         // Branch free: a rejected draw swaps a[i] with itself.
         const uint4 h = reinterpret_cast<const uint4*>(ring)[grp++];
         const uint32_t hs[4] = {h.x, h.y, h.z, h.w};
@@ -400,13 +413,14 @@ __global__ void __launch_bounds__(PERM_WARPS * 32) permute_warp_kernel(uint64_t 
         }
     }
     __syncwarp();
+    if (!valid) return;
     int32_t* dst = out + (size_t)j * n;
-    for (int t = lane; t < n; t += 32) dst[t] = (int32_t)a[t];
+    for (int t = sl; t < n; t += PERM_LANES) dst[t] = (int32_t)a[t];
     if (inv) {  // inverse permutation: position of every strategy in this shuffle
         int32_t* idst = inv + (size_t)j * n;
-        for (int t = lane; t < n; t += 32) idst[a[t]] = t;
+        for (int t = sl; t < n; t += PERM_LANES) idst[a[t]] = t;
     }
-    if (prefix && lane == 0) {  // shared 12-word prefix of this shuffle's seat streams (ss_pool_prefix)
+    if (prefix && sl == 0) {  // shared 12-word prefix of this shuffle's seat streams (ss_pool_prefix)
         Coord pc{FB_PURPOSE_TOURNAMENT_PLAYER, root, (uint64_t)k, shuffle0 + (uint64_t)j, 0, 0, 0, 0, 0};
         uint32_t pool[4];
         ss_pool_prefix(pc, pool);
@@ -786,11 +800,10 @@ static int permute_shuffles(uint64_t root_seed, int k, uint64_t shuffle0, int n_
     FB_REQUIRE_INIT();
     if (n_shuffles < 0 || n_strategies < 1) return fail(FB_ERR_BAD_ARG, "bad shuffle or strategy count");
     if (n_shuffles == 0) return FB_OK;
-    const size_t per_warp = (((size_t)n_strategies * 2 + 15) & ~(size_t)15) + 64 * 4;
-    const size_t smem = per_warp * PERM_WARPS;
+    const size_t smem = perm_bytes_per_shuffle(n_strategies) * PERM_SHUFFLES;
     if (n_strategies <= 65535 && smem <= (size_t)g_ctx.max_smem_optin - 1024) {
         FB_CUDA(cudaFuncSetAttribute(permute_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        permute_warp_kernel<<<(n_shuffles + PERM_WARPS - 1) / PERM_WARPS, PERM_WARPS * 32, smem,
+        permute_warp_kernel<<<(n_shuffles + PERM_SHUFFLES - 1) / PERM_SHUFFLES, 32, smem,
                               (cudaStream_t)stream>>>(root_seed, k, shuffle0, n_shuffles, n_strategies,
                                                       g_ctx.jump_dev, perm_out_dev, inv_out_dev, prefix_out_dev);
         return launch_check("permute_warp_kernel");
