@@ -181,18 +181,21 @@ def tallies_to_outcome(tallies: np.ndarray, ids: Sequence[int], games: Tuple[int
     wins = OutcomeCounter()
     sums: MetricSums = {m: defaultdict(float) for m in METRIC_LABELS}
     sq_sums: MetricSums = {m: defaultdict(float) for m in METRIC_LABELS}
-    ids = [int(i) for i in ids]
+    ids = np.asarray([int(i) for i in ids], dtype=object)
+
+    def column(rows: np.ndarray, col: int, as_float: bool = False) -> dict:
+        vals = t[rows, col]
+        return dict(zip(ids[rows].tolist(), (vals.astype(np.float64) if as_float else vals).tolist()))
+
     for col, target in ((T_ATTEMPTED, wins.attempted_exposures),
                         (T_COMPLETED, wins.completed_exposures),
                         (T_SAFETY, wins.safety_limit_exposures)):
-        for j in np.flatnonzero(t[:, col]):
-            target[ids[j]] = int(t[j, col])
+        target.update(column(np.flatnonzero(t[:, col]), col))
     winners = np.flatnonzero(t[:, T_WINS])
-    for j in winners:
-        wins[ids[j]] = int(t[j, T_WINS])
-        for m, label in enumerate(METRIC_LABELS):
-            sums[label][ids[j]] = float(t[j, T_SUMS + m])
-            sq_sums[label][ids[j]] = float(t[j, T_SQ_SUMS + m])
+    wins.update(column(winners, T_WINS))
+    for m, label in enumerate(METRIC_LABELS):
+        sums[label].update(column(winners, T_SUMS + m, as_float=True))
+        sq_sums[label].update(column(winners, T_SQ_SUMS + m, as_float=True))
     wins.games_attempted, wins.games_completed, wins.games_safety_limit = (int(x) for x in games)
     return wins, sums, sq_sums
 
