@@ -87,7 +87,12 @@ __device__ __forceinline__ uint4 lds128(uint32_t smem_addr) {
 // lane are immediate offsets from one address register.
 constexpr int PLAY_THREADS = 1024;
 constexpr uint32_t STAGE_STRIDE = PLAY_THREADS * 16u;
-constexpr size_t PLAY_SMEM_BYTES = (size_t)((LUT_BYTES + 15) & ~15) + 5u * STAGE_STRIDE;
+constexpr uint32_t QUEUE_CAP = 64;  // games per warp queue (a top-up adds <= 32 to < 32)
+constexpr size_t PLAY_QUEUE_OFFSET = (size_t)((LUT_BYTES + 15) & ~15) + 5u * STAGE_STRIDE;
+constexpr size_t PLAY_SMEM_BYTES = PLAY_QUEUE_OFFSET + (PLAY_THREADS / 32) * QUEUE_CAP * 4u;
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 
 // K2: two-seat games (every H2H block and the k=2 tournament cells).  The other seat always plays
 // next, so the turn switch needs no seat-order logic, the staged record is always the right one
@@ -112,6 +117,12 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
     // skip the ones the long list already covered.
     const uint32_t n_long = P.counter[1];
     const uint32_t n_ordinals = P.n_games + n_long;
+
+    // per-warp game queue (warp-uniform registers; entries = game | HDR_LONG)
+    const uint32_t gq = lut_s + (uint32_t)PLAY_QUEUE_OFFSET + (threadIdx.x >> 5) * (QUEUE_CAP * 4u);
+    uint32_t q_head = 0, q_tail = 0, q_seen = 0;  // q_seen: the global counter as last observed
+    const uint32_t q_share = 2u * gridDim.x * (blockDim.x >> 5);  // twice the number of warps
+    bool q_dry = false;
 
     // ---- per-lane game state ------------------------------------------------
     int status = ST_NEED;
@@ -188,43 +199,73 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
     // One loop iteration; returns true when every lane of the warp is out of work.
     auto roll_step = [&]() -> bool {
         // ================= R: lane refill =====================================
+        // Games come from a per-warp queue in shared memory.  When the queue cannot serve the
+        // lanes that need a game, the warp reserves 32 ordinals with ONE atomic, every lane
+        // resolves its ordinal to a game (long list first, then all games minus the ones the
+        // list covered), prefetches that game's first seat record into L2 and enqueues it.  The
+        // atomic, the ordinal->game load and the first-touch DRAM latency of the record are
+        // thus paid one top-up ahead of use instead of stalling the warp at every game start.
         const uint32_t need = __ballot_sync(FULL, status == ST_NEED);
         if (need) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(P.counter, (unsigned)__popc(need));
-            base = __shfl_sync(FULL, base, 0);
-            if (status == ST_NEED) {
-                const uint32_t ng = base + (uint32_t)__popc(need & lt_mask);
-                if (ng < n_ordinals) {
-                    bool take = true;
+            const uint32_t want = (uint32_t)__popc(need);
+            if (q_tail - q_head < want && !q_dry) {
+                // guided chunk size: 32 while plenty is left, shrinking to 1 so that no warp is
+                // left holding a queue of games while the others have run dry
+                const uint32_t left = n_ordinals - min(n_ordinals, q_seen);
+                const uint32_t chunk = min(32u, max(max(want, 1u), left / q_share));
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(P.counter, chunk);
+                base = __shfl_sync(FULL, base, 0);
+                q_seen = base + chunk;
+                const uint32_t ng = base + (uint32_t)lane;
+                bool ok = (uint32_t)lane < chunk && ng < n_ordinals;
+                uint32_t gq_entry = 0;
+                if (ok) {
                     if (ng < n_long) {
-                        g = P.long_list[ng];
-                        err = HDR_LONG;  // carried into the header (bit 31), not a row flag
+                        gq_entry = P.long_list[ng] | HDR_LONG;
                     } else {
-                        g = ng - n_long;
-                        err = 0;
-                        take = !(__ldcg(&P.header[g]) & HDR_LONG);  // already played from the list
+                        gq_entry = ng - n_long;
+                        ok = !(__ldcg(&P.header[gq_entry]) & HDR_LONG);  // already played from the list
                     }
-                    if (take) {
-                        seat = 0;
-                        round = 1;
-                        trigger = -1;
-                        if (LIMITS) {
-                            target = P.limits[2 * (size_t)g];
-                            max_rounds = P.limits[2 * (size_t)g + 1];
-                        }
-                        stb = target;
-                        if (max_rounds <= 0) {  // `while rounds < max_rounds` never runs (engine.py:455)
-                            P.header[g] = ((uint32_t)FB_ROW_SAFETY_LIMIT << 16) | err;
-                        } else {
-                            start_turn_from_l2();
-                            status = ST_PLAY;
-                        }
+                }
+                if (ok) {
+                    const char* rp = reinterpret_cast<const char*>(P.seats + (size_t)(gq_entry & ~HDR_LONG) * k);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 32));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 64));
+                }
+                const uint32_t m = __ballot_sync(FULL, ok);
+                if (ok) sts_u32(gq + ((q_tail + (uint32_t)__popc(m & lt_mask)) & (QUEUE_CAP - 1u)) * 4u, gq_entry);
+                q_tail += (uint32_t)__popc(m);
+                q_dry = base + chunk >= n_ordinals;
+                __syncwarp();
+            }
+            const uint32_t have = min(want, q_tail - q_head);
+            if (status == ST_NEED) {
+                const uint32_t rank = (uint32_t)__popc(need & lt_mask);
+                if (rank < have) {
+                    const uint32_t entry = lds_u32(gq + ((q_head + rank) & (QUEUE_CAP - 1u)) * 4u);
+                    g = entry & ~HDR_LONG;
+                    err = entry & HDR_LONG;  // carried into the header (bit 31), not a row flag
+                    seat = 0;
+                    round = 1;
+                    trigger = -1;
+                    if (LIMITS) {
+                        target = P.limits[2 * (size_t)g];
+                        max_rounds = P.limits[2 * (size_t)g + 1];
                     }
-                } else {
-                    status = ST_DEAD;
+                    stb = target;
+                    if (max_rounds <= 0) {  // `while rounds < max_rounds` never runs (engine.py:455)
+                        P.header[g] = ((uint32_t)FB_ROW_SAFETY_LIMIT << 16) | err;
+                    } else {
+                        start_turn_from_l2();
+                        status = ST_PLAY;
+                    }
+                } else if (q_dry) {
+                    status = ST_DEAD;  // (have == q_tail - q_head here: the queue is empty too)
                 }
             }
+            q_head += have;
         }
         if (__all_sync(FULL, status == ST_DEAD)) return true;
 
