@@ -834,7 +834,7 @@ int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuff
     if (n_shuffles == 0) return FB_OK;
     const uint32_t gps = (uint32_t)(n_strategies / k);
     const uint64_t n_games = (uint64_t)n_shuffles * gps;
-    if (n_games * (uint64_t)k > 0xfffffff0ull || n_games >= 0x80000000ull)
+    if (n_games * (uint64_t)k > 0xfffffff0ull || n_games >= 0x7ff00000ull)
         return fail(FB_ERR_BAD_ARG, "more than 2^32 seats or 2^31 games in one launch");
     Workspace w;
     const size_t perm_bytes = align_up((size_t)n_shuffles * n_strategies * 4, 256);
@@ -990,7 +990,7 @@ int fb_play_games(const uint64_t* coords_dev, uint64_t n_games, int k,
     cudaStream_t stream = (cudaStream_t)stream_v;
     if (k < 1 || k > FB_MAX_PLAYERS) return fail(FB_ERR_BAD_ARG, "k=%d outside [1,%d]", k, FB_MAX_PLAYERS);
     if (n_games == 0) return FB_OK;
-    if (n_games * (uint64_t)k > 0xfffffff0ull || n_games >= 0x80000000ull)
+    if (n_games * (uint64_t)k > 0xfffffff0ull || n_games >= 0x7ff00000ull)
         return fail(FB_ERR_BAD_ARG, "more than 2^32 seats or 2^31 games in one launch");
     Workspace w;
     if (!carve(workspace_dev, workspace_bytes, k, n_games, w))

@@ -49,6 +49,34 @@ def cell(root, k, shuffles=4300):
             "safety_limit_games": int(tot[2])}
 
 
+# configs[0]: fast grid (80 strategies), k=2, seed 42, 600 shuffles = 24,000 games (launch-latency bound)
+fast_host = pack_strategies(generate_strategy_grid(
+    score_thresholds=[250, 300, 350, 400], smart_five_opts=[True], smart_one_opts=[True],
+    consider_score_opts=[True], consider_dice_opts=[True], auto_hot_dice_opts=[True],
+    run_up_score_opts=[True])[0])
+fast = eng.to_device(fast_host)
+ms, res = timed(lambda: eng.play_tournament(42, 2, 0, 600, fast), reps=10)
+out["fast_config_k2_seed42"] = {"games": 24000, "ms": ms, "games_per_s": 24000 / ms * 1e3,
+                                "wins_42_46_51": res.tallies.cpu().numpy()[0][[42, 46, 51], 0].tolist()}
+
+# the Python surface end to end: run_tournament() for the full k=2 cell (checkpoint + metrics parquet)
+import tempfile  # noqa: E402
+
+from farkle_ii_b200 import run_tournament as frt  # noqa: E402
+
+with tempfile.TemporaryDirectory() as td:
+    cfg = frt.TournamentConfig(n_players=2, num_shuffles=4300, deterministic_batch_size=43)
+    kw = dict(config=cfg, global_seed=42, checkpoint_path=Path(td) / "2p_checkpoint.pkl",
+              collect_metrics=True, num_shuffles=4300, strategies=generate_strategy_grid()[0])
+    frt.run_tournament(**kw)
+    t0 = time.perf_counter()
+    frt.run_tournament(**kw)
+    dt = time.perf_counter() - t0
+out["run_tournament_python_surface_k2"] = {
+    "games": 4300 * (N // 2), "seconds": dt, "games_per_s": 4300 * (N // 2) / dt,
+    "note": "farkle_ii_b200.run_tournament.run_tournament(): strategy packing, launch, tallies D2H, "
+            "OutcomeCounter / metric dict building, checkpoint pickle and 2p_metrics.parquet"}
+
 out["k6_full_grid"] = cell(42, 6)
 mega = [cell(102, k) for k in (2, 3, 4, 5, 6, 8, 10, 12)]
 out["mega_root_102"] = {"cells": mega, "games": sum(c["games"] for c in mega),
@@ -85,11 +113,13 @@ def h2h():
 
 
 h2h()
-torch.cuda.synchronize()
-t0 = time.perf_counter()
-prog, rounds, attempts = h2h()
-torch.cuda.synchronize()
-dt = time.perf_counter() - t0
+dt = 1e9
+for _ in range(3):  # best of three (the first call also sizes the 8 GB workspace)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    prog, rounds, attempts = h2h()
+    torch.cuda.synchronize()
+    dt = min(dt, time.perf_counter() - t0)
 out["h2h_2p"] = {"blocks": nb, "n_completed_required": target, "max_attempts": max_attempts,
                  "attempts_played": attempts, "launch_rounds": rounds, "seconds": dt,
                  "attempts_per_s": attempts / dt, "complete_blocks": int((prog[:, 1] >= target).sum()),
