@@ -184,6 +184,10 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
         }
     };
     auto start_turn_from_l2 = [&]() {
+        // An unconsumed prefetch of this lane (previous game, or a seat order the prediction
+        // missed) must have landed before the staging slots are targeted again: cp.async
+        // copies of one thread are not ordered among themselves.
+        cp_async_wait_all();
         const uint4* sp = reinterpret_cast<const uint4*>(P.seats + (g * (uint32_t)k + (uint32_t)seat));
         const uint4 m0 = __ldcg(sp), m1 = __ldcg(sp + 1), m2 = __ldcg(sp + 2), i0 = __ldcg(sp + 3), i1 = __ldcg(sp + 4);
         start_turn(m0, m1, m2, i0, i1, sp + 5);  // K2: a game starts with seat 0, seat 1 is the next record

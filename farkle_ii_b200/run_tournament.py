@@ -583,11 +583,18 @@ def run_tournament(*, config: TournamentConfig | None = None, global_seed: int =
         import pyarrow as pa
         import pyarrow.parquet as pq
 
-        metric_rows = [{"metric": label, "strategy": s, "sum": float(v),
-                        "square_sum": float(sqs[label].get(s, 0.0))}
-                       for label in METRIC_LABELS for s, v in sums[label].items()]
+        # label-major rows for the strategies that won at least once (run_tournament.py:1797-1826),
+        # built column-wise from the tally tensor
+        t_np = tallies.cpu().numpy()[0]
+        won = np.flatnonzero(t_np[:, T_WINS])
+        n_lab = len(METRIC_LABELS)
         schema = pa.schema([pa.field("metric", pa.string()), pa.field("strategy", pa.int32()),
                             pa.field("sum", pa.float64()), pa.field("square_sum", pa.float64())])
-        tbl = pa.Table.from_pylist(metric_rows, schema=schema)
+        tbl = pa.Table.from_arrays([
+            pa.array(np.repeat(np.array(METRIC_LABELS, dtype=object), len(won)), type=pa.string()),
+            pa.array(np.tile(state.ids[won], n_lab).astype(np.int32)),
+            pa.array(t_np[won, T_SUMS:T_SUMS + n_lab].T.reshape(-1).astype(np.float64)),
+            pa.array(t_np[won, T_SQ_SUMS:T_SQ_SUMS + n_lab].T.reshape(-1).astype(np.float64)),
+        ], schema=schema)
         _atomic_write(ckpt_path.with_name(f"{k}p_metrics.parquet"), lambda p: pq.write_table(tbl, p))
     LOGGER.info("Tournament run complete after %d attempted games", wins.games_attempted)
