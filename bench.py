@@ -172,8 +172,9 @@ def workload_config(n_gpus: int) -> dict:
         "sharding": (f"rank r plays shuffles [r*{SHUFFLES},(r+1)*{SHUFFLES}) of each cell; "
                      "one int64 all-reduce of the tally tensor per cell" if n_gpus > 1
                      else "single GPU"),
-        "l2": ("per-seat stream workspace is 0.7 GB (k=2) / 0.7 GB (k=4) per cell, larger than the "
-               "126 MB L2; the kernels are not memory bound"),
+        "l2": ("no flush needed: every step re-seeds 1.77 GB of seat records per cell (80 B x 22.2 M "
+               "seats), 14x the 126 MB L2, and consecutive steps alternate roots; the kernels are "
+               "not memory bound"),
     }
 
 
