@@ -452,3 +452,36 @@ def test_run_tournament_end_to_end(eng, golden_dir, tmp_path):
     frt.run_tournament(config=cfg2, global_seed=42, checkpoint_path=tmp_path / "c2.pkl",
                        row_output_directory=row_dir, num_shuffles=4, strategies=strategies)
     assert len((row_dir / "manifest.jsonl").read_text().splitlines()) == 4  # resume skipped all
+
+
+def test_longest_first_scheduling_and_tiny_launches(eng):
+    """Tables made of never-banking strategies (the longest-first list covers every game), mixed
+    tables, and launches smaller than a warp: scheduling must not change any result."""
+    never = [(300, 0, 0x04 | 0x08 | 0x10), (0, 0, 0x08), (250, 0, 0x04 | 0x08 | 0x10 | 0x20)]
+    normal = [(300, 2, 0x04 | 0x08), (500, 1, 0x01 | 0x04 | 0x08 | 0x20 | 0x80), (350, 3, 0x04 | 0x40)]
+    for entries, k, nsh, mr in ((never[:2], 2, 3, 40), (never + normal, 2, 9, 25), (never + normal, 3, 7, 30),
+                                (never + normal, 6, 5, 200), (normal[:1], 1, 4, 200)):
+        table = np.array(entries, dtype=fo.STRATEGY_DTYPE)
+        res = eng.play_tournament(77, k, 2, nsh, table, max_rounds=mr, want_rows=True, want_game_seeds=True)
+        want_t, want_tot, want_rows = fo.play_tournament(77, k, 2, nsh, table, max_rounds=mr, want_rows=True,
+                                                         want_game_seeds=True)
+        assert np.array_equal(res.tallies.cpu().numpy(), want_t), (k, nsh)
+        assert np.array_equal(res.totals.cpu().numpy(), want_tot), (k, nsh)
+        assert res.rows_numpy().tobytes() == want_rows.tobytes()
+
+
+def test_large_grid_global_memory_permutation(eng):
+    """More strategies than the shared-memory Fisher-Yates holds (fallback permute_kernel)."""
+    rng = np.random.Generator(np.random.PCG64DXSM(5))
+    n = 120_000
+    table = np.zeros(n, dtype=fo.STRATEGY_DTYPE)
+    table["score_threshold"] = rng.integers(4, 20, size=n) * 50
+    table["dice_threshold"] = rng.integers(1, 5, size=n)
+    table["flags"] = 0x04 | 0x08 | np.where(rng.integers(0, 2, size=n) == 1, 0x20, 0)
+    perm = eng.permute_shuffles(9, 4, 5, 2, n)
+    for j in range(2):
+        assert np.array_equal(perm[j], fo.permutation(9, 4, 5 + j, n))
+    res = eng.play_tournament(9, 4, 5, 2, table)
+    want_t, want_tot, _ = fo.play_tournament(9, 4, 5, 2, table, n_threads=8)
+    assert np.array_equal(res.tallies.cpu().numpy(), want_t)
+    assert np.array_equal(res.totals.cpu().numpy(), want_tot)
