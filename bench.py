@@ -298,6 +298,34 @@ def main() -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = games_per_step_rank * world * e2e_steps / e2e_s
+
+    # e2e with the per-game rows as well: every game's compact row lands in pinned host memory
+    # (the ingest hand-off), copied under the kernels of the next chunk of shuffles
+    from farkle_ii_b200.layout import row_dtype
+
+    rows_pin = {k: torch.empty(n_sh * (N_STRATEGIES // k) * row_dtype(k).itemsize,
+                               dtype=torch.uint8).pin_memory() for k in CELLS_K}
+    rows_host = {k: rows_pin[k].numpy().view(row_dtype(k)) for k in CELLS_K}
+
+    def rows_step(i: int) -> None:
+        root = ROOTS[i % len(ROOTS)]
+        for k in CELLS_K:
+            eng.run_tournament_host(root, k, shuffle0, n_sh, table_pinned, out_tallies=out_t[k],
+                                    want_rows=True, out_rows=rows_host[k])
+
+    rows_step(0)
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(2):
+        rows_step(i)
+    torch.cuda.synchronize()
+    rows_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([rows_s], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rows_s = float(t.item())
+    rows_value = games_per_step_rank * world * 2 / rows_s
+    rows_d2h = sum(rows_pin[k].numel() for k in CELLS_K)
     h2d = len(CELLS_K) * table_host.nbytes
     d2h = len(CELLS_K) * (N_STRATEGIES * TALLY_WIDTH * 8 + TOTALS_WIDTH * 8)
 
@@ -361,6 +389,10 @@ def main() -> None:
         "e2e": {"value": e2e_value, "unit": "games/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "call": "Engine.run_tournament_host -> fb_run_tournament_host (host buffers)"},
+        "e2e_rows": {"value": rows_value, "unit": "games/s", "h2d_bytes_per_step": h2d,
+                     "d2h_bytes_per_step": d2h + rows_d2h, "steps": 2,
+                     "call": "fb_run_tournament_host with rows_host: tallies + one compact row per game "
+                             "into pinned host memory, D2H overlapped with the next chunk's kernels"},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roofline,

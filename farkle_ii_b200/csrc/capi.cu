@@ -11,6 +11,7 @@
 //   test kernels            seedseq / coordinate_seed / roll_dice / default_score
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -48,6 +49,9 @@ struct Ctx {
     void* host_ws = nullptr;
     size_t host_ws_bytes = 0;
     bool smem_opted = false;  // play_kernel dynamic shared memory opt-in done on this device
+    // fb_run_tournament_host: compute / copy streams and the events that hand the row buffers over
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_played[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
 };
 Ctx g_ctx;
 std::mutex g_mu;
@@ -818,13 +822,14 @@ int fb_permute_shuffles(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuf
     return permute_shuffles(root_seed, k, shuffle0, n_shuffles, n_strategies, perm_out_dev, nullptr, nullptr, stream);
 }
 
-int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
-                       const fb_strategy_t* strategies_dev, const int32_t* strategy_ids_dev,
-                       int n_strategies, int n_tally_ids, int32_t target_score, int32_t max_rounds,
-                       const uint64_t* override_shuffle_dev, const uint32_t* override_game_dev,
-                       const int32_t* override_max_rounds_dev, int n_overrides, int shuffles_per_slot,
-                       int64_t* tallies_dev, int64_t* totals_dev, void* rows_dev, int want_game_seeds,
-                       void* workspace_dev, size_t workspace_bytes, void* stream_v) {
+static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
+                                const fb_strategy_t* strategies_dev, const int32_t* strategy_ids_dev,
+                                int n_strategies, int n_tally_ids, int32_t target_score, int32_t max_rounds,
+                                const uint64_t* override_shuffle_dev, const uint32_t* override_game_dev,
+                                const int32_t* override_max_rounds_dev, int n_overrides, int shuffles_per_slot,
+                                int64_t* tallies_dev, int64_t* totals_dev, void* rows_dev, int want_game_seeds,
+                                void* workspace_dev, size_t workspace_bytes, void* stream_v,
+                                uint32_t ordinal_base) {
     FB_REQUIRE_INIT();
     cudaStream_t stream = (cudaStream_t)stream_v;
     if (k < 1 || k > FB_MAX_PLAYERS) return fail(FB_ERR_BAD_ARG, "k=%d outside [1,%d]", k, FB_MAX_PLAYERS);
@@ -879,6 +884,7 @@ int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuff
     F.totals = reinterpret_cast<unsigned long long*>(totals_dev);
     F.rows = reinterpret_cast<uint32_t*>(rows_dev);
     F.row_words = (int)(fb_row_stride(k) / 4);
+    F.ordinal_base = ordinal_base;
     if (!F.tallies) return launch_play(P, F, stream);
     // tallies: exposures per slot now, winner metrics by gather after the finish pass
     const int n_slots = shuffles_per_slot > 0 ? (n_shuffles + shuffles_per_slot - 1) / shuffles_per_slot : 1;
@@ -905,6 +911,19 @@ int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuff
     const int n_chunks = (n_shuffles + G.chunk - 1) / G.chunk;
     tally_gather_kernel<<<dim3(blocks_for((uint64_t)n_strategies, 128), (unsigned)n_chunks), 128, 0, stream>>>(G);
     return launch_check("tally_gather_kernel");
+}
+
+int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
+                       const fb_strategy_t* strategies_dev, const int32_t* strategy_ids_dev,
+                       int n_strategies, int n_tally_ids, int32_t target_score, int32_t max_rounds,
+                       const uint64_t* override_shuffle_dev, const uint32_t* override_game_dev,
+                       const int32_t* override_max_rounds_dev, int n_overrides, int shuffles_per_slot,
+                       int64_t* tallies_dev, int64_t* totals_dev, void* rows_dev, int want_game_seeds,
+                       void* workspace_dev, size_t workspace_bytes, void* stream_v) {
+    return play_tournament_impl(root_seed, k, shuffle0, n_shuffles, strategies_dev, strategy_ids_dev, n_strategies,
+                                n_tally_ids, target_score, max_rounds, override_shuffle_dev, override_game_dev,
+                                override_max_rounds_dev, n_overrides, shuffles_per_slot, tallies_dev, totals_dev,
+                                rows_dev, want_game_seeds, workspace_dev, workspace_bytes, stream_v, 0u);
 }
 
 int fb_play_h2h(uint64_t root_seed, int n_blocks, const uint64_t* pair_id_dev, const uint8_t* order_dev,
@@ -1041,15 +1060,25 @@ int fb_run_tournament_host(uint64_t root_seed, int k, uint64_t shuffle0, int n_s
     if (k < 1 || k > FB_MAX_PLAYERS || n_strategies < k || n_strategies % k != 0 || n_shuffles < 1)
         return fail(FB_ERR_BAD_ARG, "bad k / strategy / shuffle count");
     const uint64_t gps = (uint64_t)(n_strategies / k);
-    const uint64_t n_games = (uint64_t)n_shuffles * gps;
     const int n_slots = shuffles_per_slot > 0 ? (n_shuffles + shuffles_per_slot - 1) / shuffles_per_slot : 1;
+    // Rows mode streams the rows to the host while the next part of the range is being played:
+    // the range is cut into up to four chunks (whole tally slots), two device row buffers
+    // alternate, and the D2H copy of chunk i runs on a second stream under the kernels of i+1.
+    int chunk = n_shuffles;
+    if (rows_host && (uint64_t)n_shuffles * gps >= (1u << 20)) {
+        chunk = (n_shuffles + 3) / 4;
+        if (shuffles_per_slot > 0) chunk = (chunk + shuffles_per_slot - 1) / shuffles_per_slot * shuffles_per_slot;
+    }
+    const int n_chunks = (n_shuffles + chunk - 1) / chunk;
+    const uint64_t chunk_games = (uint64_t)chunk * gps;
+    const size_t stride = fb_row_stride(k);
     const size_t strat_b = align_up((size_t)n_strategies * sizeof(fb_strategy_t), 256);
     const size_t ids_b = align_up((size_t)n_strategies * 4, 256);
     const size_t tally_b = align_up((size_t)n_slots * n_tally_ids * FB_TALLY_WIDTH * 8, 256);
     const size_t totals_b = 256;
-    const size_t rows_b = rows_host ? align_up(n_games * fb_row_stride(k), 256) : 0;
-    const size_t ws_b = fb_workspace_bytes(k, n_games) + 2 * align_up((size_t)n_shuffles * n_strategies * 4, 256);
-    const size_t total = strat_b + ids_b + tally_b + totals_b + rows_b + ws_b;
+    const size_t rows_b = rows_host ? align_up(chunk_games * stride, 256) : 0;  // one of two buffers
+    const size_t ws_b = fb_workspace_bytes(k, chunk_games) + 2 * align_up((size_t)chunk * n_strategies * 4, 256);
+    const size_t total = strat_b + ids_b + tally_b + totals_b + (n_chunks > 1 ? 2 : 1) * rows_b + ws_b;
     std::lock_guard<std::mutex> lock(g_mu);
     if (g_ctx.host_ws_bytes < total) {
         if (g_ctx.host_ws) cudaFree(g_ctx.host_ws);
@@ -1058,33 +1087,57 @@ int fb_run_tournament_host(uint64_t root_seed, int k, uint64_t shuffle0, int n_s
         FB_CUDA(cudaMalloc(&g_ctx.host_ws, total));
         g_ctx.host_ws_bytes = total;
     }
+    if (!g_ctx.s_compute) {
+        FB_CUDA(cudaStreamCreateWithFlags(&g_ctx.s_compute, cudaStreamNonBlocking));
+        FB_CUDA(cudaStreamCreateWithFlags(&g_ctx.s_copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            FB_CUDA(cudaEventCreateWithFlags(&g_ctx.ev_played[i], cudaEventDisableTiming));
+            FB_CUDA(cudaEventCreateWithFlags(&g_ctx.ev_copied[i], cudaEventDisableTiming));
+        }
+    }
     uint8_t* p = static_cast<uint8_t*>(g_ctx.host_ws);
     fb_strategy_t* d_strat = reinterpret_cast<fb_strategy_t*>(p); p += strat_b;
     int32_t* d_ids = reinterpret_cast<int32_t*>(p); p += ids_b;
     int64_t* d_tally = reinterpret_cast<int64_t*>(p); p += tally_b;
     int64_t* d_totals = reinterpret_cast<int64_t*>(p); p += totals_b;
-    void* d_rows = rows_host ? p : nullptr; p += rows_b;
+    uint8_t* d_rows[2] = {rows_host ? p : nullptr, nullptr};
+    p += rows_b;
+    if (n_chunks > 1) { d_rows[1] = p; p += rows_b; }
     void* d_ws = p;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = g_ctx.s_compute, copy = g_ctx.s_copy;
     FB_CUDA(cudaMemcpyAsync(d_strat, strategies_host, (size_t)n_strategies * sizeof(fb_strategy_t),
                             cudaMemcpyHostToDevice, stream));
     if (strategy_ids_host)
         FB_CUDA(cudaMemcpyAsync(d_ids, strategy_ids_host, (size_t)n_strategies * 4, cudaMemcpyHostToDevice, stream));
     FB_CUDA(cudaMemsetAsync(d_tally, 0, tally_b, stream));
     FB_CUDA(cudaMemsetAsync(d_totals, 0, totals_b, stream));
-    int rc = fb_play_tournament(root_seed, k, shuffle0, n_shuffles, d_strat, strategy_ids_host ? d_ids : nullptr,
-                                n_strategies, n_tally_ids, target_score, max_rounds, nullptr, nullptr, nullptr, 0,
-                                shuffles_per_slot, tallies_host ? d_tally : nullptr, d_totals, d_rows,
-                                want_game_seeds, d_ws, ws_b, stream);
-    if (rc) return rc;
+    for (int c = 0; c < n_chunks; c++) {
+        const int s0 = c * chunk, cnt = std::min(chunk, n_shuffles - s0);
+        const int b = c & 1;
+        if (c >= 2) FB_CUDA(cudaStreamWaitEvent(stream, g_ctx.ev_copied[b], 0));  // row buffer b is free again
+        int64_t* tally_c = nullptr;
+        if (tallies_host)
+            tally_c = d_tally + (shuffles_per_slot > 0 ? (size_t)(s0 / shuffles_per_slot) * n_tally_ids * FB_TALLY_WIDTH : 0);
+        int rc = play_tournament_impl(root_seed, k, shuffle0 + (uint64_t)s0, cnt, d_strat,
+                                      strategy_ids_host ? d_ids : nullptr, n_strategies, n_tally_ids, target_score,
+                                      max_rounds, nullptr, nullptr, nullptr, 0, shuffles_per_slot, tally_c, d_totals,
+                                      d_rows[b], want_game_seeds, d_ws, ws_b, stream, (uint32_t)((uint64_t)s0 * gps));
+        if (rc) return rc;
+        if (rows_host) {
+            FB_CUDA(cudaEventRecord(g_ctx.ev_played[b], stream));
+            FB_CUDA(cudaStreamWaitEvent(copy, g_ctx.ev_played[b], 0));
+            FB_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(rows_host) + (uint64_t)s0 * gps * stride, d_rows[b],
+                                    (uint64_t)cnt * gps * stride, cudaMemcpyDeviceToHost, copy));
+            FB_CUDA(cudaEventRecord(g_ctx.ev_copied[b], copy));
+        }
+    }
     if (tallies_host)
         FB_CUDA(cudaMemcpyAsync(tallies_host, d_tally, (size_t)n_slots * n_tally_ids * FB_TALLY_WIDTH * 8,
                                 cudaMemcpyDeviceToHost, stream));
     if (totals_host)
         FB_CUDA(cudaMemcpyAsync(totals_host, d_totals, FB_TOTALS_WIDTH * 8, cudaMemcpyDeviceToHost, stream));
-    if (rows_host)
-        FB_CUDA(cudaMemcpyAsync(rows_host, d_rows, n_games * fb_row_stride(k), cudaMemcpyDeviceToHost, stream));
     FB_CUDA(cudaStreamSynchronize(stream));
+    if (rows_host) FB_CUDA(cudaStreamSynchronize(copy));
     return FB_OK;
 }
 

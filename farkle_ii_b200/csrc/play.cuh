@@ -484,6 +484,7 @@ struct FinishParams {
     unsigned long long* tallies;  // [slots][ids][26] or nullptr (filled by tally_gather_kernel)
     unsigned long long* totals;   // [FB_TOTALS_WIDTH] or nullptr
     uint32_t* rows;               // or nullptr
+    uint32_t ordinal_base;        // game_ordinal of the launch's first game (chunked host calls)
     int row_words;
     uint8_t* outcome;  // [n_games] or nullptr
 };
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
         if (row) {
             const uint64_t gs = F.game_seed ? F.game_seed[g] : 0ull;
             reinterpret_cast<uint4*>(row)[0] =
-                make_uint4((uint32_t)gs, (uint32_t)(gs >> 32), g,
+                make_uint4((uint32_t)gs, (uint32_t)(gs >> 32), F.ordinal_base + g,
                            rounds | ((uint32_t)(safety ? 0xFF : winner) << 16) | (flags << 24));
         }
         // pass 2: the compact row

@@ -485,3 +485,28 @@ def test_large_grid_global_memory_permutation(eng):
     want_t, want_tot, _ = fo.play_tournament(9, 4, 5, 2, table, n_threads=8)
     assert np.array_equal(res.tallies.cpu().numpy(), want_t)
     assert np.array_equal(res.totals.cpu().numpy(), want_tot)
+
+
+@pytest.mark.parametrize("spb", [0, 43])
+def test_host_call_streams_rows_in_chunks(eng, golden_dir, spb):
+    """fb_run_tournament_host in rows mode cuts the range into chunks and copies the rows of one
+    chunk to the host under the kernels of the next: same rows, tallies and totals as one launch."""
+    table = np.load(golden_dir / "games_full_0_2.npz")["strategies"]
+    nsh = 500                                   # 1.29 M games: above the chunking threshold
+    t, tot, rows = eng.run_tournament_host(7, 2, 11, nsh, table, shuffles_per_slot=spb, want_rows=True,
+                                           want_game_seeds=True)
+    one = eng.play_tournament(7, 2, 11, nsh, table, shuffles_per_slot=spb, want_rows=True,
+                              want_game_seeds=True)
+    assert rows.tobytes() == one.rows_numpy().tobytes()
+    assert np.array_equal(rows["game_ordinal"], np.arange(len(rows), dtype=np.uint32))
+    assert np.array_equal(t, one.tallies.cpu().numpy())
+    assert np.array_equal(tot, one.totals.cpu().numpy())
+    want_t, _, want_rows = fo.play_tournament(7, 2, 11 + 43 * 3, 43, table, want_rows=True,
+                                              want_game_seeds=True, n_threads=8)
+    gps = len(table) // 2
+    raw = rows.view(np.uint8).reshape(len(rows), -1)[43 * 3 * gps:43 * 4 * gps].copy()  # keeps the padding bytes
+    got = raw.reshape(-1).view(rows.dtype)
+    got["game_ordinal"] -= 43 * 3 * gps
+    assert got.tobytes() == want_rows.tobytes()
+    if spb:
+        assert np.array_equal(t[3], want_t[0])
