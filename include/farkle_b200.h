@@ -260,9 +260,13 @@ int fb_play_games(const uint64_t* coords_dev /*[n][7]*/, uint64_t n_games, int k
                   size_t workspace_bytes, void* stream);
 
 /* Host-buffer convenience for the reference-facing plug-in: H2D strategy
- * table, fb_play_tournament, D2H tallies/totals(/rows), stream-synchronised
- * before returning.  All pointers are HOST pointers; rows_host may be NULL.
- * tallies_host/totals_host are overwritten (not accumulated).               */
+ * table, fb_play_tournament, D2H tallies/totals(/rows), synchronised before
+ * returning.  All pointers are HOST pointers; rows_host may be NULL.
+ * tallies_host/totals_host are overwritten (not accumulated).  With rows_host
+ * (pinned memory recommended) a large range is played in up to four chunks of
+ * whole tally slots and the rows of one chunk are copied to the host on a
+ * second stream while the next chunk is being played; game_ordinal still runs
+ * over the whole call.                                                       */
 int fb_run_tournament_host(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
                            const fb_strategy_t* strategies_host,
                            const int32_t* strategy_ids_host, int n_strategies, int n_tally_ids,
