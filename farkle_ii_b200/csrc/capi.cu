@@ -875,6 +875,7 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
     F.header = w.header;
     F.strategy_ids = strategy_ids_dev;
     F.ids_mode = strategy_ids_dev ? 1 : 0;
+    F.perm = perm;
     F.game_seed = want_game_seeds ? w.game_seed : nullptr;
     F.n_games = (uint32_t)n_games;
     F.k = k;

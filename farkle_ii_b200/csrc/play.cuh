@@ -474,6 +474,7 @@ struct FinishParams {
     const Seat* seats;
     uint32_t* header;
     const int32_t* strategy_ids;  // id of table entry (ids_mode 1)
+    const int32_t* perm;          // table index of record r (tournaments: the permutations); nullptr = r
     int ids_mode;                 // 0 id = table index, 1 id = strategy_ids[index], 2 id = seat
     const uint64_t* game_seed;    // [n_games] or nullptr
     uint32_t n_games;
@@ -538,7 +539,8 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
         for (int s = 0; row && s < k; s++) {
             const uint4 a = __ldcg(&seats[s].a);
             const uint4 b = __ldcg(&seats[s].b);
-            const uint32_t idx = __ldcg(&seats[s].cst.w);
+            const uint32_t rec = g * (uint32_t)k + (uint32_t)s;
+            const uint32_t idx = F.ids_mode == 2 ? 0u : (F.perm ? (uint32_t)F.perm[rec] : rec);
             const int sid = F.ids_mode == 0 ? (int)idx : (F.ids_mode == 1 ? F.strategy_ids[idx] : s);
             uint32_t* w = row + 4 + s * 7;
             w[0] = a.y;
