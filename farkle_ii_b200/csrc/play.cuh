@@ -24,12 +24,15 @@
 // games in flight stay L2 resident.
 //
 // play_kernel   one game per lane, loop body = ONE ROLL, straight-line; persistent CTAs
-//               (one per SM); a lane whose game ended takes the next ordinal from a
-//               global counter (lane refill), so the 100x spread of game lengths does
-//               not idle the warp.  It only plays: at game end it writes the header.
+//               (one per SM); a lane whose game ended takes the next game from its warp's
+//               queue (lane refill), so the 100x spread of game lengths does not idle the
+//               warp.  It only plays: at game end it writes the header.
 // finish_kernel one thread per finished game, dense and lane-parallel: ranks the seats,
-//               emits the compact row (every byte of a row is written by one thread, L2
-//               merges the sectors), and adds the tallies with RED.64.
+//               marks the winner in the header, emits the compact row (every byte of a row
+//               is written by one thread, L2 merges the sectors) and the launch totals.
+// exposure_kernel / tally_gather_kernel
+//               the per-strategy tallies: exposures per slot, winner metrics by gather over
+//               the inverse permutation (few atomics).
 #pragma once
 #include <cstdint>
 
