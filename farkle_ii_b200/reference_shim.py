@@ -104,13 +104,17 @@ def install(rt: Any = None, *, device: int | None = None) -> dict[str, Any]:
     def _run_chunk_metrics(shuffle_tasks: Sequence[Any], *, collect_rows: bool = False,
                            row_dir: Path | None = None, manifest_path: Path | None = None,
                            row_sidecar: Any = None):
-        if row_sidecar is not None:
-            raise NotImplementedError(
-                "hash-bound row sidecars (artifact contract v3) are outside the accelerated path; "
-                "run with row_sidecar=None or keep the reference's _run_chunk_metrics for rows mode")
+        def reference_writer(out: Path, manifest_file: Path, table: Any, extra: Any) -> None:
+            # the reference's own shard publisher: Parquet writer, manifest line and — when the
+            # runner passes one — the hash-bound sidecar (run_tournament.py:530-558)
+            rt.run_streaming_shard(out_path=str(out), manifest_path=str(manifest_file),
+                                   schema=table.schema, batch_iter=(table,),
+                                   manifest_extra=dict(extra), sidecar=row_sidecar)
+
         w, s, q = gpu_rt._run_chunk_metrics([task_of(t) for t in shuffle_tasks],
                                             collect_rows=collect_rows, row_dir=row_dir,
-                                            manifest_path=manifest_path)
+                                            manifest_path=manifest_path, row_sidecar=row_sidecar,
+                                            shard_writer=reference_writer)
         return counter_of(w), sums_of(s), sums_of(q)
 
     for name, fn in (("_init_worker", _init_worker), ("_play_one_shuffle", _play_one_shuffle),

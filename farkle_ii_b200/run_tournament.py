@@ -359,25 +359,54 @@ def _append_manifest(manifest_path: Path, record: Mapping[str, Any]) -> None:
         os.fsync(fh.fileno())
 
 
+def shard_manifest_extra(state: WorkerState, task: ShuffleTask, shard_name: str) -> Dict[str, Any]:
+    """The manifest fields the reference records per row shard (run_tournament.py:536-557)."""
+    record: Dict[str, Any] = {
+        "path": shard_name, "root_seed": task.root_seed, "n_players": task.k,
+        "shuffle_index": task.shuffle_index, "shuffle_seed": task.shuffle_seed,
+        "deterministic_batch_id": task.deterministic_batch_id,
+        "rng_scheme_version": RNG_SCHEME_VERSION,
+        "rng_purpose_namespace": int(RandomPurpose.TOURNAMENT_SHUFFLE),
+        "outcome_schema_version": OUTCOME_SCHEMA_VERSION,
+        "tournament_method_version": TOURNAMENT_METHOD_VERSION, "pid": os.getpid(),
+    }
+    if state.game_profile is not None:
+        record["game_profile_sha256"] = state.game_profile.sha256
+    return record
+
+
+def _write_shard(out: Path, manifest_file: Path, table, manifest_extra: Mapping[str, Any]) -> None:
+    """Default shard writer: Parquet temp->fsync->rename, then one manifest line."""
+    import pyarrow.parquet as pq
+
+    _atomic_write(out, lambda p: pq.write_table(table, p))
+    _append_manifest(manifest_file, {"path": out.name, "rows": table.num_rows, **manifest_extra})
+
+
 def _run_chunk_metrics(shuffle_tasks: Sequence[ShuffleTask | int], *, collect_rows: bool = False,
                        row_dir: Path | None = None, manifest_path: Path | None = None,
-                       row_sidecar: object | None = None) -> Tuple[Counter, MetricSums, MetricSums]:
+                       row_sidecar: object | None = None,
+                       shard_writer: Callable[[Path, Path, Any, Mapping[str, Any]], None] | None = None
+                       ) -> Tuple[Counter, MetricSums, MetricSums]:
     """Play shuffles and accumulate metrics (run_tournament.py:473-585).
 
     In rows mode every shuffle leaves one Parquet shard
-    ``rows_{root}_{k}p_{shuffle:012d}.parquet`` plus one manifest line before returning,
-    written temp->rename.  ``row_sidecar`` (the reference's hash-bound artifact sidecar) is
-    accepted but not produced: the artifact contract is outside this path.
+    ``rows_{root}_{k}p_{shuffle:012d}.parquet`` plus one manifest line before returning.
+    ``shard_writer(out_path, manifest_path, arrow_table, manifest_extra)`` publishes a shard; the
+    default writes temp->rename without a sidecar, ``reference_shim`` passes the reference's own
+    ``run_streaming_shard`` so that hash-bound sidecars come out exactly as the reference
+    writes them.  ``row_sidecar`` without such a writer is refused: the artifact contract is
+    outside this path.
     """
-    import pyarrow.parquet as pq
-
-    del row_sidecar
+    if row_sidecar is not None and shard_writer is None:
+        raise NotImplementedError("row_sidecar needs a shard_writer that implements the artifact contract")
     state = _require_state()
     tasks = [_coerce_shuffle_task(t) for t in shuffle_tasks]
     wins_total = OutcomeCounter()
     sums_total: MetricSums = {m: defaultdict(float) for m in METRIC_LABELS}
     sq_total: MetricSums = {m: defaultdict(float) for m in METRIC_LABELS}
     want_rows = collect_rows and row_dir is not None
+    writer = shard_writer or _write_shard
     gps = state.cfg.games_per_shuffle
     for a, b in _contiguous_runs(tasks):
         run = tasks[a:b]
@@ -400,20 +429,8 @@ def _run_chunk_metrics(shuffle_tasks: Sequence[ShuffleTask | int], *, collect_ro
                 game_index=np.arange(gps), deterministic_batch_id=task.deterministic_batch_id,
                 shuffle_seed=task.shuffle_seed)
             out = Path(row_dir) / f"rows_{task.root_seed}_{task.k}p_{task.shuffle_index:012d}.parquet"
-            _atomic_write(out, lambda p, t=tbl: pq.write_table(t, p))
-            record = {
-                "path": out.name, "rows": tbl.num_rows, "root_seed": task.root_seed,
-                "n_players": task.k, "shuffle_index": task.shuffle_index,
-                "shuffle_seed": task.shuffle_seed,
-                "deterministic_batch_id": task.deterministic_batch_id,
-                "rng_scheme_version": RNG_SCHEME_VERSION,
-                "rng_purpose_namespace": int(RandomPurpose.TOURNAMENT_SHUFFLE),
-                "outcome_schema_version": OUTCOME_SCHEMA_VERSION,
-                "tournament_method_version": TOURNAMENT_METHOD_VERSION, "pid": os.getpid(),
-            }
-            if state.game_profile is not None:
-                record["game_profile_sha256"] = state.game_profile.sha256
-            _append_manifest(Path(manifest_path or (Path(row_dir) / "manifest.jsonl")), record)
+            writer(out, Path(manifest_path or (Path(row_dir) / "manifest.jsonl")), tbl,
+                   shard_manifest_extra(state, task, out.name))
     return wins_total, sums_total, sq_total
 
 

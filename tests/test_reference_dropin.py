@@ -79,3 +79,41 @@ def test_reference_driver_with_gpu_seams(ref_rt, tmp_path):
     assert {m: dict(v) for m, v in got[1].items()} == {m: dict(v) for m, v in want[1].items()}
     assert {m: dict(v) for m, v in got[2].items()} == {m: dict(v) for m, v in want[2].items()}
     assert got[3] == want[3] and [list(r) for r in got[3]] == [list(r) for r in want[3]]
+
+
+def test_row_shards_through_the_reference_writer(ref_rt, tmp_path):
+    """Rows mode: the shim hands its Arrow tables to the reference's own run_streaming_shard, so the
+    shards and manifest lines must equal the reference's (pid and timestamps aside)."""
+    import json
+
+    import pyarrow.parquet as pq
+    from farkle.simulation import simulation as ref_sim
+
+    from farkle_ii_b200 import reference_shim
+
+    rt = ref_rt
+    strats = _grid(ref_sim)
+    cfg = rt.TournamentConfig(n_players=5, n_strategies=len(strats))
+    tasks = [rt.ShuffleTask(54, 5, s, 1000 + s, s // 2) for s in (3, 4, 7)]
+    rt._init_worker(strats, cfg)
+    want = rt._run_chunk_metrics(tasks, collect_rows=True, row_dir=tmp_path / "ref",
+                                 manifest_path=tmp_path / "ref" / "manifest.jsonl")
+    originals = reference_shim.install(rt)
+    try:
+        rt._init_worker(strats, cfg)
+        got = rt._run_chunk_metrics(tasks, collect_rows=True, row_dir=tmp_path / "gpu",
+                                    manifest_path=tmp_path / "gpu" / "manifest.jsonl")
+    finally:
+        reference_shim.uninstall(originals, rt)
+    assert dict(got[0]) == dict(want[0]) and got[0].outcome_payload() == want[0].outcome_payload()
+    for i in (1, 2):
+        assert {m: dict(v) for m, v in got[i].items()} == {m: dict(v) for m, v in want[i].items()}
+    drop = ("pid", "ts", "timestamp", "written_at")
+    lines = {side: [{k: v for k, v in json.loads(x).items() if k not in drop}
+                    for x in (tmp_path / side / "manifest.jsonl").read_text().splitlines()]
+             for side in ("ref", "gpu")}
+    assert lines["gpu"] == lines["ref"] and len(lines["ref"]) == 3
+    for rec in lines["ref"]:
+        a = pq.read_table(tmp_path / "ref" / rec["path"])
+        b = pq.read_table(tmp_path / "gpu" / rec["path"])
+        assert a.schema == b.schema and a.equals(b)
