@@ -117,3 +117,29 @@ def test_row_shards_through_the_reference_writer(ref_rt, tmp_path):
         a = pq.read_table(tmp_path / "ref" / rec["path"])
         b = pq.read_table(tmp_path / "gpu" / rec["path"])
         assert a.schema == b.schema and a.equals(b)
+
+
+def test_h2h_block_runner_against_reference(ref_rt, tmp_path):
+    """The H2H BlockRunner (h2h_schedule.py:1521): same progress dict as the reference's
+    `_simulate_block`, accepted unchanged by its `_normalize_runner_result`."""
+    from farkle.analysis import h2h_schedule as ref_h2h
+    from farkle.simulation import simulation as ref_sim
+    from farkle.simulation.strategies import build_strategy_manifest
+
+    from farkle_ii_b200 import h2h as gpu_h2h
+
+    strats = ref_sim.generate_strategy_grid()[0]
+    manifest_path = tmp_path / "strategy_manifest.parquet"
+    build_strategy_manifest(strats).to_parquet(manifest_path)
+    for pair_id, (a, b), order, target, max_att in ((7, (12, 3400), 0, 20, 40), (8, (5000, 77), 1, 15, 30)):
+        s1, s2 = (a, b) if order == 0 else (b, a)
+        block = {"block_id": f"blk{pair_id}", "family_hash": "fam", "schedule_hash": "sched",
+                 "root_seed": 4242, "pair_id": pair_id, "order": order, "seat1_strategy": s1,
+                 "seat2_strategy": s2, "n_completed_required": target, "max_attempts": max_att,
+                 "rng_scheme_version": 2, "rng_purpose_namespace": 203}
+        for chunk in (7, 5000):
+            want = ref_h2h._simulate_block(dict(block), manifest_path, chunk)
+            got = gpu_h2h.gpu_block_runner(dict(block), manifest_path, chunk)
+            assert got == want and list(got) == list(want)
+            assert ref_h2h._normalize_runner_result(block, got) == ref_h2h._normalize_runner_result(block, want)
+            block = dict(want)          # resume from the reference's progress
