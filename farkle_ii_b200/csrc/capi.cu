@@ -839,8 +839,9 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
                                 const int32_t* override_max_rounds_dev, int n_overrides, int shuffles_per_slot,
                                 int64_t* tallies_dev, int64_t* totals_dev, void* rows_dev, int want_game_seeds,
                                 void* workspace_dev, size_t workspace_bytes, void* stream_v,
-                                uint32_t ordinal_base) {
+                                uint32_t ordinal_base, int64_t* seat_tallies_dev = nullptr) {
     FB_REQUIRE_INIT();
+    if (seat_tallies_dev && !tallies_dev) return fail(FB_ERR_BAD_ARG, "seat tallies need tallies_dev");
     cudaStream_t stream = (cudaStream_t)stream_v;
     if (k < 1 || k > FB_MAX_PLAYERS) return fail(FB_ERR_BAD_ARG, "k=%d outside [1,%d]", k, FB_MAX_PLAYERS);
     if (n_strategies < k || n_strategies % k != 0)
@@ -919,6 +920,7 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
     G.chunk = shuffles_per_slot > 0 ? shuffles_per_slot : 43;
     G.slotted = shuffles_per_slot > 0;
     G.tallies = F.tallies;
+    G.seat_tallies = reinterpret_cast<unsigned long long*>(seat_tallies_dev);
     const int n_chunks = (n_shuffles + G.chunk - 1) / G.chunk;
     tally_gather_kernel<<<dim3(blocks_for((uint64_t)n_strategies, 128), (unsigned)n_chunks), 128, 0, stream>>>(G);
     return launch_check("tally_gather_kernel");
@@ -935,6 +937,21 @@ int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuff
                                 n_tally_ids, target_score, max_rounds, override_shuffle_dev, override_game_dev,
                                 override_max_rounds_dev, n_overrides, shuffles_per_slot, tallies_dev, totals_dev,
                                 rows_dev, want_game_seeds, workspace_dev, workspace_bytes, stream_v, 0u);
+}
+
+int fb_play_tournament_seats(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
+                             const fb_strategy_t* strategies_dev, const int32_t* strategy_ids_dev,
+                             int n_strategies, int n_tally_ids, int32_t target_score, int32_t max_rounds,
+                             const uint64_t* override_shuffle_dev, const uint32_t* override_game_dev,
+                             const int32_t* override_max_rounds_dev, int n_overrides, int shuffles_per_slot,
+                             int64_t* tallies_dev, int64_t* totals_dev, void* rows_dev, int want_game_seeds,
+                             int64_t* seat_tallies_dev, void* workspace_dev, size_t workspace_bytes,
+                             void* stream_v) {
+    return play_tournament_impl(root_seed, k, shuffle0, n_shuffles, strategies_dev, strategy_ids_dev, n_strategies,
+                                n_tally_ids, target_score, max_rounds, override_shuffle_dev, override_game_dev,
+                                override_max_rounds_dev, n_overrides, shuffles_per_slot, tallies_dev, totals_dev,
+                                rows_dev, want_game_seeds, workspace_dev, workspace_bytes, stream_v, 0u,
+                                seat_tallies_dev);
 }
 
 int fb_play_h2h(uint64_t root_seed, int n_blocks, const uint64_t* pair_id_dev, const uint8_t* order_dev,

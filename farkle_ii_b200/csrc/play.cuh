@@ -611,6 +611,7 @@ struct GatherParams {
     int chunk;    // shuffles per thread
     int slotted;  // 1: chunk c -> tally slot c, 0: single slot
     unsigned long long* tallies;
+    unsigned long long* seat_tallies;  // [slots][ids][k][FB_SEAT_TALLY_WIDTH] or nullptr
 };
 
 __global__ void __launch_bounds__(128) tally_gather_kernel(const GatherParams G) {
@@ -626,9 +627,19 @@ __global__ void __launch_bounds__(128) tally_gather_kernel(const GatherParams G)
         const uint32_t gi = pos / (uint32_t)G.k, seat = pos - gi * (uint32_t)G.k;
         const uint32_t game = (uint32_t)j * G.gps + gi;
         const uint32_t hdr = __ldg(&G.header[game]);
-        if ((hdr >> 16) & FB_ROW_SAFETY_LIMIT) {
+        const bool is_safety = (hdr >> 16) & FB_ROW_SAFETY_LIMIT;
+        const bool won = !is_safety && ((hdr >> 24) & 15u) == seat + 1u;
+        if (G.seat_tallies) {  // per (strategy, seat): wins, exposures, completed, safety limit
+            const int sid_s = G.strategy_ids ? G.strategy_ids[i] : i;
+            unsigned long long* S = G.seat_tallies +
+                (((size_t)(G.slotted ? c : 0) * G.n_tally_ids + sid_s) * G.k + seat) * FB_SEAT_TALLY_WIDTH;
+            if (won) atomicAdd(&S[0], 1ull);
+            atomicAdd(&S[1], 1ull);
+            atomicAdd(&S[is_safety ? 3 : 2], 1ull);
+        }
+        if (is_safety) {
             safety++;
-        } else if (((hdr >> 24) & 15u) == seat + 1u) {
+        } else if (won) {
             const Seat* s = G.seats + ((size_t)game * G.k + seat);
             const uint4 a = __ldg(&s->a), b = __ldg(&s->b);
             // METRIC_LABELS order, run_tournament.py:109-121 (winner_hit_max_rounds stays 0)

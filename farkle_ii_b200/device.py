@@ -16,6 +16,7 @@ import torch
 
 from . import _native
 from .layout import (
+    SEAT_TALLY_WIDTH,
     STRATEGY_DTYPE,
     TALLY_WIDTH,
     TOTALS_WIDTH,
@@ -52,6 +53,7 @@ class TournamentResult:
     rows: torch.Tensor | None     # uint8 [n_games, stride]
     n_games: int
     k: int
+    seat_tallies: torch.Tensor | None = None  # int64 [slots, ids, k, 4]
 
     def rows_numpy(self) -> np.ndarray:
         assert self.rows is not None
@@ -209,7 +211,8 @@ class Engine:
                         max_rounds: int = 200, overrides=(), shuffles_per_slot: int = 0,
                         want_tallies: bool = True, want_rows: bool = False,
                         want_game_seeds: bool = False, tallies: torch.Tensor | None = None,
-                        totals: torch.Tensor | None = None) -> TournamentResult:
+                        totals: torch.Tensor | None = None, want_seat_tallies: bool = False,
+                        seat_tallies: torch.Tensor | None = None) -> TournamentResult:
         """Enqueue shuffles ``shuffle0 .. shuffle0+n_shuffles-1`` of cell (root_seed, k).
 
         ``strategies`` is a device uint8 tensor holding ``fb_strategy_t`` entries, or a
@@ -236,6 +239,9 @@ class Engine:
                                   device=self.device)
         if totals is None:
             totals = torch.zeros(TOTALS_WIDTH, dtype=torch.int64, device=self.device)
+        if want_seat_tallies and seat_tallies is None:
+            seat_tallies = torch.zeros((n_slots, n_tally_ids, max(k, 1), SEAT_TALLY_WIDTH),
+                                       dtype=torch.int64, device=self.device)
         rows = None
         if want_rows:
             rows = torch.empty((max(n_games, 1), row_stride(k)), dtype=torch.uint8,
@@ -248,12 +254,12 @@ class Engine:
             d_om = self.to_device(np.array([o[2] for o in ov], dtype=np.int32))
         ws_bytes = self.workspace_bytes(max(k, 1), n_games) + 2 * (n_shuffles * n_strategies * 4 + 256)
         ws = self.workspace(ws_bytes)
-        _native.check(self.lib.fb_play_tournament(
+        _native.check(self.lib.fb_play_tournament_seats(
             root_seed, k, shuffle0, n_shuffles, _ptr(strategies), _ptr(d_ids), n_strategies,
             n_tally_ids, target_score, max_rounds, _ptr(d_os), _ptr(d_og), _ptr(d_om), len(ov),
             shuffles_per_slot, _ptr(tallies if want_tallies else None), _ptr(totals), _ptr(rows),
-            int(want_game_seeds), _ptr(ws), ws.numel(), self._stream()))
-        return TournamentResult(tallies if want_tallies else None, totals, rows, n_games, k)
+            int(want_game_seeds), _ptr(seat_tallies), _ptr(ws), ws.numel(), self._stream()))
+        return TournamentResult(tallies if want_tallies else None, totals, rows, n_games, k, seat_tallies)
 
     def play_games(self, coords: np.ndarray, k: int, seat_strategies: np.ndarray, *,
                    seat_strategy_ids=None, target_score: int = 10_000, max_rounds: int = 200,

@@ -615,3 +615,54 @@ def run_tournament(*, config: TournamentConfig | None = None, global_seed: int =
         ], schema=schema)
         _atomic_write(ckpt_path.with_name(f"{k}p_metrics.parquet"), lambda p: pq.write_table(tbl, p))
     LOGGER.info("Tournament run complete after %d attempted games", wins.games_attempted)
+
+
+# --------------------------------------------------------------------------- seat tallies
+def seat_counts_from_rows(rows: np.ndarray, batch_ids: np.ndarray) -> Dict[Tuple[int, int, int], List[int]]:
+    """``{(batch, strategy, seat 1-based): [wins, exposures, completed, safety_limit]}`` from compact
+    rows — the counts of the reference's ``_iter_seat_count_tables`` (analysis/seat_analysis.py:166-229).
+    Host restatement used to check the device-side seat tallies."""
+    out: Dict[Tuple[int, int, int], List[int]] = {}
+    k = rows["seats"].shape[1]
+    safety = (rows["flags"] & 1) != 0
+    for s in range(k):
+        strat = rows["seats"]["strategy"][:, s]
+        won = (~safety) & (rows["winner_seat"] == s)
+        for b, sid, w, sl in zip(batch_ids.tolist(), strat.tolist(), won.tolist(), safety.tolist()):
+            cell = out.setdefault((b, sid, s + 1), [0, 0, 0, 0])
+            cell[0] += int(w)
+            cell[1] += 1
+            cell[2] += int(not sl)
+            cell[3] += int(sl)
+    return out
+
+
+def seat_counts_table(seat_tallies: np.ndarray, ids: Sequence[int], *, root_seed: int, k: int,
+                      first_batch_id: int = 0):
+    """Device seat tallies ``[slots, ids, k, 4]`` -> Arrow table with the reference's seat-count
+    schema (analysis/seat_analysis.py:42-54), rows ordered by (batch, strategy, seat), empty cells
+    dropped."""
+    import pyarrow as pa
+
+    t = np.asarray(seat_tallies)
+    n_slots, n_ids = t.shape[0], t.shape[1]
+    order = np.argsort(np.asarray(ids), kind="stable")
+    t = t[:, order]
+    sid = np.asarray(ids)[order]
+    slot_i, id_i, seat_i = np.nonzero(t[..., 1])
+    schema = pa.schema([
+        pa.field("root_seed", pa.int64(), nullable=False), pa.field("k", pa.int16(), nullable=False),
+        pa.field("deterministic_batch_id", pa.int32(), nullable=False),
+        pa.field("strategy", pa.int32(), nullable=False), pa.field("seat", pa.int16(), nullable=False),
+        pa.field("raw_wins", pa.int64(), nullable=False),
+        pa.field("raw_exposures", pa.int64(), nullable=False),
+        pa.field("raw_completed_exposures", pa.int64(), nullable=False),
+        pa.field("raw_safety_limit_exposures", pa.int64(), nullable=False)])
+    cells = t[slot_i, id_i, seat_i]
+    n = len(slot_i)
+    del n_slots, n_ids
+    return pa.Table.from_arrays([
+        pa.array(np.full(n, root_seed, dtype=np.int64)), pa.array(np.full(n, k, dtype=np.int16)),
+        pa.array((slot_i + first_batch_id).astype(np.int32)), pa.array(sid[id_i].astype(np.int32)),
+        pa.array((seat_i + 1).astype(np.int16)), pa.array(cells[:, 0]), pa.array(cells[:, 1]),
+        pa.array(cells[:, 2]), pa.array(cells[:, 3])], schema=schema)

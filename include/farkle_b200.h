@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FB_ABI_VERSION 1
+#define FB_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------- */
 enum fb_status {
@@ -118,6 +118,12 @@ typedef struct fb_row_seat {
  */
 #define FB_TALLY_WIDTH 26
 #define FB_N_METRICS 11
+
+/* Optional per-seat tallies, int64[n_slots][n_tally_ids][k][FB_SEAT_TALLY_WIDTH]
+ * (the counts src/farkle/analysis/seat_analysis.py:166-229 re-derives from rows):
+ *   0 raw_wins  1 raw_exposures  2 raw_completed_exposures
+ *   3 raw_safety_limit_exposures        of strategy id x 0-based seat.        */
+#define FB_SEAT_TALLY_WIDTH 4
 
 /* Per-launch totals, int64[FB_TOTALS_WIDTH]:
  *   0 games_attempted  1 games_completed  2 games_safety_limit
@@ -219,6 +225,18 @@ int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuff
                        int n_overrides, int shuffles_per_slot, int64_t* tallies_dev,
                        int64_t* totals_dev, void* rows_dev, int want_game_seeds,
                        void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* fb_play_tournament plus the per-seat tallies (seat_tallies_dev accumulated into, caller
+ * zeroes; NULL = plain fb_play_tournament; needs tallies_dev).                */
+int fb_play_tournament_seats(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
+                             const fb_strategy_t* strategies_dev, const int32_t* strategy_ids_dev,
+                             int n_strategies, int n_tally_ids, int32_t target_score,
+                             int32_t max_rounds, const uint64_t* override_shuffle_dev,
+                             const uint32_t* override_game_dev,
+                             const int32_t* override_max_rounds_dev, int n_overrides,
+                             int shuffles_per_slot, int64_t* tallies_dev, int64_t* totals_dev,
+                             void* rows_dev, int want_game_seeds, int64_t* seat_tallies_dev,
+                             void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* Head-to-head attempts.  Replaces the attempt loop of
  * _simulate_block_from_manifest (src/farkle/analysis/h2h_schedule.py:1149-1243)

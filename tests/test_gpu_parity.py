@@ -510,3 +510,29 @@ def test_host_call_streams_rows_in_chunks(eng, golden_dir, spb):
     assert got.tobytes() == want_rows.tobytes()
     if spb:
         assert np.array_equal(t[3], want_t[0])
+
+
+@pytest.mark.parametrize("name,spb", [("fast_54_4", 2), ("fast_42_2", 5), ("full_0_5", 0)])
+def test_seat_tallies(eng, golden_dir, name, spb):
+    """Per (batch, strategy, seat) wins / exposures / completed / safety-limit counts from the
+    gather pass equal the counts the reference's seat analysis derives from the rows
+    (analysis/seat_analysis.py:166-229; the rows themselves are golden)."""
+    from farkle_ii_b200 import run_tournament as frt
+
+    z = np.load(golden_dir / f"games_{name}.npz")
+    root, k, sh0, nsh = (int(x) for x in z["meta"])
+    res = eng.play_tournament(root, k, sh0, nsh, z["strategies"], shuffles_per_slot=spb,
+                              want_seat_tallies=True)
+    seat = res.seat_tallies.cpu().numpy()
+    n = len(z["strategies"])
+    gps = n // k
+    batch = (np.arange(len(z["rows"])) // gps) // (spb if spb else nsh)
+    want = frt.seat_counts_from_rows(z["rows"], batch)
+    got = {(int(b), int(s), int(q) + 1): seat[b, s, q].tolist()
+           for b, s, q in zip(*np.nonzero(seat[..., 1]))}
+    assert got == want
+    assert (seat[..., 1] == seat[..., 2] + seat[..., 3]).all()
+    assert np.array_equal(seat[..., 0].sum(axis=2), res.tallies.cpu().numpy()[..., 0])
+    tbl = frt.seat_counts_table(seat, np.arange(n), root_seed=root, k=k)
+    assert tbl.num_rows == len(want) and tbl.column("raw_exposures").to_pylist() == [
+        want[key][1] for key in sorted(want)]

@@ -143,3 +143,32 @@ def test_h2h_block_runner_against_reference(ref_rt, tmp_path):
             assert got == want and list(got) == list(want)
             assert ref_h2h._normalize_runner_result(block, got) == ref_h2h._normalize_runner_result(block, want)
             block = dict(want)          # resume from the reference's progress
+
+
+def test_seat_count_semantics_match_reference_seat_analysis(ref_rt, tmp_path):
+    """`seat_counts_from_rows` (the host restatement the GPU seat tallies are tested against) equals
+    the reference's `_iter_seat_count_tables` on a curated Parquet of the same games."""
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from farkle.analysis import seat_analysis as ref_seat
+
+    from farkle_ii_b200 import run_tournament as frt
+    from farkle_ii_b200 import simulation as fsim
+
+    z = np.load(Path(__file__).parent / "golden" / "games_fast_54_4.npz")
+    root, k, sh0, nsh = (int(x) for x in z["meta"])
+    rows = z["rows"]
+    gps = len(z["strategies"]) // k
+    shuffle = sh0 + np.arange(len(rows)) // gps
+    batch = (shuffle - sh0) // 2
+    tbl = fsim.compact_rows_to_table(rows, root_seed=root, k=k, shuffle_index=shuffle,
+                                     game_index=np.arange(len(rows)) % gps,
+                                     deterministic_batch_id=batch, shuffle_seed=0)
+    src = tmp_path / "curated.parquet"
+    pq.write_table(tbl, src)
+    ref_tbl = pa.concat_tables(list(ref_seat._iter_seat_count_tables(src, k))).to_pylist()
+    want = {(r["deterministic_batch_id"], r["strategy"], r["seat"]):
+            [r["raw_wins"], r["raw_exposures"], r["raw_completed_exposures"], r["raw_safety_limit_exposures"]]
+            for r in ref_tbl}
+    assert frt.seat_counts_from_rows(rows, batch) == want
