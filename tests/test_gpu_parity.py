@@ -536,3 +536,16 @@ def test_seat_tallies(eng, golden_dir, name, spb):
     tbl = frt.seat_counts_table(seat, np.arange(n), root_seed=root, k=k)
     assert tbl.num_rows == len(want) and tbl.column("raw_exposures").to_pylist() == [
         want[key][1] for key in sorted(want)]
+
+
+def test_full_size_cell_bit_exact(eng, golden_dir):
+    """The whole BASELINE cell — full grid, k=2, root 43, all 4,300 shuffles = 11,094,000 games —
+    bit for bit against the oracle: every per-batch tally slot and the launch totals."""
+    import os
+
+    table = np.load(golden_dir / "games_full_0_2.npz")["strategies"]
+    res = eng.play_tournament(43, 2, 0, 4300, table, shuffles_per_slot=43)
+    want_t, want_tot, _ = fo.play_tournament(43, 2, 0, 4300, table, shuffles_per_slot=43,
+                                             n_threads=os.cpu_count() or 8)
+    assert np.array_equal(res.tallies.cpu().numpy(), want_t)
+    assert np.array_equal(res.totals.cpu().numpy(), want_tot)
