@@ -36,6 +36,10 @@ def get_engine(device: int | None = None) -> "Engine":
         device = torch.cuda.current_device()
     eng = _engines.get(device)
     if eng is None:
+        if _engines:  # the C library binds ONE device per process (one process per GPU)
+            raise _native.NativeError(
+                f"this process is already bound to cuda:{next(iter(_engines))}; "
+                "run one process per GPU (torchrun) instead of switching devices")
         eng = _engines[device] = Engine(device)
     return eng
 
