@@ -273,8 +273,9 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                 }
             }
             q_head += have;
+            // lanes only die here, so this is the one place the warp can run out of work
+            if (__all_sync(FULL, status == ST_DEAD)) return true;
         }
-        if (__all_sync(FULL, status == ST_DEAD)) return true;
 
         // ================= P: one roll (straight-line, no divergent branches) =====
         if (status == ST_PLAY) {
