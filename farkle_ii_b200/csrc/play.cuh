@@ -458,6 +458,8 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
         if (roll_step()) break;
     }
 
+    cp_async_wait_all();  // no prefetch may still be in flight when the CTA's shared memory is released
+
     // ---- work counters: warp shuffle -> shared memory -> one global RED per CTA ----
     unsigned long long v[2] = {a_dice, a_words};
 #pragma unroll
