@@ -125,6 +125,67 @@ def parse_strategy_identifier(value: Any, manifest: Any) -> ThresholdStrategy:
     return ThresholdStrategy(**attrs, strategy_id=sid)
 
 
+_PACKED_MANIFESTS: dict[int, tuple[Any, np.ndarray, np.ndarray]] = {}
+
+
+def _packed_manifest(manifest: Any) -> tuple[np.ndarray, np.ndarray]:
+    """``(sorted strategy ids, packed fb_strategy_t rows)`` of a manifest, built once per manifest
+    object (a schedule looks the same two columns up for tens of thousands of blocks)."""
+    from .layout import (SF_AUTO_HOT_DICE, SF_CONSIDER_DICE, SF_CONSIDER_SCORE, SF_FAVOR_SCORE,
+                         SF_REQUIRE_BOTH, SF_RUN_UP_SCORE, SF_SMART_FIVE, SF_SMART_ONE, STRATEGY_DTYPE)
+
+    hit = _PACKED_MANIFESTS.get(id(manifest))
+    if hit is not None and hit[0] is manifest:
+        return hit[1], hit[2]
+    if isinstance(manifest, Mapping):
+        ids = np.array(sorted(manifest), dtype=np.int64)
+        packed = pack_strategies([manifest[int(i)] for i in ids])
+    else:
+        frame = manifest.sort_values("strategy_id", kind="mergesort")
+        ids = frame["strategy_id"].to_numpy(dtype=np.int64)
+        flags = np.zeros(len(frame), dtype=np.uint16)
+        for col, bit in (("smart_five", SF_SMART_FIVE), ("smart_one", SF_SMART_ONE),
+                         ("consider_score", SF_CONSIDER_SCORE), ("consider_dice", SF_CONSIDER_DICE),
+                         ("require_both", SF_REQUIRE_BOTH), ("auto_hot_dice", SF_AUTO_HOT_DICE),
+                         ("run_up_score", SF_RUN_UP_SCORE)):
+            flags |= np.where(frame[col].to_numpy(dtype=bool), bit, 0).astype(np.uint16)
+        favor = frame["favor_dice_or_score"].map(
+            lambda v: (v if isinstance(v, str) else getattr(v, "value", v)) == FavorDiceOrScore.SCORE.value)
+        flags |= np.where(favor.to_numpy(dtype=bool), SF_FAVOR_SCORE, 0).astype(np.uint16)
+        smart_one_without_five = (flags & SF_SMART_ONE != 0) & (flags & SF_SMART_FIVE == 0)
+        both_without_two = (flags & SF_REQUIRE_BOTH != 0) & (
+            (flags & SF_CONSIDER_SCORE == 0) | (flags & SF_CONSIDER_DICE == 0))
+        if smart_one_without_five.any() or both_without_two.any():
+            raise ValueError("strategy manifest holds a combination ThresholdStrategy rejects")
+        packed = np.zeros(len(frame), dtype=STRATEGY_DTYPE)
+        packed["score_threshold"] = frame["score_threshold"].to_numpy(dtype=np.int64)
+        packed["dice_threshold"] = frame["dice_threshold"].to_numpy(dtype=np.int64)
+        packed["flags"] = flags
+    if len(_PACKED_MANIFESTS) > 4:
+        _PACKED_MANIFESTS.clear()
+    _PACKED_MANIFESTS[id(manifest)] = (manifest, ids, packed)
+    return ids, packed
+
+
+def _lookup_packed(manifest: Any, wanted: Sequence[Any]) -> np.ndarray:
+    """Packed strategies of canonical numeric identifiers (strategies.py:762-800), vectorised."""
+    numeric = []
+    for value in wanted:
+        if (isinstance(value, (int, np.integer)) and not isinstance(value, bool)) or (
+                isinstance(value, str) and value.isdigit()):
+            numeric.append(int(value))
+        else:
+            raise ValueError(f"Cannot parse nonnumeric strategy identifier: {value!r}")
+    ids, packed = _packed_manifest(manifest)
+    want = np.asarray(numeric, dtype=np.int64)
+    pos = np.searchsorted(ids, want)
+    pos_c = np.minimum(pos, max(len(ids) - 1, 0))
+    missing = (len(ids) == 0) | (ids[pos_c] != want) if len(ids) else np.ones(len(want), dtype=bool)
+    if np.any(missing):
+        raise KeyError(f"strategy_id {int(want[np.argmax(missing)])} missing from manifest/encoder")
+    return packed[pos_c]
+
+
 def _check_outcomes(outcome: np.ndarray) -> None:
     if (outcome & 0x80).any():
         raise RollLimitError("an H2H attempt hit ROLL_LIMIT or overflowed an int16 row counter")
@@ -149,8 +210,8 @@ def simulate_blocks(blocks: Sequence[Mapping[str, Any]], manifest: Any, chunk_ga
     prof = oracle_game_profile
     target_score = prof.default_target_score if prof else 10_000
     max_rounds = prof.default_max_rounds if prof else 200
-    s1 = pack_strategies([parse_strategy_identifier(b["seat1_strategy"], manifest) for b in blocks])
-    s2 = pack_strategies([parse_strategy_identifier(b["seat2_strategy"], manifest) for b in blocks])
+    s1 = _lookup_packed(manifest, [b["seat1_strategy"] for b in blocks])
+    s2 = _lookup_packed(manifest, [b["seat2_strategy"] for b in blocks])
     root = np.array([int(b["root_seed"]) for b in blocks], dtype=np.uint64)
     pair = np.array([int(b["pair_id"]) for b in blocks], dtype=np.uint64)
     order = np.array([int(b["order"]) for b in blocks], dtype=np.uint8)

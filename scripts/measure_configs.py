@@ -126,4 +126,22 @@ out["h2h_2p"] = {"blocks": nb, "n_completed_required": target, "max_attempts": m
                  "unresolved_blocks": int(((prog[:, 1] < target) & (prog[:, 0] >= max_attempts)).sum()),
                  "games_completed": int(prog[:, 1].sum()), "games_safety_limit": int(prog[:, 2].sum()),
                  "note": "wall clock including host progress bookkeeping, H2D block tables and D2H progress"}
+# the same schedule through the Python surface (block dicts in, progress dicts out)
+from farkle_ii_b200 import h2h as fh2h  # noqa: E402
+
+manifest = fh2h.build_strategy_manifest(generate_strategy_grid()[0])
+block_dicts = [{"block_id": f"b{i}", "family_hash": "f", "schedule_hash": "s", "root_seed": 42,
+                "pair_id": int(blocks_pair[i]), "order": int(order[i]), "seat1_strategy": int(s1[i]),
+                "seat2_strategy": int(s2[i]), "n_completed_required": target, "max_attempts": max_attempts,
+                "rng_scheme_version": 2, "rng_purpose_namespace": 203} for i in range(nb)]
+fh2h.simulate_blocks(block_dicts[:64], manifest, max_attempts)
+t0 = time.perf_counter()
+results = fh2h.simulate_blocks(block_dicts, manifest, max_attempts)
+dt = time.perf_counter() - t0
+out["h2h_2p_python_surface"] = {
+    "blocks": nb, "seconds": dt, "attempts": int(sum(r["games_attempted"] for r in results)),
+    "attempts_per_s": sum(r["games_attempted"] for r in results) / dt,
+    "complete_blocks": sum(r["completion_status"] == "complete" for r in results),
+    "note": "farkle_ii_b200.h2h.simulate_blocks: manifest lookup, launches, early-stop resolve, one result "
+            "dict per block with the reference's fields (incl. the attempt-range SHA-256)"}
 print(json.dumps(out, indent=1))
