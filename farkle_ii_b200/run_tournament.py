@@ -222,10 +222,28 @@ def _init_worker(strategies: Sequence[ThresholdStrategy], config: TournamentConf
     del progress_endpoint
     if len(strategies) % config.n_players != 0:
         raise ValueError(f"n_players must divide {len(strategies):,}")
-    strats = _prepare_public_helper_strategies(strategies)
+    strats, table, ids = _prepared_table(strategies)
     config.n_strategies = len(strats)
-    _STATE = WorkerState(strats, config, game_profile, pack_strategies(strats),
-                         np.array([s.strategy_id for s in strats], dtype=np.int64), device)
+    _STATE = WorkerState(strats, config, game_profile, table, ids, device)
+
+
+_TABLE_CACHE: Dict[tuple, tuple] = {}
+
+
+def _prepared_table(strategies: Sequence[ThresholdStrategy]):
+    """Id resolution + packing of a strategy list, memoised on its contents: a runner calls
+    ``_init_worker`` once per (root, k) cell with the same 5,160-strategy grid."""
+    key = tuple((s.score_threshold, s.dice_threshold, s.smart_five, s.smart_one, s.consider_score,
+                 s.consider_dice, s.require_both, s.auto_hot_dice, s.run_up_score,
+                 s.favor_dice_or_score, s.strategy_id) for s in strategies)
+    hit = _TABLE_CACHE.get(key)
+    if hit is None:
+        strats = _prepare_public_helper_strategies(strategies)
+        hit = (strats, pack_strategies(strats), np.array([s.strategy_id for s in strats], dtype=np.int64))
+        if len(_TABLE_CACHE) >= 2:
+            _TABLE_CACHE.clear()
+        _TABLE_CACHE[key] = hit
+    return hit
 
 
 def _coerce_shuffle_task(task: ShuffleTask | int) -> ShuffleTask:
