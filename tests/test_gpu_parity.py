@@ -549,3 +549,32 @@ def test_full_size_cell_bit_exact(eng, golden_dir):
                                              n_threads=os.cpu_count() or 8)
     assert np.array_equal(res.tallies.cpu().numpy(), want_t)
     assert np.array_equal(res.totals.cpu().numpy(), want_tot)
+
+
+def test_random_tables_fuzz(eng):
+    """Random strategy tables (thresholds that are not multiples of 50, dice thresholds -1..6, every
+    legal flag combination incl. "considers nothing"), random k / target / safety limit: rows,
+    tallies and totals against the oracle."""
+    rng = np.random.Generator(np.random.PCG64DXSM(20260118))
+    for case in range(24):
+        k = int(rng.choice([1, 2, 2, 3, 4, 5, 6, 8, 12]))
+        n = k * int(rng.integers(2, 40))
+        table = np.zeros(n, dtype=fo.STRATEGY_DTYPE)
+        table["score_threshold"] = rng.integers(0, 1600, size=n) if case % 2 else rng.integers(0, 30, size=n) * 50
+        table["dice_threshold"] = rng.integers(-1, 7, size=n)
+        flags = rng.integers(0, 256, size=n)
+        flags &= np.where(flags & 0x01, 0xFF, 0xFF & ~0x02)                      # smart_one needs smart_five
+        flags &= np.where((flags & 0x0C) == 0x0C, 0xFF, 0xFF & ~0x10)            # require_both needs both
+        table["flags"] = flags
+        target = int(rng.choice([200, 1000, 2500, 10_000]))
+        max_rounds = int(rng.choice([1, 3, 12, 200]))
+        nsh = int(rng.integers(1, 60))
+        root, sh0 = int(rng.integers(0, 2**62)), int(rng.integers(0, 2**40))
+        res = eng.play_tournament(root, k, sh0, nsh, table, target_score=target, max_rounds=max_rounds,
+                                  want_rows=True, want_game_seeds=True, shuffles_per_slot=int(rng.integers(0, 4)))
+        want_t, want_tot, want_rows = fo.play_tournament(
+            root, k, sh0, nsh, table, target_score=target, max_rounds=max_rounds, want_rows=True,
+            want_game_seeds=True, shuffles_per_slot=0, n_threads=4)
+        assert res.rows_numpy().tobytes() == want_rows.tobytes(), case
+        assert np.array_equal(res.tallies.cpu().numpy().sum(axis=0), want_t[0]), case
+        assert np.array_equal(res.totals.cpu().numpy(), want_tot), case
