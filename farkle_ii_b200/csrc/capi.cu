@@ -50,6 +50,7 @@ struct Ctx {
     void* host_ws = nullptr;
     size_t host_ws_bytes = 0;
     bool smem_opted = false;  // play_kernel dynamic shared memory opt-in done on this device
+    bool finish_opted = false;
     // fb_run_tournament_host: compute / copy streams and the events that hand the row buffers over
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
     cudaEvent_t ev_played[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
@@ -685,7 +686,12 @@ int launch_play(const PlayParams& P, const FinishParams& F, cudaStream_t stream)
     if (rc) return rc;
     FB_CUDA(cudaEventRecord(t_ev1, stream));
     t_ev_valid = true;
-    finish_kernel<<<(unsigned)((F.n_games + 255) / 256), 256, 0, stream>>>(F);
+    const size_t tile = F.rows ? (size_t)256 * F.row_words * 4 : 0;  // <= 88 KB at k = 12
+    if (tile > 40 * 1024 && !g_ctx.finish_opted) {
+        FB_CUDA(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 352));
+        g_ctx.finish_opted = true;
+    }
+    finish_kernel<<<(unsigned)((F.n_games + 255) / 256), 256, tile, stream>>>(F);
     return launch_check("finish_kernel");
 }
 
@@ -741,6 +747,7 @@ int fb_init(int device) {
     }
     g_ctx.device = device;
     g_ctx.smem_opted = false;
+    g_ctx.finish_opted = false;
     return FB_OK;
 }
 

@@ -496,7 +496,10 @@ struct FinishParams {
     uint8_t* outcome;  // [n_games] or nullptr
 };
 
+// Rows mode stages the CTA's 256 rows in dynamic shared memory and writes them out as one
+// contiguous run of 16-byte stores (coalesced); dynamic shared memory = 256 * row bytes then.
 __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
+    extern __shared__ __align__(16) uint32_t row_tile[];
     __shared__ unsigned long long s_tot[FB_TOTALS_WIDTH];
     if (threadIdx.x < FB_TOTALS_WIDTH) s_tot[threadIdx.x] = 0ull;
     __syncthreads();
@@ -534,7 +537,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
         if (F.outcome)
             F.outcome[g] = (uint8_t)((safety ? 0 : winner + 1) | ((flags & ~FB_ROW_SAFETY_LIMIT) ? 0x80 : 0));
         if (F.mark_winner) F.header[g] = hdr | ((uint32_t)(winner + 1) << 24);
-        uint32_t* row = F.rows ? F.rows + (size_t)g * F.row_words : nullptr;
+        uint32_t* row = F.rows ? row_tile + (size_t)threadIdx.x * F.row_words : nullptr;
         if (row) {
             const uint64_t gs = F.game_seed ? F.game_seed[g] : 0ull;
             reinterpret_cast<uint4*>(row)[0] =
@@ -560,6 +563,15 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
         if (row) {
             for (int w = 4 + 7 * k; w < F.row_words; w++) row[w] = 0u;  // padding
         }
+    }
+    if (F.rows) {  // the tile is one contiguous piece of the row array
+        __syncthreads();
+        const uint32_t first = blockIdx.x * blockDim.x;
+        const uint32_t n_rows = min((uint32_t)blockDim.x, F.n_games - first);
+        uint4* dst = reinterpret_cast<uint4*>(F.rows + (size_t)first * F.row_words);
+        const uint4* src = reinterpret_cast<const uint4*>(row_tile);
+        const uint32_t n_vec = n_rows * (uint32_t)F.row_words / 4u;
+        for (uint32_t i = threadIdx.x; i < n_vec; i += blockDim.x) dst[i] = src[i];
     }
     // ---- totals: warp shuffle -> shared memory -> one global RED per CTA ----
     if (F.totals) {
