@@ -137,3 +137,33 @@ def test_no_cpu_fallback():
 
     with pytest.raises(_native.NativeError):
         get_engine()
+
+
+def test_workload_planner_kats():
+    """The reference's own planner KATs (tests/unit/simulation/test_workload_planner.py:18-60) and
+    the grid sizes bench.py uses."""
+    from farkle_ii_b200.workload_planner import (minimum_shuffles_for_resolution,
+                                                 plan_tournament_workload, worst_case_wilson_width)
+
+    plan = plan_tournament_workload(root_seed=17, k=4, strategy_count=200, resolution_delta=0.03)
+    assert plan.required_shuffles_unrounded == 4265
+    assert worst_case_wilson_width(4264) > 0.03 and worst_case_wilson_width(4265) <= 0.03
+    assert (plan.required_shuffles, plan.batch_count, plan.shuffles_per_batch) == (4300, 100, 43)
+    assert plan.required_games == 215_000 and plan.achieved_resolution <= 0.03
+    assert plan.batch_construction == "equal_contiguous" and plan.status == "not_started"
+    low = plan_tournament_workload(root_seed=1, k=2, strategy_count=20, resolution_delta=0.9)
+    assert minimum_shuffles_for_resolution(0.9) == 1
+    assert (low.required_shuffles, low.shuffles_per_batch) == (3_000, 30)
+    capped = plan_tournament_workload(root_seed=9, k=2, strategy_count=10, resolution_delta=0.03,
+                                      shuffle_cap=4_000)
+    assert capped.cap_exceeded and capped.status == "blocked_by_cap"
+    assert capped.achieved_resolution_at_cap > 0.03
+    fast = plan_tournament_workload(root_seed=42, k=2, strategy_count=80, resolution_delta=0.08,
+                                    batch_count=20)
+    assert (fast.required_shuffles, fast.shuffles_per_batch, fast.required_games) == (600, 30, 24_000)
+    full = plan_tournament_workload(root_seed=42, k=2, strategy_count=5160, resolution_delta=0.03)
+    assert full.required_games == 11_094_000
+    assert full.with_games_per_second(4e8).projected_runtime_seconds == pytest.approx(0.0277, rel=1e-2)
+    for bad in (dict(k=1), dict(strategy_count=7), dict(batch_count=1), dict(resolution_delta=1.5)):
+        with pytest.raises(ValueError):
+            plan_tournament_workload(**{**dict(root_seed=0, k=2, strategy_count=10, resolution_delta=0.1), **bad})
