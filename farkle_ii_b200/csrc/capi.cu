@@ -60,8 +60,11 @@ std::mutex g_mu;
 std::atomic<uint64_t> g_launches{0};
 
 thread_local std::string t_err;
-thread_local cudaEvent_t t_ev0 = nullptr, t_ev1 = nullptr;
-thread_local bool t_ev_valid = false;
+// CUDA-event pairs around the most recent play_kernel launches of this thread (a ring)
+constexpr int EV_RING = 64;
+thread_local cudaEvent_t t_ev[EV_RING][2];
+thread_local bool t_ev_made = false;
+thread_local uint64_t t_ev_count = 0;  // launches recorded so far
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -669,11 +672,15 @@ int launch_play(const PlayParams& P, const FinishParams& F, cudaStream_t stream)
         FB_CUDA(cudaFuncSetAttribute(play_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         g_ctx.smem_opted = true;
     }
-    if (!t_ev0) {
-        FB_CUDA(cudaEventCreate(&t_ev0));
-        FB_CUDA(cudaEventCreate(&t_ev1));
+    if (!t_ev_made) {
+        for (int i = 0; i < EV_RING; i++) {
+            FB_CUDA(cudaEventCreate(&t_ev[i][0]));
+            FB_CUDA(cudaEventCreate(&t_ev[i][1]));
+        }
+        t_ev_made = true;
     }
-    FB_CUDA(cudaEventRecord(t_ev0, stream));
+    cudaEvent_t* ev = t_ev[t_ev_count % EV_RING];
+    FB_CUDA(cudaEventRecord(ev[0], stream));
     const dim3 block((unsigned)warps * 32u);
     if (P.k == 2) {
         if (P.limits) play_kernel<true, true><<<grid, block, smem, stream>>>(P, g_ctx.lut_dev);
@@ -684,8 +691,8 @@ int launch_play(const PlayParams& P, const FinishParams& F, cudaStream_t stream)
     }
     int rc = launch_check("play_kernel");
     if (rc) return rc;
-    FB_CUDA(cudaEventRecord(t_ev1, stream));
-    t_ev_valid = true;
+    FB_CUDA(cudaEventRecord(ev[1], stream));
+    t_ev_count++;
     const size_t tile = F.rows ? (size_t)256 * F.row_words * 4 : 0;  // <= 88 KB at k = 12
     if (tile > 40 * 1024 && !g_ctx.finish_opted) {
         FB_CUDA(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 352));
@@ -1203,12 +1210,20 @@ int fb_measure_issue_peak(int iters, double* lane_ops_per_second) {
     return FB_OK;
 }
 
+int fb_play_kernel_ms_history(float* out_ms, int max_entries) {
+    if (!out_ms || max_entries < 0) return fail(FB_ERR_BAD_ARG, "bad history buffer");
+    const int n = (int)std::min<uint64_t>({(uint64_t)max_entries, t_ev_count, (uint64_t)EV_RING});
+    for (int i = 0; i < n; i++) {  // most recent first
+        cudaEvent_t* ev = t_ev[(t_ev_count - 1 - (uint64_t)i) % EV_RING];
+        FB_CUDA(cudaEventSynchronize(ev[1]));
+        FB_CUDA(cudaEventElapsedTime(&out_ms[i], ev[0], ev[1]));
+    }
+    return n;
+}
+
 float fb_last_play_kernel_ms(void) {
-    if (!t_ev_valid) return -1.0f;
-    if (cudaEventSynchronize(t_ev1) != cudaSuccess) return -1.0f;
     float ms = -1.0f;
-    if (cudaEventElapsedTime(&ms, t_ev0, t_ev1) != cudaSuccess) return -1.0f;
-    return ms;
+    return fb_play_kernel_ms_history(&ms, 1) == 1 ? ms : -1.0f;
 }
 
 }  // extern "C"

@@ -107,6 +107,14 @@ class Engine:
     def last_play_kernel_ms(self) -> float:
         return float(self.lib.fb_last_play_kernel_ms())
 
+    def play_kernel_ms_history(self, n: int) -> list[float]:
+        """CUDA-event durations of the last ``n`` play_kernel launches of this thread, newest first."""
+        buf = (C.c_float * max(n, 1))()
+        got = self.lib.fb_play_kernel_ms_history(buf, n)
+        if got < 0:
+            _native.check(got)
+        return [float(buf[i]) for i in range(got)]
+
     def measure_issue_peak(self, iters: int = 20000) -> float:
         """Measured 32-bit integer lane-instructions per second (roofline denominator)."""
         out = C.c_double()

@@ -296,6 +296,10 @@ int fb_run_tournament_host(uint64_t root_seed, int k, uint64_t shuffle0, int n_s
  * this thread took, measured with CUDA events on the launching stream.  Blocks
  * until that kernel has finished.  Returns < 0 if nothing was launched.      */
 float fb_last_play_kernel_ms(void);
+/* The same for the most recent launches of this thread, newest first: fills out_ms with up
+ * to max_entries durations (the library keeps the last 64) and returns how many were
+ * written (negative fb_status on error).  Blocks until those kernels have finished.      */
+int fb_play_kernel_ms_history(float* out_ms, int max_entries);
 /* Roofline probe: runs a register-only kernel of independent 32-bit integer
  * mad / xor / add chains on every SM (1,024 threads per SM, `iters` iterations of
  * 32 lane instructions each, half on the FMA pipe and half on the ALU pipe) and
