@@ -23,7 +23,7 @@ from typing import Any, Mapping, Sequence
 
 import numpy as np
 
-from .game_profile import GameProfile
+from .limits import GameProfile
 from .layout import ROW_I16_OVERFLOW, ROW_ROLL_LIMIT
 from .random import RandomPurpose
 from .simulation import PlayerRngCoordinates, RollLimitError, play_games_batch

@@ -23,7 +23,7 @@ from pathlib import Path
 from typing import Any, Sequence
 
 from . import run_tournament as gpu_rt
-from .game_profile import GameProfile, H2HMaxRoundsOverride, TournamentMaxRoundsOverride
+from .limits import GameProfile, H2HMaxRoundsOverride, TournamentMaxRoundsOverride
 from .strategies import FavorDiceOrScore, ThresholdStrategy
 
 _SEAMS = ("_init_worker", "_play_one_shuffle", "_play_shuffle", "_run_chunk", "_run_chunk_metrics")

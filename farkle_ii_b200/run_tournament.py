@@ -34,7 +34,7 @@ from typing import Any, Callable, Dict, Iterator, List, Mapping, Sequence, Tuple
 
 import numpy as np
 
-from .game_profile import GameProfile
+from .limits import GameProfile
 from .layout import N_METRICS, T_ATTEMPTED, T_COMPLETED, T_SAFETY, T_SQ_SUMS, T_SUMS, T_WINS, TALLY_WIDTH
 from .random import RNG_SCHEME_VERSION, RandomPurpose, coordinate_seed
 from .simulation import (

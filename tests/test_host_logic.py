@@ -142,7 +142,7 @@ def test_no_cpu_fallback():
 def test_workload_planner_kats():
     """The reference's own planner KATs (tests/unit/simulation/test_workload_planner.py:18-60) and
     the grid sizes bench.py uses."""
-    from farkle_ii_b200.workload_planner import (minimum_shuffles_for_resolution,
+    from farkle_ii_b200.shuffle_plan import (minimum_shuffles_for_resolution,
                                                  plan_tournament_workload, worst_case_wilson_width)
 
     plan = plan_tournament_workload(root_seed=17, k=4, strategy_count=200, resolution_delta=0.03)

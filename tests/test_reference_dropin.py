@@ -172,3 +172,53 @@ def test_seat_count_semantics_match_reference_seat_analysis(ref_rt, tmp_path):
             [r["raw_wins"], r["raw_exposures"], r["raw_completed_exposures"], r["raw_safety_limit_exposures"]]
             for r in ref_tbl}
     assert frt.seat_counts_from_rows(rows, batch) == want
+
+
+def test_plan_and_limits_match_reference_modules(ref_rt):
+    """`shuffle_plan` / `limits` against the reference's `workload_planner` / `game_profile`:
+    every float of the plan bit-identical, same identity hash, same rejections."""
+    import itertools
+
+    from farkle.simulation import game_profile as ref_gp
+    from farkle.simulation import workload_planner as ref_wp
+
+    from farkle_ii_b200 import limits, shuffle_plan
+
+    for n, c in itertools.product([*range(1, 120), 4264, 4265, 4300, 1_234_567], (0.8, 0.95, 0.99)):
+        assert shuffle_plan.worst_case_wilson_width(n, confidence=c) == \
+            ref_wp.worst_case_wilson_width(n, confidence=c)
+    for d, c in itertools.product((0.9, 0.2, 0.08, 0.03, 0.01), (0.9, 0.95, 0.999)):
+        assert shuffle_plan.minimum_shuffles_for_resolution(d, confidence=c) == \
+            ref_wp.minimum_shuffles_for_resolution(d, confidence=c)
+    for k, sc, d, bc, cap in itertools.product((2, 6), (12, 5160), (0.03, 0.3), (2, 100),
+                                               (None, 50)):
+        kw = dict(root_seed=5, k=k, strategy_count=sc, resolution_delta=d, batch_count=bc,
+                  shuffle_cap=cap, projected_games_per_second=4e8)
+        mine, ref = shuffle_plan.plan_tournament_workload(**kw), ref_wp.plan_tournament_workload(**kw)
+        assert mine.to_dict() == ref.to_dict()
+        assert str(shuffle_plan.WorkloadCapExceeded(mine)) == str(ref_wp.WorkloadCapExceeded(ref))
+
+    def profile(mod):
+        return mod.GameProfile(
+            default_target_score=500, default_max_rounds=7,
+            tournament_max_rounds_overrides=(mod.TournamentMaxRoundsOverride(3, 2, 1, 0, 5),
+                                             mod.TournamentMaxRoundsOverride(1, 2, 1, 0, 0)),
+            h2h_max_rounds_overrides=(mod.H2HMaxRoundsOverride(1, 2, 1, 3, 4),))
+
+    mine, ref = profile(limits), profile(ref_gp)
+    assert mine.sha256 == ref.sha256 and mine.canonical_payload() == ref.canonical_payload()
+    assert limits.GameProfile().sha256 == ref_gp.GameProfile().sha256
+    for coord in ((3, 2, 1, 0), (1, 2, 1, 0), (1, 2, 1, 1)):
+        kw = dict(zip(("root_seed", "k", "shuffle_index", "game_index"), coord))
+        a, b = mine.tournament_limits(**kw), ref.tournament_limits(**kw)
+        assert (a.target_score, a.max_rounds) == (b.target_score, b.max_rounds)
+    a = mine.h2h_limits(root_seed=1, pair_id=2, order=1, attempt_index=3)
+    b = ref.h2h_limits(root_seed=1, pair_id=2, order=1, attempt_index=3)
+    assert (a.target_score, a.max_rounds) == (b.target_score, b.max_rounds) == (500, 4)
+    for bad in ((1, 1, 0, 0, 5), (-1, 2, 0, 0, 5), (1, 2, 0, 0, -5), (1, 2, True, 0, 5)):
+        msgs = []
+        for mod in (limits, ref_gp):
+            with pytest.raises(ValueError) as err:
+                mod.TournamentMaxRoundsOverride(*bad)
+            msgs.append(str(err.value))
+        assert msgs[0] == msgs[1]
