@@ -1104,14 +1104,31 @@ int fb_run_tournament_host(uint64_t root_seed, int k, uint64_t shuffle0, int n_s
     const uint64_t gps = (uint64_t)(n_strategies / k);
     const int n_slots = shuffles_per_slot > 0 ? (n_shuffles + shuffles_per_slot - 1) / shuffles_per_slot : 1;
     // Rows mode streams the rows to the host while the next part of the range is being played:
-    // the range is cut into up to four chunks (whole tally slots), two device row buffers
-    // alternate, and the D2H copy of chunk i runs on a second stream under the kernels of i+1.
-    int chunk = n_shuffles;
+    // the range is cut into four chunks of whole tally slots, two device row buffers alternate,
+    // and the D2H copy of chunk i runs on a second stream under the kernels of i+1.  The chunks
+    // shrink (44/30/18/8 %): the copy of the last one is the only part nothing overlaps, while
+    // every extra launch costs a kernel start-up and tail, so few launches and a small last one.
+    // FB_ROW_CHUNKS=n (1..64) forces n equal chunks instead.
+    std::vector<int> starts{0};
     if (rows_host && (uint64_t)n_shuffles * gps >= (1u << 20)) {
-        chunk = (n_shuffles + 3) / 4;
-        if (shuffles_per_slot > 0) chunk = (chunk + shuffles_per_slot - 1) / shuffles_per_slot * shuffles_per_slot;
+        const int unit = shuffles_per_slot > 0 ? shuffles_per_slot : 1;
+        auto cut = [&](double frac) {  // chunk boundary at frac of the range, on a slot boundary
+            int at = (int)((double)n_shuffles * frac / unit + 0.5) * unit;
+            if (at > starts.back() && at < n_shuffles) starts.push_back(at);
+        };
+        if (const char* e = getenv("FB_ROW_CHUNKS")) {
+            const int parts = std::max(1, std::min(64, atoi(e)));
+            for (int i = 1; i < parts; i++) cut((double)i / parts);
+        } else {
+            cut(0.44);
+            cut(0.74);
+            cut(0.92);
+        }
     }
-    const int n_chunks = (n_shuffles + chunk - 1) / chunk;
+    starts.push_back(n_shuffles);
+    const int n_chunks = (int)starts.size() - 1;
+    int chunk = 0;  // the largest chunk sizes the buffers
+    for (int c = 0; c < n_chunks; c++) chunk = std::max(chunk, starts[c + 1] - starts[c]);
     const uint64_t chunk_games = (uint64_t)chunk * gps;
     const size_t stride = fb_row_stride(k);
     const size_t strat_b = align_up((size_t)n_strategies * sizeof(fb_strategy_t), 256);
@@ -1154,7 +1171,7 @@ int fb_run_tournament_host(uint64_t root_seed, int k, uint64_t shuffle0, int n_s
     FB_CUDA(cudaMemsetAsync(d_tally, 0, tally_b, stream));
     FB_CUDA(cudaMemsetAsync(d_totals, 0, totals_b, stream));
     for (int c = 0; c < n_chunks; c++) {
-        const int s0 = c * chunk, cnt = std::min(chunk, n_shuffles - s0);
+        const int s0 = starts[c], cnt = starts[c + 1] - s0;
         const int b = c & 1;
         if (c >= 2) FB_CUDA(cudaStreamWaitEvent(stream, g_ctx.ev_copied[b], 0));  // row buffer b is free again
         int64_t* tally_c = nullptr;
