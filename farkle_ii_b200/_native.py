@@ -28,7 +28,7 @@ SYMBOLS = (
     "fb_abi_version", "fb_last_error", "fb_init", "fb_device_info", "fb_row_stride",
     "fb_workspace_bytes", "fb_seedseq_generate", "fb_coordinate_seeds", "fb_seed_streams",
     "fb_roll_dice", "fb_default_score", "fb_permute_shuffles", "fb_play_tournament",
-    "fb_play_tournament_seats",
+    "fb_play_tournament_seats", "fb_play_tournament_lags",
     "fb_play_h2h", "fb_h2h_resolve", "fb_play_games", "fb_run_tournament_host",
     "fb_measure_issue_peak", "fb_last_play_kernel_ms", "fb_play_kernel_ms_history",
     "fb_kernel_launch_count",
@@ -93,6 +93,9 @@ def _declare(L: C.CDLL) -> None:
     L.fb_play_tournament_seats.argtypes = [_u64, _int, _u64, _int, _vp, _vp, _int, _int, _i32, _i32,
                                            _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _int, _vp, _vp,
                                            _sz, _vp]
+    L.fb_play_tournament_lags.argtypes = [_u64, _int, _u64, _int, _vp, _vp, _int, _int, _i32, _i32,
+                                          _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _int, _vp, _vp,
+                                          _int, _vp, _vp, _vp, _sz, _vp]
     L.fb_play_h2h.argtypes = [_u64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _i32, _i32, _vp,
                               _vp, _vp, _vp, _sz, _vp]
     L.fb_h2h_resolve.argtypes = [_int, _vp, _vp, _vp, _vp, _vp]

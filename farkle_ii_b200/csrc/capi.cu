@@ -853,9 +853,25 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
                                 const int32_t* override_max_rounds_dev, int n_overrides, int shuffles_per_slot,
                                 int64_t* tallies_dev, int64_t* totals_dev, void* rows_dev, int want_game_seeds,
                                 void* workspace_dev, size_t workspace_bytes, void* stream_v,
-                                uint32_t ordinal_base, int64_t* seat_tallies_dev = nullptr) {
+                                uint32_t ordinal_base, int64_t* seat_tallies_dev = nullptr,
+                                const int32_t* lags_host = nullptr, int n_lags = 0,
+                                int64_t* lag_stats_dev = nullptr, uint32_t* lag_edges_dev = nullptr) {
     FB_REQUIRE_INIT();
     if (seat_tallies_dev && !tallies_dev) return fail(FB_ERR_BAD_ARG, "seat tallies need tallies_dev");
+    LagParams L{};
+    if (n_lags != 0) {
+        if (n_lags < 0 || n_lags > FB_MAX_LAGS || !lags_host || !lag_stats_dev || !lag_edges_dev || !tallies_dev)
+            return fail(FB_ERR_BAD_ARG, "lag statistics need 1..%d lags, both lag buffers and tallies_dev", FB_MAX_LAGS);
+        for (int z = 0; z < n_lags; z++) {
+            if (lags_host[z] < 1 || lags_host[z] > FB_MAX_LAG)
+                return fail(FB_ERR_BAD_ARG, "lag %d outside [1,%d]", lags_host[z], FB_MAX_LAG);
+            for (int y = 0; y < z; y++)
+                if (lags_host[y] == lags_host[z]) return fail(FB_ERR_BAD_ARG, "duplicate lag %d", lags_host[z]);
+            L.lags[z] = lags_host[z];
+            L.max_lag = std::max(L.max_lag, lags_host[z]);
+        }
+        L.n_lags = n_lags;
+    }
     cudaStream_t stream = (cudaStream_t)stream_v;
     if (k < 1 || k > FB_MAX_PLAYERS) return fail(FB_ERR_BAD_ARG, "k=%d outside [1,%d]", k, FB_MAX_PLAYERS);
     if (n_strategies < k || n_strategies % k != 0)
@@ -937,7 +953,24 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
     G.seat_tallies = reinterpret_cast<unsigned long long*>(seat_tallies_dev);
     const int n_chunks = (n_shuffles + G.chunk - 1) / G.chunk;
     tally_gather_kernel<<<dim3(blocks_for((uint64_t)n_strategies, 128), (unsigned)n_chunks), 128, 0, stream>>>(G);
-    return launch_check("tally_gather_kernel");
+    rc = launch_check("tally_gather_kernel");
+    if (rc || !L.n_lags) return rc;
+    L.header = w.header;
+    L.inv = inv;
+    L.n_strategies = n_strategies;
+    L.n_shuffles = n_shuffles;
+    L.k = k;
+    L.gps = gps;
+    L.chunk = 43;
+    L.stats = reinterpret_cast<unsigned long long*>(lag_stats_dev);
+    L.edges = lag_edges_dev;
+    const unsigned sblocks = blocks_for((uint64_t)n_strategies, 128);
+    lag_gather_kernel<<<dim3(sblocks, (unsigned)((n_shuffles + L.chunk - 1) / L.chunk), (unsigned)L.n_lags), 128, 0,
+                        stream>>>(L);
+    rc = launch_check("lag_gather_kernel");
+    if (rc) return rc;
+    lag_edges_kernel<<<dim3(sblocks, (unsigned)std::min(L.max_lag, n_shuffles)), 128, 0, stream>>>(L);
+    return launch_check("lag_edges_kernel");
 }
 
 int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
@@ -966,6 +999,22 @@ int fb_play_tournament_seats(uint64_t root_seed, int k, uint64_t shuffle0, int n
                                 override_max_rounds_dev, n_overrides, shuffles_per_slot, tallies_dev, totals_dev,
                                 rows_dev, want_game_seeds, workspace_dev, workspace_bytes, stream_v, 0u,
                                 seat_tallies_dev);
+}
+
+int fb_play_tournament_lags(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
+                            const fb_strategy_t* strategies_dev, const int32_t* strategy_ids_dev,
+                            int n_strategies, int n_tally_ids, int32_t target_score, int32_t max_rounds,
+                            const uint64_t* override_shuffle_dev, const uint32_t* override_game_dev,
+                            const int32_t* override_max_rounds_dev, int n_overrides, int shuffles_per_slot,
+                            int64_t* tallies_dev, int64_t* totals_dev, void* rows_dev, int want_game_seeds,
+                            int64_t* seat_tallies_dev, const int32_t* lags_host, int n_lags,
+                            int64_t* lag_stats_dev, uint32_t* lag_edges_dev, void* workspace_dev,
+                            size_t workspace_bytes, void* stream_v) {
+    return play_tournament_impl(root_seed, k, shuffle0, n_shuffles, strategies_dev, strategy_ids_dev, n_strategies,
+                                n_tally_ids, target_score, max_rounds, override_shuffle_dev, override_game_dev,
+                                override_max_rounds_dev, n_overrides, shuffles_per_slot, tallies_dev, totals_dev,
+                                rows_dev, want_game_seeds, workspace_dev, workspace_bytes, stream_v, 0u,
+                                seat_tallies_dev, lags_host, n_lags, lag_stats_dev, lag_edges_dev);
 }
 
 int fb_play_h2h(uint64_t root_seed, int n_blocks, const uint64_t* pair_id_dev, const uint8_t* order_dev,

@@ -684,4 +684,79 @@ __global__ void __launch_bounds__(128) tally_gather_kernel(const GatherParams G)
     }
 }
 
+// ---------------------------------------------------------------------------
+// RNG lag diagnostics, strategy groups (analysis/rng_diagnostics.py:2032-2077,1870-1901)
+// ---------------------------------------------------------------------------
+// The reference sorts every seat exposure of a (strategy, k) group by its RNG coordinate
+// (root, k, shuffle, game, seat) and feeds win indicator and n_rounds to an online lagged-pair
+// accumulator.  A strategy is seated exactly once per shuffle, so inside one (root, k) cell its
+// sequence is simply "its game of shuffle 0, 1, 2, ...": observation j of strategy i is found
+// through the inverse permutation, like the winner tallies.  All six sums are small integers, so
+// int64 accumulation equals the reference's float64 accumulation exactly.
+struct LagParams {
+    const uint32_t* header;  // rounds | flags << 16 | (winner seat + 1) << 24
+    const int32_t* inv;      // [n_shuffles][n_strategies]
+    int n_strategies, n_shuffles, k;
+    uint32_t gps;
+    int chunk;  // shuffles per thread
+    int n_lags, max_lag;
+    int lags[FB_MAX_LAGS];
+    unsigned long long* stats;  // [n_strategies][n_lags][FB_LAG_WIDTH], accumulated into
+    uint32_t* edges;            // [n_strategies][2][max_lag]: first / last observations of the launch
+};
+
+// observation j of strategy i: n_rounds | win << 16
+__device__ __forceinline__ uint32_t lag_observation(const LagParams& L, int i, int j) {
+    const uint32_t pos = (uint32_t)L.inv[(size_t)j * L.n_strategies + i];
+    const uint32_t gi = pos / (uint32_t)L.k, seat = pos - gi * (uint32_t)L.k;
+    const uint32_t hdr = __ldg(&L.header[(uint32_t)j * L.gps + gi]);
+    const bool won = !((hdr >> 16) & FB_ROW_SAFETY_LIMIT) && ((hdr >> 24) & 15u) == seat + 1u;
+    return (hdr & 0xffffu) | (won ? 0x10000u : 0u);
+}
+
+// thread (strategy i, chunk c of the shuffles, lag z): the pairs (j - lag, j) with j in the chunk
+__global__ void __launch_bounds__(128) lag_gather_kernel(const LagParams L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.n_strategies) return;
+    const int lag = L.lags[blockIdx.z];
+    const int j0 = max(blockIdx.y * L.chunk, lag), j1 = min((blockIdx.y + 1) * L.chunk, L.n_shuffles);
+    if (j0 >= j1) return;
+    unsigned long long wx = 0, wy = 0, wxy = 0, rx = 0, ry = 0, rx2 = 0, ry2 = 0, rxy = 0;
+    for (int j = j0; j < j1; j++) {
+        const uint32_t x = lag_observation(L, i, j - lag), y = lag_observation(L, i, j);
+        const unsigned long long xr = x & 0xffffu, yr = y & 0xffffu;
+        const uint32_t xw = x >> 16, yw = y >> 16;
+        wx += xw;
+        wy += yw;
+        wxy += xw & yw;
+        rx += xr;
+        ry += yr;
+        rx2 += xr * xr;
+        ry2 += yr * yr;
+        rxy += xr * yr;
+    }
+    unsigned long long* S = L.stats + ((size_t)i * L.n_lags + blockIdx.z) * FB_LAG_WIDTH;
+    atomicAdd(&S[0], (unsigned long long)(j1 - j0));
+    if (wx) { atomicAdd(&S[1], wx); atomicAdd(&S[3], wx); }  // x^2 == x for an indicator
+    if (wy) { atomicAdd(&S[2], wy); atomicAdd(&S[4], wy); }
+    if (wxy) atomicAdd(&S[5], wxy);
+    atomicAdd(&S[6], rx);
+    atomicAdd(&S[7], ry);
+    atomicAdd(&S[8], rx2);
+    atomicAdd(&S[9], ry2);
+    atomicAdd(&S[10], rxy);
+}
+
+// The first and last min(max_lag, n_shuffles) observations of every strategy: what a caller needs
+// to add the pairs that straddle two launches of one cell (batches, ranks).
+__global__ void lag_edges_kernel(const LagParams L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y;
+    const int cnt = min(L.max_lag, L.n_shuffles);
+    if (i >= L.n_strategies || m >= cnt) return;
+    uint32_t* E = L.edges + (size_t)i * 2 * L.max_lag;
+    E[m] = lag_observation(L, i, m);
+    E[L.max_lag + m] = lag_observation(L, i, L.n_shuffles - cnt + m);
+}
+
 }  // namespace fb

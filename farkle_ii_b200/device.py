@@ -16,6 +16,7 @@ import torch
 
 from . import _native
 from .layout import (
+    LAG_WIDTH,
     SEAT_TALLY_WIDTH,
     STRATEGY_DTYPE,
     TALLY_WIDTH,
@@ -58,6 +59,8 @@ class TournamentResult:
     n_games: int
     k: int
     seat_tallies: torch.Tensor | None = None  # int64 [slots, ids, k, 4]
+    lag_stats: torch.Tensor | None = None     # int64 [n_strategies, n_lags, LAG_WIDTH]
+    lag_edges: torch.Tensor | None = None     # int32 [n_strategies, 2, max_lag]: n_rounds | win << 16
 
     def rows_numpy(self) -> np.ndarray:
         assert self.rows is not None
@@ -224,8 +227,13 @@ class Engine:
                         want_tallies: bool = True, want_rows: bool = False,
                         want_game_seeds: bool = False, tallies: torch.Tensor | None = None,
                         totals: torch.Tensor | None = None, want_seat_tallies: bool = False,
-                        seat_tallies: torch.Tensor | None = None) -> TournamentResult:
+                        seat_tallies: torch.Tensor | None = None,
+                        lags: tuple[int, ...] = ()) -> TournamentResult:
         """Enqueue shuffles ``shuffle0 .. shuffle0+n_shuffles-1`` of cell (root_seed, k).
+
+        ``lags`` asks for the RNG lag statistics of the strategy groups (``lag_stats``
+        int64 [n_strategies, n_lags, LAG_WIDTH] by table position, ``lag_edges`` uint32
+        [n_strategies, 2, max(lags)]); see ``farkle_ii_b200.rng_diagnostics``.
 
         ``strategies`` is a device uint8 tensor holding ``fb_strategy_t`` entries, or a
         host STRATEGY_DTYPE array (copied).  ``tallies`` / ``totals`` may be passed to
@@ -266,12 +274,21 @@ class Engine:
             d_om = self.to_device(np.array([o[2] for o in ov], dtype=np.int32))
         ws_bytes = self.workspace_bytes(max(k, 1), n_games) + 2 * (n_shuffles * n_strategies * 4 + 256)
         ws = self.workspace(ws_bytes)
-        _native.check(self.lib.fb_play_tournament_seats(
+        lag_stats = lag_edges = None
+        lags_c = (C.c_int32 * max(len(lags), 1))(*[int(v) for v in lags])
+        if lags:
+            lag_stats = torch.zeros((n_strategies, len(lags), LAG_WIDTH), dtype=torch.int64,
+                                    device=self.device)
+            lag_edges = torch.zeros((n_strategies, 2, max(int(v) for v in lags)), dtype=torch.int32,
+                                    device=self.device)
+        _native.check(self.lib.fb_play_tournament_lags(
             root_seed, k, shuffle0, n_shuffles, _ptr(strategies), _ptr(d_ids), n_strategies,
             n_tally_ids, target_score, max_rounds, _ptr(d_os), _ptr(d_og), _ptr(d_om), len(ov),
             shuffles_per_slot, _ptr(tallies if want_tallies else None), _ptr(totals), _ptr(rows),
-            int(want_game_seeds), _ptr(seat_tallies), _ptr(ws), ws.numel(), self._stream()))
-        return TournamentResult(tallies if want_tallies else None, totals, rows, n_games, k, seat_tallies)
+            int(want_game_seeds), _ptr(seat_tallies), C.cast(lags_c, C.c_void_p), len(lags),
+            _ptr(lag_stats), _ptr(lag_edges), _ptr(ws), ws.numel(), self._stream()))
+        return TournamentResult(tallies if want_tallies else None, totals, rows, n_games, k, seat_tallies,
+                                lag_stats, lag_edges)
 
     def play_games(self, coords: np.ndarray, k: int, seat_strategies: np.ndarray, *,
                    seat_strategy_ids=None, target_score: int = 10_000, max_rounds: int = 200,

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FB_ABI_VERSION 2
+#define FB_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------- */
 enum fb_status {
@@ -124,6 +124,22 @@ typedef struct fb_row_seat {
  *   0 raw_wins  1 raw_exposures  2 raw_completed_exposures
  *   3 raw_safety_limit_exposures        of strategy id x 0-based seat.        */
 #define FB_SEAT_TALLY_WIDTH 4
+
+/* Optional RNG lag statistics of the strategy groups (replaces the external sort + online
+ * accumulator of src/farkle/analysis/rng_diagnostics.py:2032-2077 for "strategy" groups):
+ * int64[n_strategies][n_lags][FB_LAG_WIDTH], indexed by TABLE position (not strategy id).
+ * The sequence of table entry i is its seat exposure in shuffle shuffle0, shuffle0+1, ... (the
+ * reference's order by (root_seed, k, shuffle_index, game_index, seat_index): a strategy is
+ * seated once per shuffle); x is the observation `lag` places earlier, y the current one.
+ *   0       lagged pairs
+ *   1..5    win indicator: sum x, sum y, sum x^2, sum y^2, sum x*y
+ *   6..10   n_rounds:      sum x, sum y, sum x^2, sum y^2, sum x*y
+ * Edges, uint32[n_strategies][2][max_lag] with max_lag = the largest lag: the first and the last
+ * min(max_lag, n_shuffles) observations of the launch, each n_rounds | win << 16, so that the
+ * pairs straddling two launches of one cell can be added by the caller.           */
+#define FB_LAG_WIDTH 11
+#define FB_MAX_LAGS 8
+#define FB_MAX_LAG 4096
 
 /* Per-launch totals, int64[FB_TOTALS_WIDTH]:
  *   0 games_attempted  1 games_completed  2 games_safety_limit
@@ -237,6 +253,22 @@ int fb_play_tournament_seats(uint64_t root_seed, int k, uint64_t shuffle0, int n
                              int shuffles_per_slot, int64_t* tallies_dev, int64_t* totals_dev,
                              void* rows_dev, int want_game_seeds, int64_t* seat_tallies_dev,
                              void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* fb_play_tournament_seats plus the RNG lag statistics of the strategy groups (layout above).
+ * lags_host: n_lags (1..FB_MAX_LAGS) distinct lags in [1, FB_MAX_LAG], HOST array.
+ * lag_stats_dev is accumulated into (caller zeroes); lag_edges_dev is overwritten; both required
+ * when n_lags > 0.  Needs tallies_dev (the winner marks and inverse permutations come with it). */
+int fb_play_tournament_lags(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
+                            const fb_strategy_t* strategies_dev, const int32_t* strategy_ids_dev,
+                            int n_strategies, int n_tally_ids, int32_t target_score,
+                            int32_t max_rounds, const uint64_t* override_shuffle_dev,
+                            const uint32_t* override_game_dev,
+                            const int32_t* override_max_rounds_dev, int n_overrides,
+                            int shuffles_per_slot, int64_t* tallies_dev, int64_t* totals_dev,
+                            void* rows_dev, int want_game_seeds, int64_t* seat_tallies_dev,
+                            const int32_t* lags_host, int n_lags, int64_t* lag_stats_dev,
+                            uint32_t* lag_edges_dev, void* workspace_dev, size_t workspace_bytes,
+                            void* stream);
 
 /* Head-to-head attempts.  Replaces the attempt loop of
  * _simulate_block_from_manifest (src/farkle/analysis/h2h_schedule.py:1149-1243)

@@ -25,6 +25,9 @@ class _Result:
     rows: torch.Tensor | None
     n_games: int
     k: int
+    seat_tallies: torch.Tensor | None = None
+    lag_stats: torch.Tensor | None = None
+    lag_edges: torch.Tensor | None = None
 
     def rows_numpy(self) -> np.ndarray:
         return self.rows.numpy().view(row_dtype(self.k)).reshape(-1)
@@ -45,7 +48,10 @@ class OracleEngine:
     def play_tournament(self, root_seed, k, shuffle0, n_shuffles, strategies, *, strategy_ids=None,
                         n_tally_ids=None, target_score=10_000, max_rounds=200, overrides=(),
                         shuffles_per_slot=0, want_tallies=True, want_rows=False,
-                        want_game_seeds=False, tallies=None, totals=None):
+                        want_game_seeds=False, tallies=None, totals=None, lags=()):
+        if lags:
+            return self._with_lags(root_seed, k, shuffle0, n_shuffles, strategies, target_score, max_rounds,
+                                   tuple(lags))
         t, tot, rows = oracle.play_tournament(
             root_seed, k, shuffle0, n_shuffles, _table(strategies), strategy_ids=strategy_ids,
             n_tally_ids=n_tally_ids, target_score=target_score, max_rounds=max_rounds,
@@ -60,6 +66,35 @@ class OracleEngine:
             to = totals
         r = None if rows is None else torch.from_numpy(rows.view(np.uint8).reshape(len(rows), -1))
         return _Result(tt if want_tallies else None, to, r, len(rows) if rows is not None else 0, k)
+
+    def _with_lags(self, root_seed, k, shuffle0, n_shuffles, strategies, target_score, max_rounds, lags):
+        """Lag sums the slow way: one accumulator walk per strategy over the oracle's rows."""
+        table = _table(strategies)
+        t, tot, rows = oracle.play_tournament(root_seed, k, shuffle0, n_shuffles, table,
+                                              target_score=target_score, max_rounds=max_rounds,
+                                              want_rows=True, n_threads=2)
+        n, gps = len(table), len(table) // k
+        seq = [[None] * n_shuffles for _ in range(n)]           # (win, rounds) per strategy and shuffle
+        for g, row in enumerate(rows):
+            safety = bool(row["flags"] & 1)
+            for s in range(k):
+                win = int((not safety) and int(row["winner_seat"]) == s)
+                seq[int(row["seats"]["strategy"][s])][g // gps] = (win, int(row["n_rounds"]))
+        stats = np.zeros((n, len(lags), 11), dtype=np.int64)
+        max_lag = max(lags)
+        edges = np.zeros((n, 2, max_lag), dtype=np.uint32)
+        cnt = min(max_lag, n_shuffles)
+        for i in range(n):
+            for z, lag in enumerate(lags):
+                for j in range(lag, n_shuffles):
+                    (xw, xr), (yw, yr) = seq[i][j - lag], seq[i][j]
+                    stats[i, z] += [1, xw, yw, xw * xw, yw * yw, xw * yw, xr, yr, xr * xr, yr * yr, xr * yr]
+            for m in range(cnt):
+                edges[i, 0, m] = seq[i][m][1] | seq[i][m][0] << 16
+                last = seq[i][n_shuffles - cnt + m]
+                edges[i, 1, m] = last[1] | last[0] << 16
+        return _Result(torch.from_numpy(t), torch.from_numpy(tot), None, len(rows), k, None,
+                       torch.from_numpy(stats), torch.from_numpy(edges.view(np.int32)))
 
     def play_games(self, coords, k, seat_strategies, **kw):
         return oracle.play_games(coords, k, seat_strategies, **kw)

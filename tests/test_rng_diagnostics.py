@@ -1,0 +1,191 @@
+"""RNG lag diagnostics of the strategy groups.
+
+CPU: the host algebra (joining launches, the report rows) against brute force and -- where the
+reference checkout exists -- against the reference's own ``_OnlineMetric`` / ``_rows_for_online_group``.
+GPU: ``lag_gather_kernel`` / ``lag_edges_kernel`` against the same brute force over the oracle's rows.
+"""
+
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle as fo
+from farkle_ii_b200 import rng_diagnostics as rd
+from farkle_ii_b200.layout import LAG_WIDTH
+from oracle_engine import OracleEngine
+
+GOLDEN = Path(__file__).parent / "golden"
+REF = Path("/root/reference/src")
+
+
+def _random_obs(rng, n, m, max_rounds=200):
+    return (rng.integers(1, max_rounds + 1, size=(n, m)).astype(np.uint32)
+            | (rng.integers(0, 2, size=(n, m)).astype(np.uint32) << 16))
+
+
+def _online(seq, lags):
+    """The accumulator as the reference describes it, value by value (floats, ring buffer)."""
+    ring = [0.0] * max(lags)
+    acc = {lag: [0, 0.0, 0.0, 0.0, 0.0, 0.0] for lag in lags}
+    for n_obs, value in enumerate(seq):
+        for lag in lags:
+            if n_obs >= lag:
+                earlier = ring[(n_obs - lag) % len(ring)]
+                a = acc[lag]
+                a[0] += 1
+                a[1] += earlier
+                a[2] += value
+                a[3] += earlier * earlier
+                a[4] += value * value
+                a[5] += earlier * value
+        ring[n_obs % len(ring)] = float(value)
+    return acc
+
+
+@pytest.mark.parametrize("lags", [(1,), (1, 2, 5), (3, 7)])
+def test_state_matches_online_accumulator_and_joins(lags):
+    rng = np.random.default_rng(5)
+    obs = _random_obs(rng, 7, 40)
+    whole = rd.StrategyLagState.from_observations(lags, obs)
+    for i in range(obs.shape[0]):
+        wins = _online([float(v >> 16) for v in obs[i]], lags)
+        rounds = _online([float(v & 0xFFFF) for v in obs[i]], lags)
+        for z, lag in enumerate(lags):
+            assert whole.stats[i, z, 0] == wins[lag][0] == rounds[lag][0]
+            assert whole.stats[i, z, 1:6].tolist() == wins[lag][1:]
+            assert whole.stats[i, z, 6:11].tolist() == rounds[lag][1:]
+    # any way of cutting the run into launches joins back to the same state, short pieces included
+    for cuts in ([13], [1, 2, 3], [5, 6, 8, 9, 31], [39], list(range(1, 40))):
+        bounds = [0, *cuts, obs.shape[1]]
+        state = rd.StrategyLagState.empty(obs.shape[0], lags)
+        for a, b in zip(bounds, bounds[1:]):
+            state = state.extend(rd.StrategyLagState.from_observations(lags, obs[:, a:b]))
+        assert state.n_obs == whole.n_obs
+        assert np.array_equal(state.stats, whole.stats)
+        assert np.array_equal(state.head, whole.head) and np.array_equal(state.tail, whole.tail)
+
+
+def test_rows_shape_and_statuses():
+    lags = (1, 3)
+    obs = np.full((2, 6), 10, dtype=np.uint32)              # constant n_rounds, never a win
+    obs[1] = [5 | 1 << 16, 7, 9 | 1 << 16, 4, 12, 6 | 1 << 16]
+    state = rd.StrategyLagState.from_observations(lags, obs)
+    rows = state.rows([40, 41], 3)
+    assert len(rows) == 2 * 2 * 2
+    assert [r["metric"] for r in rows[:4]] == ["win_indicator", "win_indicator", "n_rounds", "n_rounds"]
+    assert {r["estimability_status"] for r in rows[:4]} == {"zero_variance"}
+    assert all(r["autocorr"] is None for r in rows[:4])
+    assert rows[4]["strategy"] == 41 and rows[4]["observations"] == 6 and rows[4]["lagged_pairs"] == 5
+    assert rows[4]["estimability_status"] == "estimated" and -1.0 <= rows[4]["autocorr"] <= 1.0
+    assert rows[5]["lagged_pairs"] == 3
+    assert rows[4]["zero_centered_descriptive_reference_band_upper"] == 1.96 / 5**0.5
+    assert rd.StrategyLagState.from_observations((4,), obs[:, :5]).rows([0, 1], 2) == []   # < lag + 2
+    short = rd.StrategyLagState.from_observations((4,), obs)                                # 2 pairs
+    assert short.rows([0, 1], 2)[0]["lagged_pairs"] == 2
+    assert rd.normalize_lags(None) == (1,) and rd.normalize_lags([5, 1, 5, 0, -2]) == (1, 5)
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference checkout not present on this box")
+def test_rows_equal_reference_rows(monkeypatch):
+    monkeypatch.syspath_prepend(str(REF))
+    import farkle.analysis.rng_diagnostics as ref
+
+    try:
+        lags = (1, 2, 6)
+        rng = np.random.default_rng(11)
+        obs = _random_obs(rng, 5, 57)
+        obs[3] = 20                                           # a zero-variance group
+        mine = rd.StrategyLagState.from_observations(lags, obs).rows([9, 4, 7, 1, 3], 4)
+        want = []
+        for i, sid in enumerate([9, 4, 7, 1, 3]):
+            rounds, wins = ref._OnlineMetric(lags), ref._OnlineMetric(lags)
+            for v in obs[i]:
+                rounds.push(float(v & 0xFFFF))
+                wins.push(float(v >> 16))
+            want += ref._rows_for_online_group((ref._GROUP_STRATEGY, 4, sid), lags=lags, rounds=rounds,
+                                               wins=wins)
+        assert mine == want                                   # floats compared by value: bit-identical
+        assert rd.normalize_lags([3, 1, 3]) == ref._normalize_lags([3, 1, 3])
+        assert rd.EXPECTED_NOTE == ref._EXPECTED_NOTE
+    finally:
+        for name in [m for m in sys.modules if m == "farkle" or m.startswith("farkle.")]:
+            sys.modules.pop(name)
+
+
+def _expected_state(z, lags):
+    root, k, sh0, nsh = (int(x) for x in z["meta"])
+    obs = rd.observations_from_rows(z["rows"], len(z["strategies"]), nsh)
+    return rd.StrategyLagState.from_observations(lags, obs)
+
+
+def test_cell_in_batches_oracle_engine():
+    """`strategy_lag_state` over launches of 3 shuffles == the whole fixture at once (CPU oracle)."""
+    z = np.load(GOLDEN / "games_fast_54_4.npz")
+    root, k, sh0, nsh = (int(x) for x in z["meta"])
+    lags = (1, 2, 4)
+    want = _expected_state(z, lags)
+    got = rd.strategy_lag_state(root, k, sh0, nsh, z["strategies"], lags, batch_shuffles=3,
+                                engine=OracleEngine())
+    assert got.n_obs == nsh and np.array_equal(got.stats, want.stats)
+    assert np.array_equal(got.head, want.head) and np.array_equal(got.tail, want.tail)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,lags", [("fast_54_4", (1, 2, 4)), ("fast_42_2", (1,)), ("full_0_5", (2, 3))])
+def test_device_lag_statistics(name, lags):
+    from farkle_ii_b200.device import get_engine
+
+    eng = get_engine(0)
+    z = np.load(GOLDEN / f"games_{name}.npz")
+    root, k, sh0, nsh = (int(x) for x in z["meta"])
+    want = _expected_state(z, lags)
+    res = eng.play_tournament(root, k, sh0, nsh, z["strategies"], lags=lags)
+    got = rd.StrategyLagState.from_launch(lags, nsh, res.lag_stats, res.lag_edges)
+    assert res.lag_stats.shape == (len(z["strategies"]), len(lags), LAG_WIDTH)
+    assert np.array_equal(got.stats, want.stats)
+    assert np.array_equal(got.head, want.head) and np.array_equal(got.tail, want.tail)
+    if nsh >= 3:                                              # launches of uneven size join up
+        parts = rd.strategy_lag_state(root, k, sh0, nsh, z["strategies"], lags, batch_shuffles=max(nsh // 3, 1),
+                                      engine=eng)
+        assert np.array_equal(parts.stats, want.stats) and np.array_equal(parts.tail, want.tail)
+    # the tallies of the same launch are untouched by the extra kernels
+    plain = eng.play_tournament(root, k, sh0, nsh, z["strategies"])
+    assert np.array_equal(res.tallies.cpu().numpy(), plain.tallies.cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_device_lag_statistics_large_cell():
+    """Full grid, 300 shuffles of k=2: device sums == brute force over the device's own rows
+    (rows are bit-exact with the oracle elsewhere); two halves join to the whole."""
+    from farkle_ii_b200.device import get_engine
+
+    eng = get_engine(0)
+    table = np.load(GOLDEN / "games_full_0_2.npz")["strategies"]
+    lags, nsh = (1, 7, 64), 300
+    res = eng.play_tournament(3, 2, 10, nsh, table, lags=lags, want_rows=True)
+    obs = rd.observations_from_rows(res.rows_numpy(), len(table), nsh)
+    want = rd.StrategyLagState.from_observations(lags, obs)
+    got = rd.StrategyLagState.from_launch(lags, nsh, res.lag_stats, res.lag_edges)
+    assert np.array_equal(got.stats, want.stats)
+    assert np.array_equal(got.head, want.head) and np.array_equal(got.tail, want.tail)
+    halves = rd.strategy_lag_state(3, 2, 10, nsh, table, lags, batch_shuffles=170, engine=eng)
+    assert np.array_equal(halves.stats, want.stats)
+    rows = got.rows(range(len(table)), 2)
+    assert len(rows) == len(table) * 2 * len(lags)
+    assert sum(r["estimability_status"] == "estimated" for r in rows) > len(rows) // 2
+
+
+@pytest.mark.gpu
+def test_lag_argument_errors():
+    from farkle_ii_b200 import _native
+    from farkle_ii_b200.device import get_engine
+
+    eng = get_engine(0)
+    table = np.load(GOLDEN / "games_fast_42_2.npz")["strategies"]
+    for bad in ((0,), (1, 1), (5000,), tuple(range(1, 10))):
+        with pytest.raises(_native.NativeError):
+            eng.play_tournament(1, 2, 0, 4, table, lags=bad)
