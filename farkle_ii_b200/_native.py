@@ -28,11 +28,25 @@ SYMBOLS = (
     "fb_abi_version", "fb_last_error", "fb_init", "fb_device_info", "fb_row_stride",
     "fb_workspace_bytes", "fb_seedseq_generate", "fb_coordinate_seeds", "fb_seed_streams",
     "fb_roll_dice", "fb_default_score", "fb_permute_shuffles", "fb_play_tournament",
-    "fb_play_tournament_seats", "fb_play_tournament_lags",
+    "fb_play_tournament_seats", "fb_play_tournament_lags", "fb_matchup_scratch_bytes",
     "fb_play_h2h", "fb_h2h_resolve", "fb_play_games", "fb_run_tournament_host",
     "fb_measure_issue_peak", "fb_last_play_kernel_ms", "fb_play_kernel_ms_history",
     "fb_kernel_launch_count",
 )
+
+
+class LagRequest(C.Structure):
+    """``fb_lag_request_t`` (include/farkle_b200.h)."""
+
+    _fields_ = [
+        ("lags", C.c_void_p), ("n_lags", C.c_int32),
+        ("matchup_min_observations", C.c_int32),
+        ("strategy_stats_dev", C.c_void_p), ("strategy_edges_dev", C.c_void_p),
+        ("matchup_capacity", C.c_uint64), ("matchup_participants_dev", C.c_void_p),
+        ("matchup_count_dev", C.c_void_p), ("matchup_stats_dev", C.c_void_p),
+        ("scratch_dev", C.c_void_p), ("scratch_bytes", C.c_size_t),
+        ("n_matchups_host", C.c_void_p),
+    ]
 
 
 class NativeError(RuntimeError):
@@ -94,8 +108,10 @@ def _declare(L: C.CDLL) -> None:
                                            _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _int, _vp, _vp,
                                            _sz, _vp]
     L.fb_play_tournament_lags.argtypes = [_u64, _int, _u64, _int, _vp, _vp, _int, _int, _i32, _i32,
-                                          _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _int, _vp, _vp,
-                                          _int, _vp, _vp, _vp, _sz, _vp]
+                                          _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _int, _vp,
+                                          C.POINTER(LagRequest), _vp, _sz, _vp]
+    L.fb_matchup_scratch_bytes.argtypes = [_u64]
+    L.fb_matchup_scratch_bytes.restype = _sz
     L.fb_play_h2h.argtypes = [_u64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _i32, _i32, _vp,
                               _vp, _vp, _vp, _sz, _vp]
     L.fb_h2h_resolve.argtypes = [_int, _vp, _vp, _vp, _vp, _vp]

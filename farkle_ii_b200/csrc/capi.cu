@@ -21,7 +21,11 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
 #include "../../include/farkle_b200.h"
+#include "matchup.cuh"
 #include "play.cuh"
 #include "rng.cuh"
 #include "scoring.cuh"
@@ -846,6 +850,95 @@ int fb_permute_shuffles(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuf
     return permute_shuffles(root_seed, k, shuffle0, n_shuffles, n_strategies, perm_out_dev, nullptr, nullptr, stream);
 }
 
+// ---- matchup groups (matchup.cuh) ------------------------------------------------------------
+static size_t matchup_cub_bound(uint64_t n) { return align_up(2 * n + (8u << 20), 256); }
+
+static size_t matchup_scratch_bytes(uint64_t n) {
+    return 2 * align_up(n * 8, 256) + 6 * align_up(n * 4, 256) + align_up((n + 1) * 4, 256) + 256 +
+           matchup_cub_bound(n);
+}
+
+static int run_matchups(const fb_lag_request_t& rq, const int* lags, int n_lags, const uint32_t* header,
+                        const int32_t* perm, const int32_t* strategy_ids_dev, uint64_t n_games, int k,
+                        cudaStream_t stream) {
+    const uint64_t n = n_games;
+    if (rq.scratch_bytes < matchup_scratch_bytes(n))
+        return fail(FB_ERR_WORKSPACE, "matchup scratch too small: need %zu bytes", matchup_scratch_bytes(n));
+    uint8_t* p = static_cast<uint8_t*>(rq.scratch_dev);
+    auto take = [&](size_t bytes) {
+        uint8_t* q = p;
+        p += align_up(bytes, 256);
+        return q;
+    };
+    uint64_t* key_a = reinterpret_cast<uint64_t*>(take(n * 8));
+    uint64_t* key_b = reinterpret_cast<uint64_t*>(take(n * 8));
+    uint32_t* game_a = reinterpret_cast<uint32_t*>(take(n * 4));
+    uint32_t* game_b = reinterpret_cast<uint32_t*>(take(n * 4));
+    MatchupParams M{};
+    M.seg_flag = reinterpret_cast<uint32_t*>(take(n * 4));
+    M.seg_id1 = reinterpret_cast<uint32_t*>(take(n * 4));
+    M.elig = reinterpret_cast<uint32_t*>(take(n * 4));
+    M.slot = reinterpret_cast<uint32_t*>(take(n * 4));
+    M.seg_first = reinterpret_cast<uint32_t*>(take((n + 1) * 4));
+    M.status = reinterpret_cast<uint32_t*>(take(256));
+    void* cub_temp = p;
+    const size_t cub_have = matchup_cub_bound(n);
+    M.header = header;
+    M.perm = perm;
+    M.strategy_ids = strategy_ids_dev;
+    M.n_games = (uint32_t)n;
+    M.k = k;
+    M.n_lags = n_lags;
+    for (int z = 0; z < n_lags; z++) M.lags[z] = lags[z];
+    M.min_obs = (uint32_t)rq.matchup_min_observations;
+    M.capacity = rq.matchup_capacity;
+    M.participants = rq.matchup_participants_dev;
+    M.count = rq.matchup_count_dev;
+    M.stats = reinterpret_cast<unsigned long long*>(rq.matchup_stats_dev);
+    FB_CUDA(cudaMemsetAsync(M.status, 0, 256, stream));
+    FB_CUDA(cudaMemsetAsync(M.stats, 0, (size_t)rq.matchup_capacity * n_lags * FB_MATCHUP_LAG_WIDTH * 8, stream));
+    const unsigned blocks = blocks_for(n, 256);
+    matchup_key_kernel<<<blocks, 256, 0, stream>>>(M, key_a, game_a);
+    int rc = launch_check("matchup_key_kernel");
+    if (rc) return rc;
+    cub::DoubleBuffer<uint64_t> keys(key_a, key_b);
+    cub::DoubleBuffer<uint32_t> vals(game_a, game_b);
+    size_t need = 0;
+    FB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, keys, vals, (int)n, 0, 64, stream));
+    if (need > cub_have) return fail(FB_ERR_WORKSPACE, "radix sort needs %zu temporary bytes, %zu reserved", need, cub_have);
+    FB_CUDA(cub::DeviceRadixSort::SortPairs(cub_temp, need, keys, vals, (int)n, 0, 64, stream));
+    g_launches.fetch_add(1);
+    M.key = keys.Current();
+    M.game = vals.Current();
+    matchup_flag_kernel<<<blocks, 256, 0, stream>>>(M);
+    rc = launch_check("matchup_flag_kernel");
+    if (rc) return rc;
+    FB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, need, M.seg_flag, M.seg_id1, (int)n, stream));
+    if (need > cub_have) return fail(FB_ERR_WORKSPACE, "scan needs %zu temporary bytes, %zu reserved", need, cub_have);
+    FB_CUDA(cub::DeviceScan::InclusiveSum(cub_temp, need, M.seg_flag, M.seg_id1, (int)n, stream));
+    matchup_first_kernel<<<blocks, 256, 0, stream>>>(M);
+    rc = launch_check("matchup_first_kernel");
+    if (rc) return rc;
+    matchup_eligible_kernel<<<blocks, 256, 0, stream>>>(M);
+    rc = launch_check("matchup_eligible_kernel");
+    if (rc) return rc;
+    FB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, M.elig, M.slot, (int)n, stream));
+    if (need > cub_have) return fail(FB_ERR_WORKSPACE, "scan needs %zu temporary bytes, %zu reserved", need, cub_have);
+    FB_CUDA(cub::DeviceScan::ExclusiveSum(cub_temp, need, M.elig, M.slot, (int)n, stream));
+    matchup_stats_kernel<<<blocks, 256, 0, stream>>>(M);
+    rc = launch_check("matchup_stats_kernel");
+    if (rc) return rc;
+    uint32_t status[2] = {0, 0};
+    FB_CUDA(cudaMemcpyAsync(status, M.status, sizeof(status), cudaMemcpyDeviceToHost, stream));
+    FB_CUDA(cudaStreamSynchronize(stream));
+    if (status[0]) return fail(FB_ERR_INTERNAL, "matchup key collision: two different matchups share a 64-bit key");
+    if (status[1] > rq.matchup_capacity)
+        return fail(FB_ERR_WORKSPACE, "matchup buffers hold %llu groups, the launch has %u",
+                    (unsigned long long)rq.matchup_capacity, status[1]);
+    *rq.n_matchups_host = (int64_t)status[1];
+    return FB_OK;
+}
+
 static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
                                 const fb_strategy_t* strategies_dev, const int32_t* strategy_ids_dev,
                                 int n_strategies, int n_tally_ids, int32_t target_score, int32_t max_rounds,
@@ -854,23 +947,29 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
                                 int64_t* tallies_dev, int64_t* totals_dev, void* rows_dev, int want_game_seeds,
                                 void* workspace_dev, size_t workspace_bytes, void* stream_v,
                                 uint32_t ordinal_base, int64_t* seat_tallies_dev = nullptr,
-                                const int32_t* lags_host = nullptr, int n_lags = 0,
-                                int64_t* lag_stats_dev = nullptr, uint32_t* lag_edges_dev = nullptr) {
+                                const fb_lag_request_t* lag = nullptr) {
     FB_REQUIRE_INIT();
     if (seat_tallies_dev && !tallies_dev) return fail(FB_ERR_BAD_ARG, "seat tallies need tallies_dev");
     LagParams L{};
-    if (n_lags != 0) {
-        if (n_lags < 0 || n_lags > FB_MAX_LAGS || !lags_host || !lag_stats_dev || !lag_edges_dev || !tallies_dev)
-            return fail(FB_ERR_BAD_ARG, "lag statistics need 1..%d lags, both lag buffers and tallies_dev", FB_MAX_LAGS);
-        for (int z = 0; z < n_lags; z++) {
-            if (lags_host[z] < 1 || lags_host[z] > FB_MAX_LAG)
-                return fail(FB_ERR_BAD_ARG, "lag %d outside [1,%d]", lags_host[z], FB_MAX_LAG);
+    if (lag) {
+        if (lag->n_lags < 1 || lag->n_lags > FB_MAX_LAGS || !lag->lags || !tallies_dev)
+            return fail(FB_ERR_BAD_ARG, "lag statistics need 1..%d lags and tallies_dev", FB_MAX_LAGS);
+        if ((lag->strategy_stats_dev != nullptr) != (lag->strategy_edges_dev != nullptr))
+            return fail(FB_ERR_BAD_ARG, "strategy lag statistics need both the stats and the edges buffer");
+        if (lag->matchup_min_observations < 0 ||
+            (lag->matchup_min_observations > 0 &&
+             (!lag->matchup_participants_dev || !lag->matchup_count_dev || !lag->matchup_stats_dev ||
+              !lag->scratch_dev || !lag->n_matchups_host)))
+            return fail(FB_ERR_BAD_ARG, "matchup lag statistics need all matchup buffers, scratch and the count pointer");
+        for (int z = 0; z < lag->n_lags; z++) {
+            if (lag->lags[z] < 1 || lag->lags[z] > FB_MAX_LAG)
+                return fail(FB_ERR_BAD_ARG, "lag %d outside [1,%d]", lag->lags[z], FB_MAX_LAG);
             for (int y = 0; y < z; y++)
-                if (lags_host[y] == lags_host[z]) return fail(FB_ERR_BAD_ARG, "duplicate lag %d", lags_host[z]);
-            L.lags[z] = lags_host[z];
-            L.max_lag = std::max(L.max_lag, lags_host[z]);
+                if (lag->lags[y] == lag->lags[z]) return fail(FB_ERR_BAD_ARG, "duplicate lag %d", lag->lags[z]);
+            L.lags[z] = lag->lags[z];
+            L.max_lag = std::max(L.max_lag, lag->lags[z]);
         }
-        L.n_lags = n_lags;
+        L.n_lags = lag->n_lags;
     }
     cudaStream_t stream = (cudaStream_t)stream_v;
     if (k < 1 || k > FB_MAX_PLAYERS) return fail(FB_ERR_BAD_ARG, "k=%d outside [1,%d]", k, FB_MAX_PLAYERS);
@@ -954,23 +1053,29 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
     const int n_chunks = (n_shuffles + G.chunk - 1) / G.chunk;
     tally_gather_kernel<<<dim3(blocks_for((uint64_t)n_strategies, 128), (unsigned)n_chunks), 128, 0, stream>>>(G);
     rc = launch_check("tally_gather_kernel");
-    if (rc || !L.n_lags) return rc;
-    L.header = w.header;
-    L.inv = inv;
-    L.n_strategies = n_strategies;
-    L.n_shuffles = n_shuffles;
-    L.k = k;
-    L.gps = gps;
-    L.chunk = 43;
-    L.stats = reinterpret_cast<unsigned long long*>(lag_stats_dev);
-    L.edges = lag_edges_dev;
-    const unsigned sblocks = blocks_for((uint64_t)n_strategies, 128);
-    lag_gather_kernel<<<dim3(sblocks, (unsigned)((n_shuffles + L.chunk - 1) / L.chunk), (unsigned)L.n_lags), 128, 0,
-                        stream>>>(L);
-    rc = launch_check("lag_gather_kernel");
-    if (rc) return rc;
-    lag_edges_kernel<<<dim3(sblocks, (unsigned)std::min(L.max_lag, n_shuffles)), 128, 0, stream>>>(L);
-    return launch_check("lag_edges_kernel");
+    if (rc || !lag) return rc;
+    if (lag->strategy_stats_dev) {
+        L.header = w.header;
+        L.inv = inv;
+        L.n_strategies = n_strategies;
+        L.n_shuffles = n_shuffles;
+        L.k = k;
+        L.gps = gps;
+        L.chunk = 43;
+        L.stats = reinterpret_cast<unsigned long long*>(lag->strategy_stats_dev);
+        L.edges = lag->strategy_edges_dev;
+        const unsigned sblocks = blocks_for((uint64_t)n_strategies, 128);
+        lag_gather_kernel<<<dim3(sblocks, (unsigned)((n_shuffles + L.chunk - 1) / L.chunk), (unsigned)L.n_lags), 128,
+                            0, stream>>>(L);
+        rc = launch_check("lag_gather_kernel");
+        if (rc) return rc;
+        lag_edges_kernel<<<dim3(sblocks, (unsigned)std::min(L.max_lag, n_shuffles)), 128, 0, stream>>>(L);
+        rc = launch_check("lag_edges_kernel");
+        if (rc) return rc;
+    }
+    if (lag->matchup_min_observations > 0)
+        return run_matchups(*lag, L.lags, L.n_lags, w.header, perm, strategy_ids_dev, n_games, k, stream);
+    return FB_OK;
 }
 
 int fb_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
@@ -1007,15 +1112,16 @@ int fb_play_tournament_lags(uint64_t root_seed, int k, uint64_t shuffle0, int n_
                             const uint64_t* override_shuffle_dev, const uint32_t* override_game_dev,
                             const int32_t* override_max_rounds_dev, int n_overrides, int shuffles_per_slot,
                             int64_t* tallies_dev, int64_t* totals_dev, void* rows_dev, int want_game_seeds,
-                            int64_t* seat_tallies_dev, const int32_t* lags_host, int n_lags,
-                            int64_t* lag_stats_dev, uint32_t* lag_edges_dev, void* workspace_dev,
+                            int64_t* seat_tallies_dev, const fb_lag_request_t* lag, void* workspace_dev,
                             size_t workspace_bytes, void* stream_v) {
     return play_tournament_impl(root_seed, k, shuffle0, n_shuffles, strategies_dev, strategy_ids_dev, n_strategies,
                                 n_tally_ids, target_score, max_rounds, override_shuffle_dev, override_game_dev,
                                 override_max_rounds_dev, n_overrides, shuffles_per_slot, tallies_dev, totals_dev,
                                 rows_dev, want_game_seeds, workspace_dev, workspace_bytes, stream_v, 0u,
-                                seat_tallies_dev, lags_host, n_lags, lag_stats_dev, lag_edges_dev);
+                                seat_tallies_dev, lag);
 }
+
+size_t fb_matchup_scratch_bytes(uint64_t n_games) { return matchup_scratch_bytes(n_games); }
 
 int fb_play_h2h(uint64_t root_seed, int n_blocks, const uint64_t* pair_id_dev, const uint8_t* order_dev,
                 const fb_strategy_t* seat1_dev, const fb_strategy_t* seat2_dev,

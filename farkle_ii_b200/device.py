@@ -17,6 +17,7 @@ import torch
 from . import _native
 from .layout import (
     LAG_WIDTH,
+    MATCHUP_LAG_WIDTH,
     SEAT_TALLY_WIDTH,
     STRATEGY_DTYPE,
     TALLY_WIDTH,
@@ -61,6 +62,9 @@ class TournamentResult:
     seat_tallies: torch.Tensor | None = None  # int64 [slots, ids, k, 4]
     lag_stats: torch.Tensor | None = None     # int64 [n_strategies, n_lags, LAG_WIDTH]
     lag_edges: torch.Tensor | None = None     # int32 [n_strategies, 2, max_lag]: n_rounds | win << 16
+    matchup_participants: torch.Tensor | None = None  # int32 [groups, k] sorted strategy ids
+    matchup_count: torch.Tensor | None = None         # int32 [groups] games
+    matchup_stats: torch.Tensor | None = None         # int64 [groups, n_lags, MATCHUP_LAG_WIDTH]
 
     def rows_numpy(self) -> np.ndarray:
         assert self.rows is not None
@@ -228,12 +232,15 @@ class Engine:
                         want_game_seeds: bool = False, tallies: torch.Tensor | None = None,
                         totals: torch.Tensor | None = None, want_seat_tallies: bool = False,
                         seat_tallies: torch.Tensor | None = None,
-                        lags: tuple[int, ...] = ()) -> TournamentResult:
+                        lags: tuple[int, ...] = (), matchup_min_observations: int = 0,
+                        strategy_lags: bool = True) -> TournamentResult:
         """Enqueue shuffles ``shuffle0 .. shuffle0+n_shuffles-1`` of cell (root_seed, k).
 
         ``lags`` asks for the RNG lag statistics of the strategy groups (``lag_stats``
         int64 [n_strategies, n_lags, LAG_WIDTH] by table position, ``lag_edges`` uint32
-        [n_strategies, 2, max(lags)]); see ``farkle_ii_b200.rng_diagnostics``.
+        [n_strategies, 2, max(lags)]); ``matchup_min_observations`` > 0 adds the matchup
+        groups with at least that many games (``matchup_participants`` / ``matchup_count`` /
+        ``matchup_stats``); see ``farkle_ii_b200.rng_diagnostics``.
 
         ``strategies`` is a device uint8 tensor holding ``fb_strategy_t`` entries, or a
         host STRATEGY_DTYPE array (copied).  ``tallies`` / ``totals`` may be passed to
@@ -274,21 +281,44 @@ class Engine:
             d_om = self.to_device(np.array([o[2] for o in ov], dtype=np.int32))
         ws_bytes = self.workspace_bytes(max(k, 1), n_games) + 2 * (n_shuffles * n_strategies * 4 + 256)
         ws = self.workspace(ws_bytes)
-        lag_stats = lag_edges = None
-        lags_c = (C.c_int32 * max(len(lags), 1))(*[int(v) for v in lags])
+        lag_stats = lag_edges = m_part = m_count = m_stats = None
+        request = None
         if lags:
-            lag_stats = torch.zeros((n_strategies, len(lags), LAG_WIDTH), dtype=torch.int64,
-                                    device=self.device)
-            lag_edges = torch.zeros((n_strategies, 2, max(int(v) for v in lags)), dtype=torch.int32,
-                                    device=self.device)
+            lags_c = (C.c_int32 * len(lags))(*[int(v) for v in lags])
+            n_found = C.c_int64(0)
+            request = _native.LagRequest()
+            request.lags = C.cast(lags_c, C.c_void_p)
+            request.n_lags = len(lags)
+            if strategy_lags:
+                lag_stats = torch.zeros((n_strategies, len(lags), LAG_WIDTH), dtype=torch.int64,
+                                        device=self.device)
+                lag_edges = torch.zeros((n_strategies, 2, max(int(v) for v in lags)), dtype=torch.int32,
+                                        device=self.device)
+                request.strategy_stats_dev, request.strategy_edges_dev = lag_stats.data_ptr(), lag_edges.data_ptr()
+            if matchup_min_observations > 0:
+                capacity = max(n_games // matchup_min_observations, 1)
+                m_part = torch.empty((capacity, max(k, 1)), dtype=torch.int32, device=self.device)
+                m_count = torch.empty(capacity, dtype=torch.int32, device=self.device)
+                m_stats = torch.empty((capacity, len(lags), MATCHUP_LAG_WIDTH), dtype=torch.int64,
+                                      device=self.device)
+                scratch = self.empty(int(self.lib.fb_matchup_scratch_bytes(n_games)) + 256)
+                request.matchup_min_observations = int(matchup_min_observations)
+                request.matchup_capacity = capacity
+                request.matchup_participants_dev = m_part.data_ptr()
+                request.matchup_count_dev, request.matchup_stats_dev = m_count.data_ptr(), m_stats.data_ptr()
+                request.scratch_dev, request.scratch_bytes = scratch.data_ptr(), scratch.numel()
+                request.n_matchups_host = C.cast(C.pointer(n_found), C.c_void_p)
         _native.check(self.lib.fb_play_tournament_lags(
             root_seed, k, shuffle0, n_shuffles, _ptr(strategies), _ptr(d_ids), n_strategies,
             n_tally_ids, target_score, max_rounds, _ptr(d_os), _ptr(d_og), _ptr(d_om), len(ov),
             shuffles_per_slot, _ptr(tallies if want_tallies else None), _ptr(totals), _ptr(rows),
-            int(want_game_seeds), _ptr(seat_tallies), C.cast(lags_c, C.c_void_p), len(lags),
-            _ptr(lag_stats), _ptr(lag_edges), _ptr(ws), ws.numel(), self._stream()))
+            int(want_game_seeds), _ptr(seat_tallies), C.byref(request) if request is not None else None,
+            _ptr(ws), ws.numel(), self._stream()))
+        if m_part is not None:
+            found = int(n_found.value)
+            m_part, m_count, m_stats = m_part[:found], m_count[:found], m_stats[:found]
         return TournamentResult(tallies if want_tallies else None, totals, rows, n_games, k, seat_tallies,
-                                lag_stats, lag_edges)
+                                lag_stats, lag_edges, m_part, m_count, m_stats)
 
     def play_games(self, coords: np.ndarray, k: int, seat_strategies: np.ndarray, *,
                    seat_strategy_ids=None, target_score: int = 10_000, max_rounds: int = 200,

@@ -1,4 +1,4 @@
-"""RNG lag diagnostics of the strategy groups, from the tournament reduction itself.
+"""RNG lag diagnostics (strategy and matchup groups) from the tournament reduction itself.
 
 The reference stage (src/farkle/analysis/rng_diagnostics.py) re-reads every curated row, routes and
 externally sorts one observation per seat exposure by ``(group, root_seed, shuffle_index,
@@ -14,22 +14,33 @@ exactly and the final floats below are computed with the same expressions.
 A cell may be played in several launches (deterministic batches, ranks): ``StrategyLagState`` is a
 monoid -- ``a.extend(b)`` adds the pairs that straddle the boundary from the ``max(lags)``
 observations each launch reports at its two ends.
+
+"Matchup" groups (the games that seat the same multiset of strategies, one n_rounds observation per
+game) come from the same launch: the device sorts the games of the cell by matchup key, keeps the
+groups that have enough games and returns their lag sums (csrc/matchup.cuh).  They need the whole
+(root, k) cell in ONE launch -- a cell of the mega config is 4,300 shuffles, far below the 2^31
+games a launch takes.  The reference's group identity (BLAKE2b digest), its deterministic priority
+cap and the report rows are host arithmetic on those few groups: ``MatchupLagGroups``.
 """
 
 from __future__ import annotations
 
+import hashlib
 from dataclasses import dataclass
 from typing import Any, Sequence
 
 import numpy as np
 
-from .layout import LAG_WIDTH
+from .layout import LAG_WIDTH, MATCHUP_LAG_WIDTH
 
 EXPECTED_NOTE = (
     "Zero-centered approximate descriptive reference band only; values inside or "
     "outside the band do not establish or refute independence"
 )
 STRATEGY_SEQUENCE_ORDER = "root_seed,k,shuffle_index,game_index,seat_index"
+MATCHUP_SEQUENCE_ORDER = "root_seed,k,shuffle_index,game_index"
+DEFAULT_MAX_MATCHUP_GROUPS = 100_000       # analysis.rng_max_matchup_groups (config.py:333)
+GROUP_STRATEGY, GROUP_MATCHUP = 0, 1
 WIN_BIT = 1 << 16           # observation word: n_rounds | win << 16 (include/farkle_b200.h)
 
 
@@ -118,17 +129,7 @@ class StrategyLagState:
         """``_OnlineMetric.result`` (:2066-2076) for table entry ``index``, lag slot ``z``;
         metric 0 = win_indicator, 1 = n_rounds.  Same float expressions, so the same bits."""
         row = self.stats[index, z]
-        pairs = int(row[0])
-        if pairs < 2:
-            return None, "insufficient_pairs"
-        sx, sy, sx2, sy2, sxy = (np.float64(v) for v in row[1 + 5 * metric:6 + 5 * metric])
-        count = float(pairs)
-        numerator = count * sxy - sx * sy
-        den_x = count * sx2 - sx ** 2
-        den_y = count * sy2 - sy ** 2
-        if den_x <= 0.0 or den_y <= 0.0:
-            return None, "zero_variance"
-        return float(numerator / (den_x * den_y) ** 0.5), "estimated"
+        return _pearson(int(row[0]), row[1 + 5 * metric:6 + 5 * metric])
 
     def rows(self, strategy_ids: Sequence[int], k: int) -> list[dict[str, Any]]:
         """Rows of the diagnostics table for the strategy groups, as ``_rows_for_online_group``
@@ -164,6 +165,166 @@ class StrategyLagState:
                         "note": EXPECTED_NOTE,
                     })
         return out
+
+
+# ---- matchup groups ------------------------------------------------------------------------------
+def _pearson(pairs: int, sums: Sequence[Any]) -> tuple[float | None, str]:
+    """``_OnlineMetric.result`` (:2066-2076) on integer sums, with the reference's float expressions."""
+    if pairs < 2:
+        return None, "insufficient_pairs"
+    sx, sy, sx2, sy2, sxy = (np.float64(v) for v in sums)
+    count = float(pairs)
+    numerator = count * sxy - sx * sy
+    den_x = count * sx2 - sx ** 2
+    den_y = count * sy2 - sy ** 2
+    if den_x <= 0.0 or den_y <= 0.0:
+        return None, "zero_variance"
+    return float(numerator / (den_x * den_y) ** 0.5), "estimated"
+
+
+def _splitmix64(values: np.ndarray) -> np.ndarray:
+    """SplitMix64 finaliser over a uint64 array (:1267-1272); wraps modulo 2^64."""
+    v = values.astype(np.uint64, copy=True)
+    with np.errstate(over="ignore"):
+        v += np.uint64(0x9E3779B97F4A7C15)
+        v = (v ^ (v >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        v = (v ^ (v >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return v ^ (v >> np.uint64(31))
+
+
+def matchup_group_ids(k: int, participants: np.ndarray, max_players: int) -> np.ndarray:
+    """The reference's 64-bit matchup ids (``_matchup_ids``, :1173-1184): BLAKE2b-8, personalised
+    ``farkle-m``, over the little-endian int32 row ``[k, sorted ids..., -1 padding]`` whose width
+    is one plus the number of seat-strategy columns of the combined table (``max_players``)."""
+    out = np.empty(len(participants), dtype=np.uint64)
+    row = np.full(1 + max_players, -1, dtype="<i4")
+    row[0] = k
+    for g, ids in enumerate(np.asarray(participants, dtype=np.int32)):
+        row[1:1 + k] = ids
+        digest = hashlib.blake2b(row.tobytes(), digest_size=8, person=b"farkle-m").digest()
+        out[g] = int.from_bytes(digest, "little", signed=False)
+    return out
+
+
+@dataclass
+class MatchupLagGroups:
+    """Lag sums of the matchup groups of one (root, k) cell that have enough observations."""
+
+    lags: tuple[int, ...]
+    k: int
+    participants: np.ndarray   # int32 [groups, k] sorted strategy ids
+    counts: np.ndarray         # int64 [groups] observations (games)
+    stats: np.ndarray          # int64 [groups, n_lags, MATCHUP_LAG_WIDTH]
+
+    @classmethod
+    def from_launch(cls, lags: Sequence[int], result: Any) -> "MatchupLagGroups":
+        """From the ``matchup_*`` outputs of a ``play_tournament(..., matchup_min_observations=m)``
+        launch that covered the whole cell; groups are put in participant order."""
+        part = result.matchup_participants.cpu().numpy().astype(np.int32)
+        counts = result.matchup_count.cpu().numpy().view(np.uint32).astype(np.int64)
+        stats = result.matchup_stats.cpu().numpy().astype(np.int64)
+        return cls(tuple(int(v) for v in lags), int(result.k), part, counts, stats)._canonical()
+
+    @classmethod
+    def from_rows(cls, lags: Sequence[int], rows: np.ndarray, min_observations: int) -> "MatchupLagGroups":
+        """Brute force over compact rows in game order (host reference for the device path)."""
+        lags = tuple(int(v) for v in lags)
+        k = rows["seats"].shape[1]
+        series: dict[tuple[int, ...], list[int]] = {}
+        for row in rows:
+            series.setdefault(tuple(sorted(int(v) for v in row["seats"]["strategy"])), []).append(
+                int(row["n_rounds"]))
+        keep = sorted(key for key, seq in series.items() if len(seq) >= min_observations)
+        stats = np.zeros((len(keep), len(lags), MATCHUP_LAG_WIDTH), dtype=np.int64)
+        for g, key in enumerate(keep):
+            seq = series[key]
+            for z, lag in enumerate(lags):
+                for j in range(lag, len(seq)):
+                    x, y = seq[j - lag], seq[j]
+                    stats[g, z] += [1, x, y, x * x, y * y, x * y]
+        return cls(lags, k, np.array(keep, dtype=np.int32).reshape(len(keep), k),
+                   np.array([len(series[key]) for key in keep], dtype=np.int64), stats)
+
+    def _canonical(self) -> "MatchupLagGroups":
+        order = np.lexsort(tuple(self.participants[:, c] for c in reversed(range(self.k))))
+        return MatchupLagGroups(self.lags, self.k, self.participants[order], self.counts[order],
+                                self.stats[order])
+
+    def __len__(self) -> int:
+        return len(self.counts)
+
+    def group_ids(self, max_players: int) -> np.ndarray:
+        return matchup_group_ids(self.k, self.participants, max_players)
+
+    def priorities(self, max_players: int) -> np.ndarray:
+        """Stable selection priority of every group (``_priority``, :1281-1284)."""
+        values = self.group_ids(max_players) ^ (np.uint64(self.k) << np.uint64(48))
+        values ^= np.uint64(GROUP_MATCHUP) << np.uint64(63)
+        return _splitmix64(values ^ np.uint64(0xD1B54A32D192ED03))
+
+    def rows(self, max_players: int, keep: np.ndarray | None = None) -> list[dict[str, Any]]:
+        """Report rows of the (selected) groups as ``_rows_for_online_group`` builds them for a
+        matchup (:2110-2159): n_rounds only, one row per lag; groups in (group id, ids) order."""
+        ids = self.group_ids(max_players)
+        chosen = np.flatnonzero(np.ones(len(self), dtype=bool) if keep is None else keep)
+        order = chosen[np.lexsort((*(self.participants[chosen, c] for c in reversed(range(self.k))),
+                                   ids[chosen]))]
+        out: list[dict[str, Any]] = []
+        for g in order:
+            people = [int(v) for v in self.participants[g]]
+            for z, lag in enumerate(self.lags):
+                pairs = int(self.stats[g, z, 0])
+                value, status = _pearson(pairs, self.stats[g, z, 1:6])
+                half_width = 1.96 / pairs**0.5 if pairs > 0 else None
+                out.append({
+                    "summary_level": "matchup",
+                    "strategy": None,
+                    "matchup_id": int(ids[g]),
+                    "matchup": " | ".join(str(v) for v in people),
+                    "participant_strategy_ids": people,
+                    "n_players": self.k,
+                    "observations": int(self.counts[g]),
+                    "lagged_pairs": pairs,
+                    "lag": lag,
+                    "metric": "n_rounds",
+                    "autocorr": value,
+                    "estimability_status": status,
+                    "zero_centered_descriptive_reference_band_lower": (
+                        -half_width if half_width is not None else None),
+                    "zero_centered_descriptive_reference_band_upper": half_width,
+                    "sequence_order": MATCHUP_SEQUENCE_ORDER,
+                    "note": EXPECTED_NOTE,
+                })
+        return out
+
+
+def select_matchup_groups(cells: Sequence[MatchupLagGroups], max_players: int,
+                          cap: int | None = DEFAULT_MAX_MATCHUP_GROUPS) -> list[np.ndarray]:
+    """The reference's deterministic cap over the eligible matchup groups of ALL player counts
+    (``_write_or_reuse_selection``, :1611-1651): keep the ``cap`` groups that come first by
+    ``(priority, group_type, k, group_id, p0, p1, ...)``.  Returns one keep-mask per cell."""
+    total = sum(len(c) for c in cells)
+    if cap is None or total <= cap:
+        return [np.ones(len(c), dtype=bool) for c in cells]
+    keys = np.zeros((total, 4 + max_players), dtype=np.uint64)     # priority, k, group id, p..., owner
+    owner = np.empty(total, dtype=np.int64)
+    at = 0
+    for index, cell in enumerate(cells):
+        n = len(cell)
+        keys[at:at + n, 0] = cell.priorities(max_players)
+        keys[at:at + n, 1] = cell.k
+        keys[at:at + n, 2] = cell.group_ids(max_players)
+        padded = np.full((n, max_players), -1, dtype=np.int64)
+        padded[:, :cell.k] = cell.participants
+        keys[at:at + n, 3:3 + max_players] = (padded + 2**31).astype(np.uint64)   # order-preserving
+        owner[at:at + n] = index
+        at += n
+    order = np.lexsort(tuple(keys[:, c] for c in reversed(range(3 + max_players))))[:cap]
+    masks = [np.zeros(len(c), dtype=bool) for c in cells]
+    starts = np.cumsum([0, *(len(c) for c in cells)])
+    for pos in order:
+        masks[owner[pos]][pos - starts[owner[pos]]] = True
+    return masks
 
 
 def observations_from_rows(rows: np.ndarray, n_strategies: int, n_shuffles: int) -> np.ndarray:
@@ -222,5 +383,7 @@ def gather_lag_states(state: StrategyLagState) -> StrategyLagState:
     return joined
 
 
-__all__ = ["EXPECTED_NOTE", "STRATEGY_SEQUENCE_ORDER", "StrategyLagState", "gather_lag_states",
-           "minimum_observations", "normalize_lags", "observations_from_rows", "strategy_lag_state"]
+__all__ = ["DEFAULT_MAX_MATCHUP_GROUPS", "EXPECTED_NOTE", "MATCHUP_SEQUENCE_ORDER", "MatchupLagGroups",
+           "STRATEGY_SEQUENCE_ORDER", "StrategyLagState", "gather_lag_states", "matchup_group_ids",
+           "minimum_observations", "normalize_lags", "observations_from_rows", "select_matchup_groups",
+           "strategy_lag_state"]

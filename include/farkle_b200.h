@@ -35,7 +35,8 @@ enum fb_status {
     FB_ERR_NO_DEVICE = -1,   /* no CUDA device / fb_init not called          */
     FB_ERR_BAD_ARG = -2,     /* argument outside the documented domain        */
     FB_ERR_CUDA = -3,        /* a CUDA runtime call failed (see last_error)   */
-    FB_ERR_WORKSPACE = -4    /* caller workspace too small                    */
+    FB_ERR_WORKSPACE = -4,   /* caller workspace too small                    */
+    FB_ERR_INTERNAL = -5     /* an internal consistency check failed          */
 };
 
 /* ---- RNG purposes (src/farkle/utils/random.py:18-37) --------------------- */
@@ -140,6 +141,33 @@ typedef struct fb_row_seat {
 #define FB_LAG_WIDTH 11
 #define FB_MAX_LAGS 8
 #define FB_MAX_LAG 4096
+
+/* "Matchup" groups of the same stage: the games of one cell that seat the same multiset of
+ * strategies, in (shuffle_index, game_index) order, observation = n_rounds (one per game;
+ * src/farkle/analysis/rng_diagnostics.py:1870-1901).  Only groups with at least
+ * matchup_min_observations games are written (the reference's eligibility rule is
+ * min(lags) + 2), in no particular order:
+ *   matchup_participants_dev int32 [capacity][k]   sorted strategy ids of the group
+ *   matchup_count_dev        uint32[capacity]      observations (games)
+ *   matchup_stats_dev        int64 [capacity][n_lags][FB_MATCHUP_LAG_WIDTH]
+ *                            lagged pairs, sum x, sum y, sum x^2, sum y^2, sum x*y of n_rounds
+ * capacity >= n_games / matchup_min_observations always suffices.                 */
+#define FB_MATCHUP_LAG_WIDTH 6
+
+typedef struct fb_lag_request {
+    const int32_t* lags;          /* HOST array: n_lags distinct lags in [1, FB_MAX_LAG]   */
+    int32_t n_lags;               /* 1..FB_MAX_LAGS                                          */
+    int32_t matchup_min_observations; /* 0 = no matchup groups                               */
+    int64_t* strategy_stats_dev;  /* accumulated into (caller zeroes); NULL = skip strategy groups */
+    uint32_t* strategy_edges_dev; /* overwritten; required with strategy_stats_dev           */
+    uint64_t matchup_capacity;    /* groups the three matchup buffers can hold               */
+    int32_t* matchup_participants_dev;
+    uint32_t* matchup_count_dev;
+    int64_t* matchup_stats_dev;   /* zeroed by the call                                      */
+    void* scratch_dev;            /* >= fb_matchup_scratch_bytes(n_games) when matchups are on */
+    size_t scratch_bytes;
+    int64_t* n_matchups_host;     /* HOST out: groups written; the call synchronises `stream` */
+} fb_lag_request_t;
 
 /* Per-launch totals, int64[FB_TOTALS_WIDTH]:
  *   0 games_attempted  1 games_completed  2 games_safety_limit
@@ -254,10 +282,9 @@ int fb_play_tournament_seats(uint64_t root_seed, int k, uint64_t shuffle0, int n
                              void* rows_dev, int want_game_seeds, int64_t* seat_tallies_dev,
                              void* workspace_dev, size_t workspace_bytes, void* stream);
 
-/* fb_play_tournament_seats plus the RNG lag statistics of the strategy groups (layout above).
- * lags_host: n_lags (1..FB_MAX_LAGS) distinct lags in [1, FB_MAX_LAG], HOST array.
- * lag_stats_dev is accumulated into (caller zeroes); lag_edges_dev is overwritten; both required
- * when n_lags > 0.  Needs tallies_dev (the winner marks and inverse permutations come with it). */
+/* fb_play_tournament_seats plus the RNG lag statistics (layouts above) of the strategy groups
+ * and / or the matchup groups of the launch.  Needs tallies_dev (the winner marks and inverse
+ * permutations come with it).  lag == NULL is plain fb_play_tournament_seats.        */
 int fb_play_tournament_lags(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
                             const fb_strategy_t* strategies_dev, const int32_t* strategy_ids_dev,
                             int n_strategies, int n_tally_ids, int32_t target_score,
@@ -266,9 +293,11 @@ int fb_play_tournament_lags(uint64_t root_seed, int k, uint64_t shuffle0, int n_
                             const int32_t* override_max_rounds_dev, int n_overrides,
                             int shuffles_per_slot, int64_t* tallies_dev, int64_t* totals_dev,
                             void* rows_dev, int want_game_seeds, int64_t* seat_tallies_dev,
-                            const int32_t* lags_host, int n_lags, int64_t* lag_stats_dev,
-                            uint32_t* lag_edges_dev, void* workspace_dev, size_t workspace_bytes,
-                            void* stream);
+                            const fb_lag_request_t* lag, void* workspace_dev,
+                            size_t workspace_bytes, void* stream);
+
+/* Scratch bytes the matchup grouping of n_games games needs (sort buffers, segment tables). */
+size_t fb_matchup_scratch_bytes(uint64_t n_games);
 
 /* Head-to-head attempts.  Replaces the attempt loop of
  * _simulate_block_from_manifest (src/farkle/analysis/h2h_schedule.py:1149-1243)

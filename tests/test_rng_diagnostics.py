@@ -189,3 +189,147 @@ def test_lag_argument_errors():
     for bad in ((0,), (1, 1), (5000,), tuple(range(1, 10))):
         with pytest.raises(_native.NativeError):
             eng.play_tournament(1, 2, 0, 4, table, lags=bad)
+
+
+# ---- matchup groups ------------------------------------------------------------------------------
+def _rows_like(k, seats, rounds):
+    """Minimal compact-row look-alike (seat strategies + n_rounds) for the host brute force."""
+    rows = np.zeros(len(rounds), dtype=[("n_rounds", "<u2"), ("seats", [("strategy", "<i4")], (k,))])
+    rows["n_rounds"] = rounds
+    rows["seats"]["strategy"] = seats
+    return rows
+
+
+def test_matchup_groups_brute_force_and_selection():
+    rng = np.random.default_rng(3)
+    k, lags = 3, (1, 2)
+    seats = np.array([rng.permutation(6)[:k] for _ in range(400)], dtype=np.int32)   # 20 possible matchups
+    rounds = rng.integers(5, 60, size=400)
+    groups = rd.MatchupLagGroups.from_rows(lags, _rows_like(k, seats, rounds), 3)
+    assert len(groups) == 20 and int(groups.counts.sum()) == 400
+    for g in range(len(groups)):
+        mine = [int(r) for s, r in zip(seats, rounds) if sorted(s) == groups.participants[g].tolist()]
+        acc = _online([float(v) for v in mine], lags)
+        for z, lag in enumerate(lags):
+            assert groups.stats[g, z].tolist() == acc[lag]
+    few = rd.MatchupLagGroups.from_rows(lags, _rows_like(k, seats[:30], rounds[:30]), 3)
+    assert 0 < len(few) < 20 and few.counts.min() >= 3
+    # the cap keeps the groups with the smallest priorities, across cells
+    other = rd.MatchupLagGroups.from_rows(lags, _rows_like(2, seats[:, :2], rounds), 3)
+    masks = rd.select_matchup_groups([groups, other], 4, cap=9)
+    assert sum(int(m.sum()) for m in masks) == 9
+    pri = np.concatenate([groups.priorities(4), other.priorities(4)])
+    kept = np.concatenate(masks)
+    assert pri[kept].max() < pri[~kept].min()
+    assert all(m.all() for m in rd.select_matchup_groups([groups, other], 4, cap=None))
+    rows = groups.rows(4, masks[0])
+    assert len(rows) == int(masks[0].sum()) * len(lags)
+    assert rows[0]["summary_level"] == "matchup" and rows[0]["metric"] == "n_rounds"
+    assert rows[0]["matchup"] == " | ".join(str(v) for v in rows[0]["participant_strategy_ids"])
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference checkout not present on this box")
+def test_matchup_identity_priority_and_rows_equal_reference(monkeypatch):
+    monkeypatch.syspath_prepend(str(REF))
+    import farkle.analysis.rng_diagnostics as ref
+
+    try:
+        rng = np.random.default_rng(8)
+        k, width, lags = 3, 5, (1, 3)
+        seats = np.array([rng.permutation(7)[:k] for _ in range(300)], dtype=np.int32)
+        rounds = rng.integers(5, 60, size=300)
+        groups = rd.MatchupLagGroups.from_rows(lags, _rows_like(k, seats, rounds), 4)
+        padded = np.full((len(groups), width), -1, dtype=np.int32)
+        padded[:, :k] = groups.participants
+        want_ids = ref._matchup_ids(np.full(len(groups), k, dtype=np.int16), padded)
+        assert np.array_equal(groups.group_ids(width), want_ids)
+        records = np.zeros(len(groups), dtype=ref._count_dtype(width))
+        records["group_type"], records["k"], records["group_id"] = ref._GROUP_MATCHUP, k, want_ids
+        assert np.array_equal(groups.priorities(width), ref._priority(records))
+        # selection order: the reference sorts (priority, group_type, k, group_id, p...) and cuts at the cap
+        top = np.zeros(len(groups), dtype=ref._priority_key_dtype(width))
+        top["priority"], top["group_type"], top["k"] = ref._priority(records), ref._GROUP_MATCHUP, k
+        top["group_id"] = want_ids
+        for c in range(width):
+            top[f"p{c}"] = padded[:, c]
+        cap = 11
+        want_keep = np.zeros(len(groups), dtype=bool)
+        want_keep[ref._priority_sort_order(top)[:cap]] = True
+        (mask,) = rd.select_matchup_groups([groups], width, cap=cap)
+        assert np.array_equal(mask, want_keep)
+        # report rows
+        mine = groups.rows(width, mask)
+        want = []
+        chosen = np.flatnonzero(mask)
+        for g in chosen[np.lexsort((*(groups.participants[chosen, c] for c in reversed(range(k))),
+                                    want_ids[chosen]))]:
+            acc = ref._OnlineMetric(lags)
+            for s, r in zip(seats, rounds):
+                if sorted(s) == groups.participants[g].tolist():
+                    acc.push(float(r))
+            want += ref._rows_for_online_group((ref._GROUP_MATCHUP, k, int(want_ids[g]), *padded[g].tolist()),
+                                               lags=lags, rounds=acc, wins=None)
+        assert mine == want
+    finally:
+        for name in [m for m in sys.modules if m == "farkle" or m.startswith("farkle.")]:
+            sys.modules.pop(name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,n_strat,nsh,min_obs,lags", [
+    (2, 80, 120, 3, (1, 2)),        # fast grid: 3,160 possible pairs, 4,800 games, exact keys
+    (4, 8, 150, 3, (1, 5)),         # 70 possible matchups, long groups, hashed keys
+    (3, 12, 40, 1, (2,)),           # every group eligible, many of size 1
+    (6, 12, 60, 2, (1,)),
+])
+def test_device_matchup_groups(k, n_strat, nsh, min_obs, lags):
+    from farkle_ii_b200.device import get_engine
+
+    eng = get_engine(0)
+    table = np.load(GOLDEN / "games_fast_42_2.npz")["strategies"][:n_strat]
+    res = eng.play_tournament(21, k, 4, nsh, table, lags=lags, matchup_min_observations=min_obs,
+                              want_rows=True, target_score=3000)
+    got = rd.MatchupLagGroups.from_launch(lags, res)
+    want = rd.MatchupLagGroups.from_rows(lags, res.rows_numpy(), min_obs)
+    assert len(got) == len(want) > 0
+    assert np.array_equal(got.participants, want.participants)
+    assert np.array_equal(got.counts, want.counts)
+    assert np.array_equal(got.stats, want.stats)
+    # strategy ids other than the table position flow into the participants
+    ids = (np.arange(n_strat, dtype=np.int32)[::-1] * 3 + 7).copy()
+    res2 = eng.play_tournament(21, k, 4, nsh, table, strategy_ids=ids, lags=lags,
+                               matchup_min_observations=min_obs, want_rows=True, target_score=3000,
+                               strategy_lags=False)
+    assert res2.lag_stats is None
+    got2 = rd.MatchupLagGroups.from_launch(lags, res2)
+    want2 = rd.MatchupLagGroups.from_rows(lags, res2.rows_numpy(), min_obs)
+    assert np.array_equal(got2.participants, want2.participants) and np.array_equal(got2.stats, want2.stats)
+
+
+@pytest.mark.gpu
+def test_device_matchup_groups_full_grid_k2():
+    """Full 5,160-strategy grid, k=2, 400 shuffles (1.03 M games over 13.3 M possible pairs):
+    the groups with >= 3 games, checked against a numpy grouping of the device's rows."""
+    from farkle_ii_b200.device import get_engine
+
+    eng = get_engine(0)
+    table = np.load(GOLDEN / "games_full_0_2.npz")["strategies"]
+    lags, nsh = (1,), 400
+    res = eng.play_tournament(5, 2, 0, nsh, table, lags=lags, matchup_min_observations=3, want_rows=True)
+    got = rd.MatchupLagGroups.from_launch(lags, res)
+    rows = res.rows_numpy()
+    ids = np.sort(rows["seats"]["strategy"], axis=1).astype(np.int64)
+    key = ids[:, 0] * len(table) + ids[:, 1]
+    order = np.argsort(key, kind="stable")
+    uniq, start, count = np.unique(key[order], return_index=True, return_counts=True)
+    keep = count >= 3
+    assert len(got) == int(keep.sum()) > 0
+    assert np.array_equal(got.participants[:, 0] * len(table) + got.participants[:, 1], uniq[keep])
+    assert np.array_equal(got.counts, count[keep])
+    r = rows["n_rounds"].astype(np.int64)[order]
+    for g in np.flatnonzero(keep)[:: max(int(keep.sum()) // 200, 1)]:      # a sample of the groups
+        seq = r[start[g]:start[g] + count[g]]
+        x, y = seq[:-1], seq[1:]
+        want = [len(x), x.sum(), y.sum(), (x * x).sum(), (y * y).sum(), (x * y).sum()]
+        at = int(np.searchsorted(uniq[keep], uniq[g]))
+        assert got.stats[at, 0].tolist() == want
