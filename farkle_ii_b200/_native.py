@@ -45,7 +45,7 @@ class LagRequest(C.Structure):
         ("matchup_capacity", C.c_uint64), ("matchup_participants_dev", C.c_void_p),
         ("matchup_count_dev", C.c_void_p), ("matchup_stats_dev", C.c_void_p),
         ("scratch_dev", C.c_void_p), ("scratch_bytes", C.c_size_t),
-        ("n_matchups_host", C.c_void_p),
+        ("n_matchups_host", C.c_void_p), ("first_seen_dev", C.c_void_p),
     ]
 
 

@@ -952,8 +952,11 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
     if (seat_tallies_dev && !tallies_dev) return fail(FB_ERR_BAD_ARG, "seat tallies need tallies_dev");
     LagParams L{};
     if (lag) {
-        if (lag->n_lags < 1 || lag->n_lags > FB_MAX_LAGS || !lag->lags || !tallies_dev)
-            return fail(FB_ERR_BAD_ARG, "lag statistics need 1..%d lags and tallies_dev", FB_MAX_LAGS);
+        if (!tallies_dev) return fail(FB_ERR_BAD_ARG, "lag statistics / first-seen ordinals need tallies_dev");
+        const bool wants_lags = lag->strategy_stats_dev || lag->strategy_edges_dev || lag->matchup_min_observations != 0;
+        if (lag->n_lags < 0 || lag->n_lags > FB_MAX_LAGS || (lag->n_lags > 0 && !lag->lags) ||
+            (lag->n_lags == 0 && wants_lags))
+            return fail(FB_ERR_BAD_ARG, "lag statistics need 1..%d lags", FB_MAX_LAGS);
         if ((lag->strategy_stats_dev != nullptr) != (lag->strategy_edges_dev != nullptr))
             return fail(FB_ERR_BAD_ARG, "strategy lag statistics need both the stats and the edges buffer");
         if (lag->matchup_min_observations < 0 ||
@@ -1050,6 +1053,8 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
     G.slotted = shuffles_per_slot > 0;
     G.tallies = F.tallies;
     G.seat_tallies = reinterpret_cast<unsigned long long*>(seat_tallies_dev);
+    G.first_seen = lag ? lag->first_seen_dev : nullptr;
+    if (G.first_seen) FB_CUDA(cudaMemsetAsync(G.first_seen, 0xff, (size_t)n_tally_ids * 4 * sizeof(uint32_t), stream));
     const int n_chunks = (n_shuffles + G.chunk - 1) / G.chunk;
     tally_gather_kernel<<<dim3(blocks_for((uint64_t)n_strategies, 128), (unsigned)n_chunks), 128, 0, stream>>>(G);
     rc = launch_check("tally_gather_kernel");

@@ -627,6 +627,7 @@ struct GatherParams {
     int slotted;  // 1: chunk c -> tally slot c, 0: single slot
     unsigned long long* tallies;
     unsigned long long* seat_tallies;  // [slots][ids][k][FB_SEAT_TALLY_WIDTH] or nullptr
+    uint32_t* first_seen;  // [ids][4] first ordinal of: win, exposure, completed exposure, safety exposure
 };
 
 __global__ void __launch_bounds__(128) tally_gather_kernel(const GatherParams G) {
@@ -635,6 +636,7 @@ __global__ void __launch_bounds__(128) tally_gather_kernel(const GatherParams G)
     const int c = blockIdx.y;
     const int j0 = c * G.chunk, j1 = min(j0 + G.chunk, G.n_shuffles);
     unsigned long long wins = 0, safety = 0, sum[10], sq[10];
+    uint32_t first[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
 #pragma unroll
     for (int m = 0; m < 10; m++) sum[m] = sq[m] = 0ull;
     for (int j = j0; j < j1; j++) {
@@ -644,6 +646,12 @@ __global__ void __launch_bounds__(128) tally_gather_kernel(const GatherParams G)
         const uint32_t hdr = __ldg(&G.header[game]);
         const bool is_safety = (hdr >> 16) & FB_ROW_SAFETY_LIMIT;
         const bool won = !is_safety && ((hdr >> 24) & 15u) == seat + 1u;
+        if (G.first_seen) {  // j ascends, so the first hit inside the chunk is the chunk's minimum
+            const uint32_t ord = (uint32_t)j * (uint32_t)G.n_strategies + pos;
+            if (won) first[0] = min(first[0], ord);
+            first[1] = min(first[1], ord);
+            first[is_safety ? 3 : 2] = min(first[is_safety ? 3 : 2], ord);
+        }
         if (G.seat_tallies) {  // per (strategy, seat): wins, exposures, completed, safety limit
             const int sid_s = G.strategy_ids ? G.strategy_ids[i] : i;
             unsigned long long* S = G.seat_tallies +
@@ -669,6 +677,11 @@ __global__ void __launch_bounds__(128) tally_gather_kernel(const GatherParams G)
         }
     }
     const int sid = G.strategy_ids ? G.strategy_ids[i] : i;
+    if (G.first_seen) {
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (first[q] != 0xffffffffu) atomicMin(&G.first_seen[(size_t)sid * 4 + q], first[q]);
+    }
     unsigned long long* T = G.tallies + ((size_t)(G.slotted ? c : 0) * G.n_tally_ids + sid) * FB_TALLY_WIDTH;
     if (wins) atomicAdd(&T[0], wins);
     if (safety) {  // move exposures from "completed" (added by exposure_kernel) to "safety limit"

@@ -65,6 +65,7 @@ class TournamentResult:
     matchup_participants: torch.Tensor | None = None  # int32 [groups, k] sorted strategy ids
     matchup_count: torch.Tensor | None = None         # int32 [groups] games
     matchup_stats: torch.Tensor | None = None         # int64 [groups, n_lags, MATCHUP_LAG_WIDTH]
+    first_seen: torch.Tensor | None = None    # int32 [ids, 4] first ordinal of win / seat / completed / safety
 
     def rows_numpy(self) -> np.ndarray:
         assert self.rows is not None
@@ -233,14 +234,17 @@ class Engine:
                         totals: torch.Tensor | None = None, want_seat_tallies: bool = False,
                         seat_tallies: torch.Tensor | None = None,
                         lags: tuple[int, ...] = (), matchup_min_observations: int = 0,
-                        strategy_lags: bool = True) -> TournamentResult:
+                        strategy_lags: bool = True, want_first_seen: bool = False) -> TournamentResult:
         """Enqueue shuffles ``shuffle0 .. shuffle0+n_shuffles-1`` of cell (root_seed, k).
 
         ``lags`` asks for the RNG lag statistics of the strategy groups (``lag_stats``
         int64 [n_strategies, n_lags, LAG_WIDTH] by table position, ``lag_edges`` uint32
         [n_strategies, 2, max(lags)]); ``matchup_min_observations`` > 0 adds the matchup
         groups with at least that many games (``matchup_participants`` / ``matchup_count`` /
-        ``matchup_stats``); see ``farkle_ii_b200.rng_diagnostics``.
+        ``matchup_stats``); see ``farkle_ii_b200.rng_diagnostics``.  ``want_first_seen`` adds
+        ``first_seen`` int32 [n_tally_ids, 4]: the first exposure ordinal at which an id won / was
+        seated / was seated in a completed / in a safety-limit game (-1 = never), i.e. the key
+        insertion order of the reference's counters.
 
         ``strategies`` is a device uint8 tensor holding ``fb_strategy_t`` entries, or a
         host STRATEGY_DTYPE array (copied).  ``tallies`` / ``totals`` may be passed to
@@ -281,12 +285,16 @@ class Engine:
             d_om = self.to_device(np.array([o[2] for o in ov], dtype=np.int32))
         ws_bytes = self.workspace_bytes(max(k, 1), n_games) + 2 * (n_shuffles * n_strategies * 4 + 256)
         ws = self.workspace(ws_bytes)
-        lag_stats = lag_edges = m_part = m_count = m_stats = None
+        lag_stats = lag_edges = m_part = m_count = m_stats = first_seen = None
         request = None
+        if lags or want_first_seen:
+            request = _native.LagRequest()
+        if want_first_seen:
+            first_seen = torch.empty((n_tally_ids, 4), dtype=torch.int32, device=self.device)
+            request.first_seen_dev = first_seen.data_ptr()
         if lags:
             lags_c = (C.c_int32 * len(lags))(*[int(v) for v in lags])
             n_found = C.c_int64(0)
-            request = _native.LagRequest()
             request.lags = C.cast(lags_c, C.c_void_p)
             request.n_lags = len(lags)
             if strategy_lags:
@@ -318,7 +326,7 @@ class Engine:
             found = int(n_found.value)
             m_part, m_count, m_stats = m_part[:found], m_count[:found], m_stats[:found]
         return TournamentResult(tallies if want_tallies else None, totals, rows, n_games, k, seat_tallies,
-                                lag_stats, lag_edges, m_part, m_count, m_stats)
+                                lag_stats, lag_edges, m_part, m_count, m_stats, first_seen)
 
     def play_games(self, coords: np.ndarray, k: int, seat_strategies: np.ndarray, *,
                    seat_strategy_ids=None, target_score: int = 10_000, max_rounds: int = 200,

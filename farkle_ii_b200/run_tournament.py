@@ -173,11 +173,24 @@ def _restore_outcome_counter(counts: dict, outcome_counts: dict[str, Any]) -> Ou
 MetricSums = Dict[str, Dict[Any, float]]
 
 
-def tallies_to_outcome(tallies: np.ndarray, ids: Sequence[int], games: Tuple[int, int, int]
+def tallies_to_outcome(tallies: np.ndarray, ids: Sequence[int], games: Tuple[int, int, int],
+                       first_seen: np.ndarray | None = None
                        ) -> Tuple[OutcomeCounter, MetricSums, MetricSums]:
     """``int64[n][26]`` -> ``(OutcomeCounter, sums, sq_sums)`` exactly as run_tournament.py:331-393
-    would have built them: keys exist only where the reference would have touched them."""
+    would have built them: keys exist only where the reference would have touched them, and --
+    given the launch's ``first_seen`` ordinals -- in the order the reference inserted them (first
+    win / first exposure in game and seat order), so that pickles of the merged counters come
+    out byte-identical.  Without ``first_seen`` keys are in table order."""
     t = np.asarray(tallies).reshape(-1, TALLY_WIDTH)
+    seen = None
+    if first_seen is not None:
+        seen = np.asarray(first_seen).reshape(-1, 4)
+        seen = seen.view(np.uint32) if seen.dtype == np.int32 else seen      # -1 = never sorts last
+
+    def touched(col: int, seen_col: int) -> np.ndarray:
+        rows = np.flatnonzero(t[:, col])
+        return rows if seen is None else rows[np.argsort(seen[rows, seen_col], kind="stable")]
+
     wins = OutcomeCounter()
     sums: MetricSums = {m: defaultdict(float) for m in METRIC_LABELS}
     sq_sums: MetricSums = {m: defaultdict(float) for m in METRIC_LABELS}
@@ -187,11 +200,11 @@ def tallies_to_outcome(tallies: np.ndarray, ids: Sequence[int], games: Tuple[int
         vals = t[rows, col]
         return dict(zip(ids[rows].tolist(), (vals.astype(np.float64) if as_float else vals).tolist()))
 
-    for col, target in ((T_ATTEMPTED, wins.attempted_exposures),
-                        (T_COMPLETED, wins.completed_exposures),
-                        (T_SAFETY, wins.safety_limit_exposures)):
-        target.update(column(np.flatnonzero(t[:, col]), col))
-    winners = np.flatnonzero(t[:, T_WINS])
+    for col, seen_col, target in ((T_ATTEMPTED, 1, wins.attempted_exposures),
+                                  (T_COMPLETED, 2, wins.completed_exposures),
+                                  (T_SAFETY, 3, wins.safety_limit_exposures)):
+        target.update(column(touched(col, seen_col), col))
+    winners = touched(T_WINS, 0)
     wins.update(column(winners, T_WINS))
     for m, label in enumerate(METRIC_LABELS):
         sums[label].update(column(winners, T_SUMS + m, as_float=True))
@@ -274,8 +287,8 @@ def _contiguous_runs(tasks: Sequence[ShuffleTask]) -> Iterator[Tuple[int, int]]:
 def _launch_run(state: WorkerState, tasks: Sequence[ShuffleTask], *, want_rows: bool):
     """One ``fb_play_tournament`` launch for a contiguous shuffle run.
 
-    Returns ``(tallies[n, 26], (attempted, completed, safety_limit), rows | None)`` as host
-    values for the whole run.
+    Returns ``(tallies[n, 26], (attempted, completed, safety_limit), rows | None,
+    first_seen[n, 4])`` as host values for the whole run.
     """
     from .device import get_engine
 
@@ -291,15 +304,16 @@ def _launch_run(state: WorkerState, tasks: Sequence[ShuffleTask], *, want_rows: 
         max_rounds=prof.default_max_rounds if prof else 200,
         overrides=(prof.tournament_overrides_for(first.root_seed, k, first.shuffle_index, n)
                    if prof else ()),
-        want_rows=want_rows, want_game_seeds=want_rows)
+        want_rows=want_rows, want_game_seeds=want_rows, want_first_seen=True)
     tallies = res.tallies.cpu().numpy()[0]
+    first_seen = res.first_seen.cpu().numpy()
     totals = res.totals.cpu().numpy()
     rows = res.rows_numpy() if res.rows is not None else None
     if rows is not None:
         check_row_flags(rows)
     elif totals[7]:
         raise RuntimeError("a game hit ROLL_LIMIT or overflowed an int16 row counter")
-    return tallies, (int(totals[0]), int(totals[1]), int(totals[2])), rows
+    return tallies, (int(totals[0]), int(totals[1]), int(totals[2])), rows, first_seen
 
 
 def _expand_shuffle_rows(state: WorkerState, task: ShuffleTask, rows: np.ndarray) -> List[Dict[str, Any]]:
@@ -321,8 +335,8 @@ def _play_one_shuffle(task: ShuffleTask | int, *, collect_rows: bool = False) ->
     """Play all games of one shuffle and aggregate the results (run_tournament.py:301-393)."""
     state = _require_state()
     work = _coerce_shuffle_task(task)
-    tallies, games, rows = _launch_run(state, [work], want_rows=collect_rows)
-    wins, sums, sq_sums = tallies_to_outcome(tallies, state.ids, games)
+    tallies, games, rows, seen = _launch_run(state, [work], want_rows=collect_rows)
+    wins, sums, sq_sums = tallies_to_outcome(tallies, state.ids, games, seen)
     out_rows = _expand_shuffle_rows(state, work, rows) if collect_rows else []
     return wins, sums, sq_sums, out_rows
 
@@ -339,8 +353,8 @@ def _run_chunk(shuffle_tasks: Sequence[ShuffleTask | int]) -> Counter:
     tasks = [_coerce_shuffle_task(t) for t in shuffle_tasks]
     total = OutcomeCounter()
     for a, b in _contiguous_runs(tasks):
-        tallies, games, _ = _launch_run(state, tasks[a:b], want_rows=False)
-        wins, _, _ = tallies_to_outcome(tallies, state.ids, games)
+        tallies, games, _, seen = _launch_run(state, tasks[a:b], want_rows=False)
+        wins, _, _ = tallies_to_outcome(tallies, state.ids, games, seen)
         total.absorb(wins)
     return total
 
@@ -428,8 +442,8 @@ def _run_chunk_metrics(shuffle_tasks: Sequence[ShuffleTask | int], *, collect_ro
     gps = state.cfg.games_per_shuffle
     for a, b in _contiguous_runs(tasks):
         run = tasks[a:b]
-        tallies, games, rows = _launch_run(state, run, want_rows=want_rows)
-        wins, sums, sqs = tallies_to_outcome(tallies, state.ids, games)
+        tallies, games, rows, seen = _launch_run(state, run, want_rows=want_rows)
+        wins, sums, sqs = tallies_to_outcome(tallies, state.ids, games, seen)
         wins_total.absorb(wins)
         for label in METRIC_LABELS:
             for key, v in sums[label].items():
@@ -499,38 +513,56 @@ def all_reduce_tallies(tallies, totals):
 
 
 def run_cell(root_seed: int, k: int, num_shuffles: int, table, *, batch_size: int,
-             launch: Callable[..., Tuple[Any, Any]], rank: int = 0, world: int = 1,
-             max_shuffles_per_launch: int = 1 << 20):
+             launch: Callable[..., Tuple[Any, ...]], rank: int = 0, world: int = 1,
+             max_shuffles_per_launch: int = 1 << 20, want_first_seen: bool = False):
     """Play this rank's share of a (root, k) cell and merge.
 
     ``launch(root_seed, k, shuffle0, n_shuffles, table, tallies, totals)`` accumulates into
     the ``int64`` tensors it is given (``Engine.play_tournament`` on a GPU; the tests pass a
-    CPU stand-in).  Returns the merged ``(tallies[1, n, 26], totals[20])`` tensors.
+    CPU stand-in).  Returns the merged ``(tallies[1, n, 26], totals[20])`` tensors; with
+    ``want_first_seen`` the launch also returns its ``first_seen`` ordinals and the result
+    gains the cell-wide ``int64 [n, 4]`` first-seen table (MIN over launches and ranks; the
+    key order of the reference's counters, see ``tallies_to_outcome``).
     """
     import torch
+    import torch.distributed as dist
 
     from .layout import TOTALS_WIDTH
 
     n = len(table) if isinstance(table, np.ndarray) else table.numel() // 8
-    tallies = totals = None
+    never = torch.iinfo(torch.int64).max
+    tallies = totals = seen = None
     for s0, cnt in merge_ranges(shard_batches(num_shuffles, batch_size, rank, world)):
         while cnt > 0:
             step = min(cnt, max_shuffles_per_launch)
-            tallies, totals = launch(root_seed, k, s0, step, table, tallies, totals)
+            out = launch(root_seed, k, s0, step, table, tallies, totals)
+            tallies, totals = out[0], out[1]
+            if want_first_seen:
+                local = out[2].to(torch.int64)          # int32, -1 = never, else ordinal in the launch
+                glob = torch.where(local < 0, torch.full_like(local, never),
+                                   (local & 0xFFFFFFFF) + s0 * n)
+                seen = glob if seen is None else torch.minimum(seen, glob)
             s0 += step
             cnt -= step
+    dev = table.device if hasattr(table, "device") else "cpu"
     if tallies is None:  # a rank that owns no batch still takes part in the reduction
-        dev = table.device if hasattr(table, "device") else "cpu"
         tallies = torch.zeros((1, n, TALLY_WIDTH), dtype=torch.int64, device=dev)
         totals = torch.zeros(TOTALS_WIDTH, dtype=torch.int64, device=dev)
-    return all_reduce_tallies(tallies, totals)
+    tallies, totals = all_reduce_tallies(tallies, totals)
+    if not want_first_seen:
+        return tallies, totals
+    if seen is None:
+        seen = torch.full((n, 4), never, dtype=torch.int64, device=dev)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(seen, op=dist.ReduceOp.MIN)
+    return tallies, totals, seen
 
 
 def _engine_launch(eng, want_kw: Mapping[str, Any]):
     def launch(root_seed, k, shuffle0, n_shuffles, table, tallies, totals):
         res = eng.play_tournament(root_seed, k, shuffle0, n_shuffles, table, tallies=tallies,
-                                  totals=totals, **want_kw)
-        return res.tallies, res.totals
+                                  totals=totals, want_first_seen=True, **want_kw)
+        return res.tallies, res.totals, res.first_seen
     return launch
 
 
@@ -591,22 +623,24 @@ def run_tournament(*, config: TournamentConfig | None = None, global_seed: int =
 
         def launch(root_seed, kk, s0, n, table, tallies, totals):
             res = eng.play_tournament(root_seed, kk, s0, n, table, tallies=tallies, totals=totals,
-                                      overrides=prof.tournament_overrides_for(root_seed, kk, s0, n), **kw)
-            return res.tallies, res.totals
+                                      overrides=prof.tournament_overrides_for(root_seed, kk, s0, n),
+                                      want_first_seen=True, **kw)
+            return res.tallies, res.totals, res.first_seen
     else:
         kw = dict(target_score=prof.default_target_score, max_rounds=prof.default_max_rounds) if prof else {}
         launch = _engine_launch(eng, kw)
     table_dev = eng.to_device(state.table)
-    tallies, totals = run_cell(root, k, cfg.num_shuffles, table_dev,
-                               batch_size=cfg.deterministic_batch_size, launch=launch, rank=rank,
-                               world=world)
+    tallies, totals, seen = run_cell(root, k, cfg.num_shuffles, table_dev,
+                                     batch_size=cfg.deterministic_batch_size, launch=launch, rank=rank,
+                                     world=world, want_first_seen=True)
     torch.cuda.synchronize(eng.device)
     if rank != 0:
         return
     tot = totals.cpu().numpy()
     if tot[7]:
         raise RuntimeError("a game hit ROLL_LIMIT or overflowed an int16 row counter")
-    wins, sums, sqs = tallies_to_outcome(tallies.cpu().numpy()[0], state.ids, tuple(tot[:3]))
+    wins, sums, sqs = tallies_to_outcome(tallies.cpu().numpy()[0], state.ids, tuple(tot[:3]),
+                                         seen.cpu().numpy())
     payload: Dict[str, Any] = {"win_totals": wins, "outcome_counts": wins.outcome_payload()}
     if collect_metrics or collect_rows:
         payload["metric_sums"] = {m: dict(v) for m, v in sums.items()}

@@ -156,7 +156,7 @@ typedef struct fb_row_seat {
 
 typedef struct fb_lag_request {
     const int32_t* lags;          /* HOST array: n_lags distinct lags in [1, FB_MAX_LAG]   */
-    int32_t n_lags;               /* 1..FB_MAX_LAGS                                          */
+    int32_t n_lags;               /* 1..FB_MAX_LAGS; 0 = no lag statistics at all            */
     int32_t matchup_min_observations; /* 0 = no matchup groups                               */
     int64_t* strategy_stats_dev;  /* accumulated into (caller zeroes); NULL = skip strategy groups */
     uint32_t* strategy_edges_dev; /* overwritten; required with strategy_stats_dev           */
@@ -167,6 +167,13 @@ typedef struct fb_lag_request {
     void* scratch_dev;            /* >= fb_matchup_scratch_bytes(n_games) when matchups are on */
     size_t scratch_bytes;
     int64_t* n_matchups_host;     /* HOST out: groups written; the call synchronises `stream` */
+    /* Independent of the lags (n_lags may be 0 when only this is wanted): uint32[n_tally_ids][4],
+     * overwritten -- the first exposure ordinal (shuffle - shuffle0) * n_strategies + game * k + seat
+     * at which the id  0: won  1: was seated  2: was seated in a completed game  3: was seated in a
+     * safety-limit game;  0xFFFFFFFF = never.  It is the insertion order of the reference's
+     * Counter / dict keys (run_tournament.py:177-195,375-391), which a byte-identical checkpoint
+     * pickle needs.                                                                           */
+    uint32_t* first_seen_dev;
 } fb_lag_request_t;
 
 /* Per-launch totals, int64[FB_TOTALS_WIDTH]:
@@ -283,8 +290,9 @@ int fb_play_tournament_seats(uint64_t root_seed, int k, uint64_t shuffle0, int n
                              void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* fb_play_tournament_seats plus the RNG lag statistics (layouts above) of the strategy groups
- * and / or the matchup groups of the launch.  Needs tallies_dev (the winner marks and inverse
- * permutations come with it).  lag == NULL is plain fb_play_tournament_seats.        */
+ * and / or the matchup groups of the launch, and / or the first-seen ordinals.  Needs
+ * tallies_dev (the winner marks and inverse permutations come with it).  lag == NULL is plain
+ * fb_play_tournament_seats.                                                          */
 int fb_play_tournament_lags(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
                             const fb_strategy_t* strategies_dev, const int32_t* strategy_ids_dev,
                             int n_strategies, int n_tally_ids, int32_t target_score,

@@ -28,6 +28,7 @@ class _Result:
     seat_tallies: torch.Tensor | None = None
     lag_stats: torch.Tensor | None = None
     lag_edges: torch.Tensor | None = None
+    first_seen: torch.Tensor | None = None
 
     def rows_numpy(self) -> np.ndarray:
         return self.rows.numpy().view(row_dtype(self.k)).reshape(-1)
@@ -48,7 +49,20 @@ class OracleEngine:
     def play_tournament(self, root_seed, k, shuffle0, n_shuffles, strategies, *, strategy_ids=None,
                         n_tally_ids=None, target_score=10_000, max_rounds=200, overrides=(),
                         shuffles_per_slot=0, want_tallies=True, want_rows=False,
-                        want_game_seeds=False, tallies=None, totals=None, lags=()):
+                        want_game_seeds=False, tallies=None, totals=None, lags=(),
+                        want_first_seen=False):
+        if want_first_seen and not lags:
+            res = self.play_tournament(root_seed, k, shuffle0, n_shuffles, strategies,
+                                       strategy_ids=strategy_ids, n_tally_ids=n_tally_ids,
+                                       target_score=target_score, max_rounds=max_rounds, overrides=overrides,
+                                       shuffles_per_slot=shuffles_per_slot, want_tallies=want_tallies,
+                                       want_rows=True, want_game_seeds=want_game_seeds, tallies=tallies,
+                                       totals=totals)
+            res.first_seen = torch.from_numpy(self._first_seen(res.rows_numpy(), len(_table(strategies)), k,
+                                                               strategy_ids))
+            if not want_rows:
+                res.rows = None
+            return res
         if lags:
             return self._with_lags(root_seed, k, shuffle0, n_shuffles, strategies, target_score, max_rounds,
                                    tuple(lags))
@@ -66,6 +80,27 @@ class OracleEngine:
             to = totals
         r = None if rows is None else torch.from_numpy(rows.view(np.uint8).reshape(len(rows), -1))
         return _Result(tt if want_tallies else None, to, r, len(rows) if rows is not None else 0, k)
+
+    @staticmethod
+    def _first_seen(rows, n, k, strategy_ids):
+        """First ordinal of: win, exposure, completed exposure, safety-limit exposure, per tally id."""
+        ids = np.arange(n) if strategy_ids is None else np.asarray(strategy_ids)
+        seen = np.full((int(ids.max()) + 1, 4), -1, dtype=np.int64)
+        gps = n // k
+
+        def note(sid, col, ordinal):
+            if seen[sid, col] < 0:
+                seen[sid, col] = ordinal
+        for g, row in enumerate(rows):
+            safety = bool(row["flags"] & 1)
+            for s in range(k):
+                sid = int(row["seats"]["strategy"][s])
+                ordinal = (g // gps) * n + (g % gps) * k + s
+                note(sid, 1, ordinal)
+                note(sid, 3 if safety else 2, ordinal)
+                if not safety and int(row["winner_seat"]) == s:
+                    note(sid, 0, ordinal)
+        return seen.astype(np.int32)
 
     def _with_lags(self, root_seed, k, shuffle0, n_shuffles, strategies, target_score, max_rounds, lags):
         """Lag sums the slow way: one accumulator walk per strategy over the oracle's rows."""

@@ -578,3 +578,26 @@ def test_random_tables_fuzz(eng):
         assert res.rows_numpy().tobytes() == want_rows.tobytes(), case
         assert np.array_equal(res.tallies.cpu().numpy().sum(axis=0), want_t[0]), case
         assert np.array_equal(res.totals.cpu().numpy(), want_tot), case
+
+
+@pytest.mark.parametrize("name,with_ids", [("fast_54_4", False), ("fast_42_2", True), ("full_0_5", False),
+                                           ("full_0_2", False)])
+def test_first_seen_ordinals(eng, golden_dir, name, with_ids):
+    """`first_seen` (key insertion order of the reference's counters): first win / exposure /
+    completed / safety-limit exposure ordinal per id == a walk over the rows in game and seat order."""
+    from oracle_engine import OracleEngine
+
+    z = np.load(golden_dir / f"games_{name}.npz")
+    root, k, sh0, nsh = (int(x) for x in z["meta"])
+    table = z["strategies"]
+    ids = (np.arange(len(table), dtype=np.int32)[::-1] * 2 + 5).copy() if with_ids else None
+    res = eng.play_tournament(root, k, sh0, nsh, table, strategy_ids=ids, want_first_seen=True, want_rows=True)
+    want = OracleEngine._first_seen(res.rows_numpy(), len(table), k, ids)
+    got = res.first_seen.cpu().numpy()
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert (got[:, 1] >= 0).sum() == len(table)          # every strategy is seated in the first shuffle
+    assert sorted(got[got[:, 1] >= 0, 1].tolist()) == list(range(len(table)))
+    # slotted tallies and several gather chunks do not change it
+    res2 = eng.play_tournament(root, k, sh0, nsh, table, strategy_ids=ids, want_first_seen=True,
+                               shuffles_per_slot=2)
+    assert np.array_equal(res2.first_seen.cpu().numpy(), want)

@@ -222,3 +222,89 @@ def test_plan_and_limits_match_reference_modules(ref_rt):
                 mod.TournamentMaxRoundsOverride(*bad)
             msgs.append(str(err.value))
         assert msgs[0] == msgs[1]
+
+
+_RUNNER_SCRIPT = """
+import os, sys
+os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/nbcache")
+ref_src, overlay, use_shim, repo = sys.argv[1], sys.argv[2], sys.argv[3] == "1", sys.argv[4]
+sys.path.insert(0, ref_src)
+from pathlib import Path
+from farkle.config import load_app_config
+from farkle.simulation import runner
+if use_shim:
+    sys.path.insert(0, repo)
+    sys.path.insert(0, os.path.join(repo, "tests"))
+    import farkle.simulation.run_tournament as rt
+    from farkle_ii_b200 import device as fdev, reference_shim
+    from oracle_engine import OracleEngine
+    eng = OracleEngine()
+    fdev.get_engine = lambda device=None: eng
+    reference_shim.install(rt)
+cfg = load_app_config(Path(ref_src).parent / "configs" / "fast_config.yaml", Path(overlay))
+print("games", runner.run_tournament(cfg))
+"""
+
+_OVERLAY = """
+io:
+  results_dir_prefix: "{prefix}"
+sim:
+  n_players_list: [2, 4]
+  seed: 42
+  seed_list: [42]
+  n_jobs: 1
+batching:
+  target_batches: 2
+  min_shuffles_per_batch: 5
+screening:
+  resolution_delta: 0.5
+resources:
+  logical_cpu_budget: 2
+  scheduler_memory_budget_mb: 2048
+  process_tree_warning_threshold_mb: 4096
+  aggregate_memory_hard_limit_mb: 6144
+  minimum_system_available_memory_mb: 256
+  os_memory_limit_enabled: false
+  os_memory_limit_required: false
+  allow_unenforced_memory_fallback: true
+"""
+
+
+def test_runner_artifact_tree_is_byte_identical(tmp_path):
+    """The reference's L4 runner (`farkle run`: `simulation.runner.run_tournament(cfg)`, fast grid,
+    k = 2 and 4, rows + expanded metrics, artifact contract v3) writes the SAME BYTES in every file
+    -- row shards, manifests, metrics / checkpoint Parquets, checkpoint pickle, hash-bound sidecars,
+    workload plan, `simulation.done.json` -- with this repo's seams installed as it does alone.
+    Runs an unmodified, git-initialised copy of the checkout in two subprocesses."""
+    import shutil
+    import subprocess
+
+    if shutil.which("git") is None:
+        pytest.skip("git not available")
+    ref = tmp_path / "ref"
+    ref.mkdir()
+    for name in ("src", "configs", "pyproject.toml"):
+        src = REF.parent / name
+        (shutil.copytree if src.is_dir() else shutil.copy)(src, ref / name)
+    outs = {}
+    for tag in ("cpu", "gpu"):
+        outs[tag] = tmp_path / f"out_{tag}"
+        (ref / f"overlay_{tag}.yaml").write_text(_OVERLAY.format(prefix=outs[tag] / "res"))
+    (ref / "drive.py").write_text(_RUNNER_SCRIPT)
+    git = ["git", "-c", "user.email=t@example.org", "-c", "user.name=t"]
+    subprocess.run([*git, "init", "-q"], cwd=ref, check=True)
+    subprocess.run([*git, "add", "-A"], cwd=ref, check=True)
+    subprocess.run([*git, "commit", "-qm", "reference copy"], cwd=ref, check=True)
+    repo = str(Path(__file__).resolve().parents[1])
+    for tag, shim in (("cpu", "0"), ("gpu", "1")):
+        done = subprocess.run([sys.executable, str(ref / "drive.py"), str(ref / "src"),
+                               str(ref / f"overlay_{tag}.yaml"), shim, repo],
+                              cwd=ref, capture_output=True, text=True, timeout=600)
+        assert done.returncode == 0, done.stderr[-2000:]
+        assert "games 720" in done.stdout            # 12 shuffles x (40 + 20) games
+    root_a, root_b = outs["cpu"] / "res_seed_42", outs["gpu"] / "res_seed_42"
+    files = sorted(p.relative_to(root_a) for p in root_a.rglob("*") if p.is_file())
+    assert files == sorted(p.relative_to(root_b) for p in root_b.rglob("*") if p.is_file())
+    assert len(files) > 60 and any(f.name == "simulation.done.json" for f in files)
+    different = [str(f) for f in files if (root_a / f).read_bytes() != (root_b / f).read_bytes()]
+    assert different == []
