@@ -194,21 +194,27 @@ def tallies_to_outcome(tallies: np.ndarray, ids: Sequence[int], games: Tuple[int
     wins = OutcomeCounter()
     sums: MetricSums = {m: defaultdict(float) for m in METRIC_LABELS}
     sq_sums: MetricSums = {m: defaultdict(float) for m in METRIC_LABELS}
-    ids = np.asarray([int(i) for i in ids], dtype=object)
+    id_list = np.asarray(ids).tolist()           # python ints, as the reference's keys are
 
-    def column(rows: np.ndarray, col: int, as_float: bool = False) -> dict:
+    def column(rows: np.ndarray, keys: list, col: int, as_float: bool = False) -> dict:
         vals = t[rows, col]
-        return dict(zip(ids[rows].tolist(), (vals.astype(np.float64) if as_float else vals).tolist()))
+        return dict(zip(keys, (vals.astype(np.float64) if as_float else vals).tolist()))
+
+    def keys_of(rows: np.ndarray) -> list:
+        return [id_list[r] for r in rows.tolist()]
 
     for col, seen_col, target in ((T_ATTEMPTED, 1, wins.attempted_exposures),
                                   (T_COMPLETED, 2, wins.completed_exposures),
                                   (T_SAFETY, 3, wins.safety_limit_exposures)):
-        target.update(column(touched(col, seen_col), col))
+        rows = touched(col, seen_col)
+        target.update(column(rows, keys_of(rows), col))
     winners = touched(T_WINS, 0)
-    wins.update(column(winners, T_WINS))
+    win_keys = keys_of(winners)                  # one key list shared by the 23 winner dicts
+    wins.update(column(winners, win_keys, T_WINS))
+    block = t[winners, T_SUMS:T_SUMS + 2 * len(METRIC_LABELS)].astype(np.float64).T.tolist()
     for m, label in enumerate(METRIC_LABELS):
-        sums[label].update(column(winners, T_SUMS + m, as_float=True))
-        sq_sums[label].update(column(winners, T_SQ_SUMS + m, as_float=True))
+        sums[label].update(zip(win_keys, block[m]))
+        sq_sums[label].update(zip(win_keys, block[T_SQ_SUMS - T_SUMS + m]))
     wins.games_attempted, wins.games_completed, wins.games_safety_limit = (int(x) for x in games)
     return wins, sums, sq_sums
 
