@@ -367,23 +367,54 @@ def strategy_lag_state(root_seed: int, k: int, shuffle0: int, n_shuffles: int, s
     return state
 
 
-def gather_lag_states(state: StrategyLagState) -> StrategyLagState:
-    """Join the states of all ranks in rank order (rank r holds the r-th contiguous shuffle
-    range of the cell, as ``run_tournament.shard_batches`` deals them).  Every rank gets the
-    result.  Payload per rank: the sums and 2 x max_lag observations per strategy."""
-    import torch.distributed as dist
-
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return state
-    parts: list[Any] = [None] * dist.get_world_size()
-    dist.all_gather_object(parts, state)
-    joined = parts[0]
-    for part in parts[1:]:
+def join_lag_segments(segments: Sequence[tuple[int, StrategyLagState]]) -> StrategyLagState:
+    """Join ``(first shuffle, state)`` segments that together tile a run of shuffles."""
+    ordered = sorted(segments, key=lambda seg: seg[0])
+    if not ordered:
+        raise ValueError("no lag segments to join")
+    at, joined = ordered[0][0] + ordered[0][1].n_obs, ordered[0][1]
+    for s0, part in ordered[1:]:
+        if s0 != at:
+            raise ValueError(f"lag segments do not tile the shuffle range: expected {at}, got {s0}")
         joined = joined.extend(part)
+        at += part.n_obs
     return joined
 
 
+def gather_lag_segments(segments: Sequence[tuple[int, StrategyLagState]]) -> StrategyLagState:
+    """All ranks' segments joined in shuffle order; every rank gets the result.  Payload per
+    segment: the sums and 2 x max_lag observations per strategy (the path's tallies travel by
+    all-reduce; these small states by one all-gather)."""
+    import torch.distributed as dist
+
+    everything = list(segments)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        parts: list[Any] = [None] * dist.get_world_size()
+        dist.all_gather_object(parts, list(segments))
+        everything = [seg for part in parts for seg in part]
+    return join_lag_segments(everything)
+
+
+def cell_lag_state(root_seed: int, k: int, num_shuffles: int, strategies: Any,
+                   lags: Sequence[int] | None = None, *, batch_size: int, rank: int = 0, world: int = 1,
+                   engine: Any = None, device: int | None = None, **limits: int) -> StrategyLagState:
+    """Strategy-group lag state of a whole (root, k) cell played the way ``run_cell`` shards it:
+    deterministic batches dealt round-robin over the ranks, one launch per contiguous run, the
+    per-launch states gathered and joined in shuffle order."""
+    from . import device as fdev
+    from .run_tournament import merge_ranges, shard_batches
+
+    lags = normalize_lags(lags)
+    eng = engine if engine is not None else fdev.get_engine(device)
+    segments = []
+    for s0, cnt in merge_ranges(shard_batches(num_shuffles, batch_size, rank, world)):
+        res = eng.play_tournament(root_seed, k, s0, cnt, strategies, lags=lags, **limits)
+        segments.append((s0, StrategyLagState.from_launch(lags, cnt, res.lag_stats, res.lag_edges)))
+    return gather_lag_segments(segments)
+
+
 __all__ = ["DEFAULT_MAX_MATCHUP_GROUPS", "EXPECTED_NOTE", "MATCHUP_SEQUENCE_ORDER", "MatchupLagGroups",
-           "STRATEGY_SEQUENCE_ORDER", "StrategyLagState", "gather_lag_states", "matchup_group_ids",
+           "STRATEGY_SEQUENCE_ORDER", "StrategyLagState", "cell_lag_state", "gather_lag_segments",
+           "join_lag_segments", "matchup_group_ids",
            "minimum_observations", "normalize_lags", "observations_from_rows", "select_matchup_groups",
            "strategy_lag_state"]

@@ -62,8 +62,24 @@ def _worker(rank: int, world: int, port: int, num_shuffles: int, batch: int, out
 
         tallies, totals = frt.run_cell(42, 2, num_shuffles, table, batch_size=batch, launch=launch,
                                        rank=dist.get_rank(), world=dist.get_world_size())
+        # the counters' key order (MIN over ranks) and the lag state (all-gather + join in order)
+        from farkle_ii_b200 import rng_diagnostics as rd
+        from oracle_engine import OracleEngine
+
+        eng = OracleEngine()
+
+        def launch_seen(root_seed, k, s0, n, tab, tallies, totals):
+            res = eng.play_tournament(root_seed, k, s0, n, tab, tallies=tallies, totals=totals,
+                                      want_first_seen=True)
+            return res.tallies, res.totals, res.first_seen
+
+        _, _, seen = frt.run_cell(42, 2, num_shuffles, table, batch_size=batch, launch=launch_seen,
+                                  rank=dist.get_rank(), world=dist.get_world_size(), want_first_seen=True)
+        lag = rd.cell_lag_state(42, 2, num_shuffles, table, (1, 3), batch_size=batch, rank=dist.get_rank(),
+                                world=dist.get_world_size(), engine=eng) if num_shuffles >= batch else None
         np.savez(Path(out_dir) / f"rank{rank}.npz", tallies=tallies.numpy(), totals=totals.numpy(),
-                 launches=np.array(launches, dtype=np.int64).reshape(-1, 2))
+                 launches=np.array(launches, dtype=np.int64).reshape(-1, 2), seen=seen.numpy(),
+                 lag_stats=lag.stats if lag else np.zeros(0), lag_tail=lag.tail if lag else np.zeros(0))
     finally:
         dist.destroy_process_group()
 
@@ -85,6 +101,20 @@ def test_two_ranks_equal_one(tmp_path, num_shuffles, batch):
     for r in (r0, r1):                                   # every rank holds the merged cell
         assert np.array_equal(r["tallies"], want_t)
         assert np.array_equal(r["totals"], want_tot)
+    from farkle_ii_b200 import rng_diagnostics as rd
+    from oracle_engine import OracleEngine
+
+    whole = OracleEngine().play_tournament(42, 2, 0, num_shuffles, table, want_first_seen=True, lags=())
+    want_seen = whole.first_seen.numpy().astype(np.int64)
+    want_seen[want_seen < 0] = np.iinfo(np.int64).max
+    for r in (r0, r1):
+        assert np.array_equal(r["seen"], want_seen)
+    if num_shuffles >= batch:
+        res = OracleEngine().play_tournament(42, 2, 0, num_shuffles, table, lags=(1, 3))
+        want_lag = rd.StrategyLagState.from_launch((1, 3), num_shuffles, res.lag_stats, res.lag_edges)
+        for r in (r0, r1):
+            assert np.array_equal(r["lag_stats"], want_lag.stats)
+            assert np.array_equal(r["lag_tail"], want_lag.tail)
     played = sorted(s for r in (r0, r1) for s0, n in r["launches"] for s in range(s0, s0 + n))
     assert played == list(range(num_shuffles))           # disjoint and complete
     if num_shuffles <= batch:
