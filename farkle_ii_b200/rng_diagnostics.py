@@ -327,6 +327,34 @@ def select_matchup_groups(cells: Sequence[MatchupLagGroups], max_players: int,
     return masks
 
 
+def diagnostics_schema():
+    """Arrow schema of ``rng_diagnostics.parquet`` (``_stats_schema``, :2079-2098)."""
+    import pyarrow as pa
+
+    text, f64 = pa.string(), pa.float64()
+    return pa.schema([
+        pa.field("summary_level", text, nullable=False), pa.field("strategy", pa.int32()),
+        pa.field("matchup_id", pa.uint64()), pa.field("matchup", text),
+        pa.field("participant_strategy_ids", pa.list_(pa.int32())),
+        pa.field("n_players", pa.int16(), nullable=False),
+        pa.field("observations", pa.int64(), nullable=False),
+        pa.field("lagged_pairs", pa.int64(), nullable=False), pa.field("lag", pa.int32(), nullable=False),
+        pa.field("metric", text, nullable=False), pa.field("autocorr", f64),
+        pa.field("estimability_status", text, nullable=False),
+        pa.field("zero_centered_descriptive_reference_band_lower", f64),
+        pa.field("zero_centered_descriptive_reference_band_upper", f64),
+        pa.field("sequence_order", text, nullable=False), pa.field("note", text, nullable=False),
+    ])
+
+
+def diagnostics_table(rows: Sequence[dict[str, Any]]):
+    """Report rows (``StrategyLagState.rows`` / ``MatchupLagGroups.rows``) as the Arrow table the
+    reference writes (``pa.Table.from_pylist(rows, schema=_stats_schema())``, :2162-2207)."""
+    import pyarrow as pa
+
+    return pa.Table.from_pylist(list(rows), schema=diagnostics_schema())
+
+
 def observations_from_rows(rows: np.ndarray, n_strategies: int, n_shuffles: int) -> np.ndarray:
     """``[n_strategies, n_shuffles]`` observation words rebuilt from compact rows whose seat
     ``strategy`` field holds the TABLE position (no strategy_ids); used to check the kernel."""
@@ -414,7 +442,8 @@ def cell_lag_state(root_seed: int, k: int, num_shuffles: int, strategies: Any,
 
 
 __all__ = ["DEFAULT_MAX_MATCHUP_GROUPS", "EXPECTED_NOTE", "MATCHUP_SEQUENCE_ORDER", "MatchupLagGroups",
-           "STRATEGY_SEQUENCE_ORDER", "StrategyLagState", "cell_lag_state", "gather_lag_segments",
+           "STRATEGY_SEQUENCE_ORDER", "StrategyLagState", "cell_lag_state", "diagnostics_schema",
+           "diagnostics_table", "gather_lag_segments",
            "join_lag_segments", "matchup_group_ids",
            "minimum_observations", "normalize_lags", "observations_from_rows", "select_matchup_groups",
            "strategy_lag_state"]

@@ -111,6 +111,10 @@ def test_rows_equal_reference_rows(monkeypatch):
         assert mine == want                                   # floats compared by value: bit-identical
         assert rd.normalize_lags([3, 1, 3]) == ref._normalize_lags([3, 1, 3])
         assert rd.EXPECTED_NOTE == ref._EXPECTED_NOTE
+        import pyarrow as pa
+
+        assert rd.diagnostics_schema().equals(ref._stats_schema(), check_metadata=True)
+        assert rd.diagnostics_table(mine).equals(pa.Table.from_pylist(want, schema=ref._stats_schema()))
     finally:
         for name in [m for m in sys.modules if m == "farkle" or m.startswith("farkle.")]:
             sys.modules.pop(name)
