@@ -427,7 +427,7 @@ def cell_lag_state(root_seed: int, k: int, num_shuffles: int, strategies: Any,
                    lags: Sequence[int] | None = None, *, batch_size: int, rank: int = 0, world: int = 1,
                    engine: Any = None, device: int | None = None, **limits: int) -> StrategyLagState:
     """Strategy-group lag state of a whole (root, k) cell played the way ``run_cell`` shards it:
-    deterministic batches dealt round-robin over the ranks, one launch per contiguous run, the
+    deterministic batches dealt in contiguous blocks over the ranks, one launch per contiguous run, the
     per-launch states gathered and joined in shuffle order."""
     from . import device as fdev
     from .run_tournament import merge_ranges, shard_batches

@@ -16,7 +16,7 @@ Same names, same argument meaning, same return types.  The bodies differ: a chun
 shuffles is ONE ``fb_play_tournament`` launch (contiguous shuffle runs), the per-strategy
 tallies come back as an ``int64[ids][26]`` tensor and are unpacked into the reference's
 ``OutcomeCounter`` / ``dict[label][strategy] -> float`` shapes.  With ``torch.distributed``
-initialised, ``run_tournament`` shards deterministic batches round-robin over ranks and
+initialised, ``run_tournament`` deals deterministic batches in contiguous blocks over ranks and
 merges the tally tensors with one all-reduce per cell (NCCL on the GPUs).
 """
 
@@ -487,14 +487,19 @@ def make_shuffle_tasks(root_seed: int, k: int, shuffle_indices: Sequence[int],
 
 def shard_batches(num_shuffles: int, batch_size: int, rank: int, world: int
                   ) -> List[Tuple[int, int, int]]:
-    """``(batch_id, shuffle0, n_shuffles)`` of the deterministic batches rank ``rank`` owns:
-    batch b (shuffles [b*B, min((b+1)*B, S)), the reference's recovery unit,
-    run_tournament.py:974) goes to rank ``b % world``."""
+    """``(batch_id, shuffle0, n_shuffles)`` of the deterministic batches rank ``rank`` owns.
+
+    Batch b is shuffles [b*B, min((b+1)*B, S)), the reference's recovery unit
+    (run_tournament.py:974).  The batches are dealt in contiguous blocks -- the first
+    ``n_batches % world`` ranks take one more -- so that a rank's share of a cell is ONE launch
+    (``merge_ranges``) large enough to fill the GPU, not one launch per batch."""
     if batch_size < 1 or world < 1 or not 0 <= rank < world:
         raise ValueError("bad batch size / rank / world")
     n_batches = -(-num_shuffles // batch_size)
+    base, extra = divmod(n_batches, world)
+    first = rank * base + min(rank, extra)
     return [(b, b * batch_size, min(batch_size, num_shuffles - b * batch_size))
-            for b in range(rank, n_batches, world)]
+            for b in range(first, first + base + (1 if rank < extra else 0))]
 
 
 def merge_ranges(batches: Sequence[Tuple[int, int, int]]) -> List[Tuple[int, int]]:
