@@ -169,22 +169,20 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
         ts = 0;
         rolls_turn = 0;
         const uint4* np = k2_next;
-        bool prefetch = true;
         if (!K2) {
             int ns = seat + 1;
             if (trigger < 0) ns = ns == k ? 0 : ns;
             else if (ns == trigger) ns++;
             nseat = ns;
-            prefetch = ns < k && k > 1;
-            np = reinterpret_cast<const uint4*>(P.seats + (g * (uint32_t)k + (uint32_t)ns));
+            // Past the last seat of the final round nobody plays next: fetch the last record
+            // anyway (valid memory, never consumed) rather than branch around the copies.
+            np = reinterpret_cast<const uint4*>(P.seats + (g * (uint32_t)k + (uint32_t)min(ns, k - 1)));
         }
-        if (prefetch) {
-            cp_async16(stage, np);
-            cp_async16(stage + STAGE_STRIDE, np + 1);
-            cp_async16(stage + 2u * STAGE_STRIDE, np + 2);
-            cp_async16(stage + 3u * STAGE_STRIDE, np + 3);
-            cp_async16(stage + 4u * STAGE_STRIDE, np + 4);
-        }
+        cp_async16(stage, np);
+        cp_async16(stage + STAGE_STRIDE, np + 1);
+        cp_async16(stage + 2u * STAGE_STRIDE, np + 2);
+        cp_async16(stage + 3u * STAGE_STRIDE, np + 3);
+        cp_async16(stage + 4u * STAGE_STRIDE, np + 4);
     };
     auto start_turn_from_l2 = [&]() {
         // An unconsumed prefetch of this lane (previous game, or a seat order the prediction
