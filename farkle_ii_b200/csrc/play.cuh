@@ -439,10 +439,20 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                                       (((trigger < 0 ? FB_ROW_SAFETY_LIMIT : 0u) | (err & 0xffu)) << 16);
                         status = ST_NEED;
                     } else {
-                        const bool staged = next == nseat && k > 1;
+                        // A trigger event (or k == 1) makes the prediction miss: restage the right
+                        // record (the outstanding copies into the same slots must land first) and
+                        // take the common path; rare, so its exposed L2 latency does not matter.
+                        if (next != nseat || k == 1) {
+                            cp_async_wait_all();
+                            const uint4* rp = reinterpret_cast<const uint4*>(P.seats + (g * (uint32_t)k + (uint32_t)next));
+                            cp_async16(stage, rp);
+                            cp_async16(stage + STAGE_STRIDE, rp + 1);
+                            cp_async16(stage + 2u * STAGE_STRIDE, rp + 2);
+                            cp_async16(stage + 3u * STAGE_STRIDE, rp + 3);
+                            cp_async16(stage + 4u * STAGE_STRIDE, rp + 4);
+                        }
                         seat = next;
-                        if (staged) start_turn_staged(nullptr);
-                        else start_turn_from_l2();
+                        start_turn_staged(nullptr);
                     }
                 }
             }
