@@ -327,6 +327,32 @@ def select_matchup_groups(cells: Sequence[MatchupLagGroups], max_players: int,
     return masks
 
 
+def diagnose_root(root_seed: int, ks: Sequence[int], n_shuffles: int, strategies: Any,
+                  strategy_ids: Sequence[int], lags: Sequence[int] | None = None, *, max_players: int,
+                  cap: int | None = DEFAULT_MAX_MATCHUP_GROUPS, engine: Any = None,
+                  device: int | None = None, **limits: int) -> list[dict[str, Any]]:
+    """Every row of the reference's ``rng_diagnostics.parquet`` for one root: each (root, k) cell is
+    played once with the lag outputs switched on; strategy groups of every k, then the matchup
+    groups that survive eligibility (``min(lags) + 2`` games) and the priority cap across all k.
+    ``max_players`` is the number of seat-strategy columns of the combined table (the largest k
+    of the run); row order is (level, k, group) -- the reference's is by hash partition."""
+    from . import device as fdev
+
+    lags = normalize_lags(lags)
+    eng = engine if engine is not None else fdev.get_engine(device)
+    ids = np.asarray(strategy_ids, dtype=np.int32)
+    rows: list[dict[str, Any]] = []
+    cells: list[MatchupLagGroups] = []
+    for k in ks:
+        res = eng.play_tournament(root_seed, k, 0, n_shuffles, strategies, strategy_ids=ids, lags=lags,
+                                  matchup_min_observations=minimum_observations(lags), **limits)
+        rows += StrategyLagState.from_launch(lags, n_shuffles, res.lag_stats, res.lag_edges).rows(ids.tolist(), k)
+        cells.append(MatchupLagGroups.from_launch(lags, res))
+    for cell, keep in zip(cells, select_matchup_groups(cells, max_players, cap)):
+        rows += cell.rows(max_players, keep)
+    return rows
+
+
 def diagnostics_schema():
     """Arrow schema of ``rng_diagnostics.parquet`` (``_stats_schema``, :2079-2098)."""
     import pyarrow as pa
@@ -443,7 +469,7 @@ def cell_lag_state(root_seed: int, k: int, num_shuffles: int, strategies: Any,
 
 __all__ = ["DEFAULT_MAX_MATCHUP_GROUPS", "EXPECTED_NOTE", "MATCHUP_SEQUENCE_ORDER", "MatchupLagGroups",
            "STRATEGY_SEQUENCE_ORDER", "StrategyLagState", "cell_lag_state", "diagnostics_schema",
-           "diagnostics_table", "gather_lag_segments",
+           "diagnostics_table", "diagnose_root", "gather_lag_segments",
            "join_lag_segments", "matchup_group_ids",
            "minimum_observations", "normalize_lags", "observations_from_rows", "select_matchup_groups",
            "strategy_lag_state"]

@@ -29,6 +29,9 @@ class _Result:
     lag_stats: torch.Tensor | None = None
     lag_edges: torch.Tensor | None = None
     first_seen: torch.Tensor | None = None
+    matchup_participants: torch.Tensor | None = None
+    matchup_count: torch.Tensor | None = None
+    matchup_stats: torch.Tensor | None = None
 
     def rows_numpy(self) -> np.ndarray:
         return self.rows.numpy().view(row_dtype(self.k)).reshape(-1)
@@ -50,7 +53,7 @@ class OracleEngine:
                         n_tally_ids=None, target_score=10_000, max_rounds=200, overrides=(),
                         shuffles_per_slot=0, want_tallies=True, want_rows=False,
                         want_game_seeds=False, tallies=None, totals=None, lags=(),
-                        want_first_seen=False):
+                        want_first_seen=False, matchup_min_observations=0, strategy_lags=True):
         if want_first_seen and not lags:
             res = self.play_tournament(root_seed, k, shuffle0, n_shuffles, strategies,
                                        strategy_ids=strategy_ids, n_tally_ids=n_tally_ids,
@@ -64,8 +67,19 @@ class OracleEngine:
                 res.rows = None
             return res
         if lags:
-            return self._with_lags(root_seed, k, shuffle0, n_shuffles, strategies, target_score, max_rounds,
-                                   tuple(lags))
+            res = self._with_lags(root_seed, k, shuffle0, n_shuffles, strategies, target_score, max_rounds,
+                                  tuple(lags))
+            if matchup_min_observations > 0:                  # the slow way: group the rows on the host
+                from farkle_ii_b200.rng_diagnostics import MatchupLagGroups
+
+                _, _, rows = oracle.play_tournament(root_seed, k, shuffle0, n_shuffles, _table(strategies),
+                                                    strategy_ids=strategy_ids, target_score=target_score,
+                                                    max_rounds=max_rounds, want_rows=True, n_threads=2)
+                groups = MatchupLagGroups.from_rows(tuple(lags), rows, matchup_min_observations)
+                res.matchup_participants = torch.from_numpy(groups.participants)
+                res.matchup_count = torch.from_numpy(groups.counts.astype(np.int32))
+                res.matchup_stats = torch.from_numpy(groups.stats)
+            return res
         t, tot, rows = oracle.play_tournament(
             root_seed, k, shuffle0, n_shuffles, _table(strategies), strategy_ids=strategy_ids,
             n_tally_ids=n_tally_ids, target_score=target_score, max_rounds=max_rounds,

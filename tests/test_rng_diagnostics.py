@@ -337,3 +337,57 @@ def test_device_matchup_groups_full_grid_k2():
         want = [len(x), x.sum(), y.sum(), (x * x).sum(), (y * y).sum(), (x * y).sum()]
         at = int(np.searchsorted(uniq[keep], uniq[g]))
         assert got.stats[at, 0].tolist() == want
+
+
+# ---- the whole stage against the reference's own output ---------------------------------------------
+def _stage_rows(engine):
+    """rng_diagnostics.parquet of the tiny run of tests/golden/make_golden_rngdiag.py, rebuilt from
+    the tournament reduction: (rows, fixture)."""
+    import json
+
+    from farkle_ii_b200.strategies import generate_strategy_grid, pack_strategies
+
+    fixture = json.loads((GOLDEN / "rng_diagnostics_fast42.json").read_text())
+    strategies = generate_strategy_grid(
+        score_thresholds=[250, 300, 350, 400], smart_five_opts=[True], smart_one_opts=[True],
+        consider_score_opts=[True], consider_dice_opts=[True], auto_hot_dice_opts=[True],
+        run_up_score_opts=[True])[0]
+    assert len(strategies) == fixture["n_strategies"]
+    n_shuffles = fixture["games"] // sum(len(strategies) // k for k in fixture["ks"])
+    rows = rd.diagnose_root(fixture["root_seed"], fixture["ks"], n_shuffles, pack_strategies(strategies),
+                            [s.strategy_id for s in strategies], fixture["lags"],
+                            max_players=fixture["seat_strategy_columns"],
+                            cap=fixture["summary"]["effective_matchup_group_cap"], engine=engine)
+    return rows, fixture
+
+
+def _canonical(rows):
+    return sorted(rows, key=lambda r: (r["summary_level"], r["n_players"], r["strategy"] or 0,
+                                       r["matchup_id"] or 0, r["metric"], r["lag"]))
+
+
+def _check_stage(engine):
+    rows, fixture = _stage_rows(engine)
+    want = [dict(r, note=fixture["note"], sequence_order=fixture["sequence_order"][r["summary_level"]])
+            for r in fixture["rows"]]
+    assert len(rows) == len(want) == 648
+    assert _canonical(rows) == _canonical(want)        # every value, floats bit for bit
+    summary = fixture["summary"]
+    assert sum(r["summary_level"] == "matchup" for r in rows) == \
+        summary["eligible_matchup_group_count"] * len(fixture["lags"])
+    assert sum(r["summary_level"] == "strategy" for r in rows) == \
+        summary["eligible_strategy_group_count"] * 2 * len(fixture["lags"])
+
+
+def test_whole_stage_equals_reference_output_oracle_engine():
+    """Strategy AND matchup rows of the reference's `rng_diagnostics.parquet` (its real stage, run on
+    rows its real runner wrote: tests/golden/make_golden_rngdiag.py) == the rows built from the lag
+    sums of the reduction.  Compute served by the CPU oracle here."""
+    _check_stage(OracleEngine())
+
+
+@pytest.mark.gpu
+def test_whole_stage_equals_reference_output_device():
+    from farkle_ii_b200.device import get_engine
+
+    _check_stage(get_engine(0))
