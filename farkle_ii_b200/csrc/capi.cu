@@ -979,7 +979,12 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
     if (n_strategies < k || n_strategies % k != 0)
         return fail(FB_ERR_BAD_ARG, "n_players must divide %d", n_strategies);  // run_tournament.py:274-275
     if (n_shuffles < 0 || shuffles_per_slot < 0 || n_overrides < 0) return fail(FB_ERR_BAD_ARG, "negative count");
-    if (n_shuffles == 0) return FB_OK;
+    if (n_shuffles == 0) {  // nothing played: the optional outputs still get their "empty" values
+        if (lag && lag->first_seen_dev)
+            FB_CUDA(cudaMemsetAsync(lag->first_seen_dev, 0xff, (size_t)n_tally_ids * 4 * sizeof(uint32_t), stream));
+        if (lag && lag->n_matchups_host) *lag->n_matchups_host = 0;
+        return FB_OK;
+    }
     const uint32_t gps = (uint32_t)(n_strategies / k);
     const uint64_t n_games = (uint64_t)n_shuffles * gps;
     if (n_games * (uint64_t)k > 0xfffffff0ull || n_games >= 0x7ff00000ull)

@@ -193,6 +193,13 @@ def test_lag_argument_errors():
     for bad in ((0,), (1, 1), (5000,), tuple(range(1, 10))):
         with pytest.raises(_native.NativeError):
             eng.play_tournament(1, 2, 0, 4, table, lags=bad)
+    # an empty launch leaves empty outputs, not stale memory
+    res = eng.play_tournament(1, 2, 0, 0, table, lags=(1, 3), matchup_min_observations=3, want_first_seen=True)
+    assert (res.first_seen.cpu().numpy() == -1).all() and len(res.matchup_count) == 0
+    state = rd.StrategyLagState.from_launch((1, 3), 0, res.lag_stats, res.lag_edges)
+    assert state.n_obs == 0 and not state.stats.any() and state.rows(range(len(table)), 2) == []
+    one = rd.strategy_lag_state(1, 2, 0, 5, table, (1, 3), engine=eng)
+    assert np.array_equal(state.extend(one).stats, one.stats)
 
 
 # ---- matchup groups ------------------------------------------------------------------------------
