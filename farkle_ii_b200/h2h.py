@@ -306,6 +306,72 @@ def gpu_block_runner(block: dict[str, Any], strategy_manifest: Path, chunk_games
     return _simulate_block_from_manifest(block, _load_manifest(strategy_manifest), chunk_games)
 
 
+class BatchedBlockRunner:
+    """A ``BlockRunner`` for the UNMODIFIED ``execute_h2h_schedule(cfg, block_runner=...)`` that
+    still plays many blocks per launch.
+
+    The stage calls its runner one block at a time (h2h_schedule.py:2040-2061), which would cost a
+    launch-resolve round trip per block.  Built with the blocks the stage is about to ask for
+    (its pending schedule rows, e.g. ``pd.read_parquet(cfg.h2h_block_manifest_path())`` as dicts)
+    and the stage's ``chunk_games``, this runner answers the first call by advancing ALL of them
+    together -- every chunk of every block until each is terminal -- and serves the later calls from
+    that table.  A call it did not foresee (unknown block, different progress or chunk bound) is
+    simply simulated on its own, so the answers are those of ``gpu_block_runner`` in every case.
+    """
+
+    def __init__(self, blocks: Sequence[Mapping[str, Any]], *, chunk_games: int = 5_000,
+                 oracle_game_profile: GameProfile | None = None, device: int | None = None) -> None:
+        if chunk_games < 1:
+            raise ValueError("chunk_games must be positive")
+        self.chunk_games = int(chunk_games)
+        self.profile = oracle_game_profile
+        self.device = device
+        self._waiting: dict[str, dict[str, Any]] = {str(b["block_id"]): dict(b) for b in blocks}
+        self._answers: dict[tuple[str, int, int], dict[str, Any]] = {}
+        self.launch_rounds = 0          # batched advances performed (for reports and tests)
+        self.unforeseen_calls = 0
+
+    def _bound(self, block: Mapping[str, Any]) -> int:
+        """The stage's per-call attempt bound (``plan_h2h_chunk``, h2h_schedule.py:94-129)."""
+        attempted = int(block.get("games_attempted", 0))
+        return min(int(block["max_attempts"]), attempted + self.chunk_games) - attempted
+
+    _IDENTITY = ("root_seed", "pair_id", "order", "seat1_strategy", "seat2_strategy",
+                 "n_completed_required", "max_attempts")
+    _PROGRESS = ("games_attempted", "games_completed", "games_safety_limit", "wins_seat1", "wins_seat2")
+
+    def _state(self, block: Mapping[str, Any]) -> tuple:
+        return (tuple(block.get(f) for f in self._IDENTITY),
+                tuple(int(block.get(f, 0)) for f in self._PROGRESS))
+
+    def _advance_all(self, manifest: Any) -> None:
+        current = [b for b in self._waiting.values() if self._bound(b) > 0
+                   and int(b.get("games_completed", 0)) < int(b["n_completed_required"])]
+        self._waiting.clear()
+        while current:
+            results = simulate_blocks(current, manifest, self.chunk_games, self.profile, device=self.device)
+            self.launch_rounds += 1
+            nxt = []
+            for before, after in zip(current, results):
+                key = (str(before["block_id"]), int(before.get("games_attempted", 0)), self._bound(before))
+                self._answers[key] = (self._state(before), after)
+                if after["completion_status"] == PARTIAL_RESUMABLE:
+                    nxt.append(after)
+            current = nxt
+
+    def __call__(self, block: dict[str, Any], strategy_manifest: Any, chunk_games: int) -> dict[str, Any]:
+        manifest = _load_manifest(strategy_manifest) if isinstance(strategy_manifest, (str, Path)) \
+            else strategy_manifest
+        if self._waiting:
+            self._advance_all(manifest)
+        key = (str(block["block_id"]), int(block.get("games_attempted", 0)), int(chunk_games))
+        hit = self._answers.pop(key, None)
+        if hit is not None and hit[0] == self._state(block):
+            return hit[1]
+        self.unforeseen_calls += 1
+        return _simulate_block_from_manifest(block, manifest, chunk_games, self.profile, device=self.device)
+
+
 def build_strategy_manifest(strategies: Sequence[ThresholdStrategy]):
     """Manifest DataFrame mapping ids to attributes (simulation/strategies.py:725-748)."""
     import pandas as pd
@@ -326,6 +392,6 @@ def build_strategy_manifest(strategies: Sequence[ThresholdStrategy]):
     return manifest
 
 
-__all__ = ["PARTIAL_RESUMABLE", "build_strategy_manifest", "gpu_block_runner",
+__all__ = ["BatchedBlockRunner", "PARTIAL_RESUMABLE", "build_strategy_manifest", "gpu_block_runner",
            "parse_strategy_identifier", "simulate_blocks", "_block_progress",
            "_simulate_block_from_manifest"]
