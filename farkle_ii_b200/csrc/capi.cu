@@ -668,12 +668,13 @@ int launch_play(const PlayParams& P, const FinishParams& F, cudaStream_t stream)
             if (warps < 1) warps = 1;
         }
     }
-    const size_t smem = PLAY_SMEM_BYTES;
+    const size_t smem = play_smem_bytes(P.k == 2);
     if (!g_ctx.smem_opted) {
-        FB_CUDA(cudaFuncSetAttribute(play_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        FB_CUDA(cudaFuncSetAttribute(play_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        FB_CUDA(cudaFuncSetAttribute(play_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        FB_CUDA(cudaFuncSetAttribute(play_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int two = (int)play_smem_bytes(true), any = (int)play_smem_bytes(false);
+        FB_CUDA(cudaFuncSetAttribute(play_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+        FB_CUDA(cudaFuncSetAttribute(play_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, two));
+        FB_CUDA(cudaFuncSetAttribute(play_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, any));
+        FB_CUDA(cudaFuncSetAttribute(play_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, any));
         g_ctx.smem_opted = true;
     }
     if (!t_ev_made) {

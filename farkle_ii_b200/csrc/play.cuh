@@ -91,8 +91,18 @@ __device__ __forceinline__ uint4 lds128(uint32_t smem_addr) {
 constexpr int PLAY_THREADS = 1024;
 constexpr uint32_t STAGE_STRIDE = PLAY_THREADS * 16u;
 constexpr uint32_t QUEUE_CAP = 64;  // games per warp queue (a top-up adds <= 32 to < 32)
-constexpr size_t PLAY_QUEUE_OFFSET = (size_t)((LUT_BYTES + 15) & ~15) + 5u * STAGE_STRIDE;
-constexpr size_t PLAY_SMEM_BYTES = PLAY_QUEUE_OFFSET + (PLAY_THREADS / 32) * QUEUE_CAP * 4u;
+// Generic kernel: 5 staging lines per lane (the prefetched record of the seat that plays next).
+// K2 kernel: 7 lines per lane -- lines 0-2 hold the mutable part of the seat that is NOT playing,
+// lines 3-4 / 5-6 the constant part (increment, strategy constants) of seat 0 / seat 1 -- so a
+// two-seat game lives in registers + shared memory from its first roll to its last.
+__host__ __device__ constexpr uint32_t stage_lines(bool k2) { return k2 ? 7u : 5u; }
+__host__ __device__ constexpr size_t play_queue_offset(bool k2) { return (size_t)((LUT_BYTES + 15) & ~15) + stage_lines(k2) * STAGE_STRIDE; }
+__host__ __device__ constexpr size_t play_smem_bytes(bool k2) { return play_queue_offset(k2) + (PLAY_THREADS / 32) * QUEUE_CAP * 4u; }
+static_assert(play_smem_bytes(true) <= 227u * 1024u, "K2 staging must fit the 227 KB of one CTA");
+__device__ __forceinline__ void sts128(uint32_t smem_addr, const uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(smem_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -122,7 +132,7 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
     const uint32_t n_ordinals = P.n_games + n_long;
 
     // per-warp game queue (warp-uniform registers; entries = game | HDR_LONG)
-    const uint32_t gq = lut_s + (uint32_t)PLAY_QUEUE_OFFSET + (threadIdx.x >> 5) * (QUEUE_CAP * 4u);
+    const uint32_t gq = lut_s + (uint32_t)play_queue_offset(K2) + (threadIdx.x >> 5) * (QUEUE_CAP * 4u);
     uint32_t q_head = 0, q_tail = 0, q_seen = 0;  // q_seen: the global counter as last observed
     const uint32_t q_share = 2u * gridDim.x * (blockDim.x >> 5);  // twice the number of warps
     bool q_dry = false;
@@ -147,8 +157,7 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
     // (engine.py:459-471,533-548); >= k means nobody — and prefetch that record into the
     // staging slots so its L2 latency overlaps this whole turn instead of stalling the warp.
     // (The predicted record was last written by this lane, earlier in program order.)
-    auto start_turn = [&](const uint4 m0, const uint4 m1, const uint4 m2, const uint4 i0, const uint4 i1,
-                          const uint4* k2_next) {
+    auto start_turn = [&](const uint4 m0, const uint4 m1, const uint4 m2, const uint4 i0, const uint4 i1) {
         rng.lo = (uint64_t)m0.x | ((uint64_t)m0.y << 32);
         rng.hi = (uint64_t)m0.z | ((uint64_t)m0.w << 32);
         rng.ilo = (uint64_t)i0.x | ((uint64_t)i0.y << 32);
@@ -168,7 +177,6 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
         dice = 6;
         ts = 0;
         rolls_turn = 0;
-        const uint4* np = k2_next;
         if (!K2) {
             int ns = seat + 1;
             if (trigger < 0) ns = ns == k ? 0 : ns;
@@ -176,29 +184,45 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
             nseat = ns;
             // Past the last seat of the final round nobody plays next: fetch the last record
             // anyway (valid memory, never consumed) rather than branch around the copies.
-            np = reinterpret_cast<const uint4*>(P.seats + (g * (uint32_t)k + (uint32_t)min(ns, k - 1)));
+            const uint4* np = reinterpret_cast<const uint4*>(P.seats + (g * (uint32_t)k + (uint32_t)min(ns, k - 1)));
+            cp_async16(stage, np);
+            cp_async16(stage + STAGE_STRIDE, np + 1);
+            cp_async16(stage + 2u * STAGE_STRIDE, np + 2);
+            cp_async16(stage + 3u * STAGE_STRIDE, np + 3);
+            cp_async16(stage + 4u * STAGE_STRIDE, np + 4);
         }
-        cp_async16(stage, np);
-        cp_async16(stage + STAGE_STRIDE, np + 1);
-        cp_async16(stage + 2u * STAGE_STRIDE, np + 2);
-        cp_async16(stage + 3u * STAGE_STRIDE, np + 3);
-        cp_async16(stage + 4u * STAGE_STRIDE, np + 4);
     };
     auto start_turn_from_l2 = [&]() {
+        const uint4* sp = reinterpret_cast<const uint4*>(P.seats + (g * (uint32_t)k + (uint32_t)seat));
+        if (K2) {
+            // A two-seat game starts: seat 0 goes to registers, the mutable lines of seat 1 and the
+            // constant lines of both seats go to this lane's shared-memory slots; after that the
+            // game touches global memory again only when it ends.
+            const uint4 m0 = __ldcg(sp), m1 = __ldcg(sp + 1), m2 = __ldcg(sp + 2), i0 = __ldcg(sp + 3), i1 = __ldcg(sp + 4);
+            const uint4 q0 = __ldcg(sp + 5), q1 = __ldcg(sp + 6), q2 = __ldcg(sp + 7), j0 = __ldcg(sp + 8), j1 = __ldcg(sp + 9);
+            sts128(stage, q0);
+            sts128(stage + STAGE_STRIDE, q1);
+            sts128(stage + 2u * STAGE_STRIDE, q2);
+            sts128(stage + 3u * STAGE_STRIDE, i0);
+            sts128(stage + 4u * STAGE_STRIDE, i1);
+            sts128(stage + 5u * STAGE_STRIDE, j0);
+            sts128(stage + 6u * STAGE_STRIDE, j1);
+            start_turn(m0, m1, m2, i0, i1);
+            return;
+        }
         // An unconsumed prefetch of this lane (previous game, or a seat order the prediction
         // missed) must have landed before the staging slots are targeted again: cp.async
         // copies of one thread are not ordered among themselves.
         cp_async_wait_all();
-        const uint4* sp = reinterpret_cast<const uint4*>(P.seats + (g * (uint32_t)k + (uint32_t)seat));
         const uint4 m0 = __ldcg(sp), m1 = __ldcg(sp + 1), m2 = __ldcg(sp + 2), i0 = __ldcg(sp + 3), i1 = __ldcg(sp + 4);
-        start_turn(m0, m1, m2, i0, i1, sp + 5);  // K2: a game starts with seat 0, seat 1 is the next record
+        start_turn(m0, m1, m2, i0, i1);
     };
-    auto start_turn_staged = [&](const uint4* k2_next) {
+    auto start_turn_staged = [&]() {
         cp_async_wait_all();
         const uint4 m0 = lds128(stage), m1 = lds128(stage + STAGE_STRIDE);
         const uint4 m2 = lds128(stage + 2u * STAGE_STRIDE), i0 = lds128(stage + 3u * STAGE_STRIDE);
         const uint4 i1 = lds128(stage + 4u * STAGE_STRIDE);
-        start_turn(m0, m1, m2, i0, i1, k2_next);
+        start_turn(m0, m1, m2, i0, i1);
     };
 
     // One loop iteration; returns true when every lane of the warp is out of work.
@@ -390,11 +414,16 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                     const uint32_t hi_turn = max(hw & HIGH_MASK, (uint32_t)ts);
                     hw = (hw & ~HIGH_MASK) | hi_turn;
                 }
+                const uint4 l0 = make_uint4((uint32_t)rng.lo, (uint32_t)(rng.lo >> 32), (uint32_t)rng.hi,
+                                            (uint32_t)(rng.hi >> 32));
+                const uint4 l1 = make_uint4(saved, (uint32_t)score, hw, c_fr);
+                const uint4 l2 = make_uint4(c_th, c_sf, c_so, 0u);
                 uint4* sp = reinterpret_cast<uint4*>(P.seats + (g * (uint32_t)k + (uint32_t)seat));
-                __stcg(sp, make_uint4((uint32_t)rng.lo, (uint32_t)(rng.lo >> 32), (uint32_t)rng.hi,
-                                      (uint32_t)(rng.hi >> 32)));
-                __stcg(sp + 1, make_uint4(saved, (uint32_t)score, hw, c_fr));
-                __stcg(sp + 2, make_uint4(c_th, c_sf, c_so, 0u));
+                if (!K2) {
+                    __stcg(sp, l0);
+                    __stcg(sp + 1, l1);
+                    __stcg(sp + 2, l2);
+                }
                 if (K2) {
                     bool over = fin;  // the seat that did not trigger has had its final turn
                     if (!fin) {
@@ -406,13 +435,28 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                             if (!over) round++;
                         }
                     }
+                    // the other seat's mutable lines come out of the slots, this seat's go in
+                    const uint4 p0 = lds128(stage), p1 = lds128(stage + STAGE_STRIDE);
+                    const uint4 p2 = lds128(stage + 2u * STAGE_STRIDE);
                     if (over || (err & FB_ROW_ROLL_LIMIT)) {
+                        // the game ends: both records go back to global memory for the finish pass
+                        __stcg(sp, l0);
+                        __stcg(sp + 1, l1);
+                        __stcg(sp + 2, l2);
+                        uint4* op = reinterpret_cast<uint4*>(P.seats + (g * 2u + (uint32_t)(seat ^ 1)));
+                        __stcg(op, p0);
+                        __stcg(op + 1, p1);
+                        __stcg(op + 2, p2);
                         P.header[g] = (uint32_t)round | (err & HDR_LONG) |
                                       (((trigger < 0 ? FB_ROW_SAFETY_LIMIT : 0u) | (err & 0xffu)) << 16);
                         status = ST_NEED;
                     } else {
+                        sts128(stage, l0);
+                        sts128(stage + STAGE_STRIDE, l1);
+                        sts128(stage + 2u * STAGE_STRIDE, l2);
                         seat ^= 1;
-                        start_turn_staged(sp);  // the record parked above is the one that plays after next
+                        const uint32_t cs = stage + (3u + 2u * (uint32_t)seat) * STAGE_STRIDE;
+                        start_turn(p0, p1, p2, lds128(cs), lds128(cs + STAGE_STRIDE));
                     }
                 } else {
                     // Who plays next.  Without a trigger event it is the seat predicted (and
@@ -452,7 +496,7 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                             cp_async16(stage + 4u * STAGE_STRIDE, rp + 4);
                         }
                         seat = next;
-                        start_turn_staged(nullptr);
+                        start_turn_staged();
                     }
                 }
             }
