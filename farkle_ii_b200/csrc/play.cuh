@@ -408,12 +408,10 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
 
             // ================= T: bank, park the seat, seat the next one ========
             if (turn_over) {
-                if (ts >= 500) hw |= HW_SCORED;  // entry turn (engine.py:266-267)
-                if (hw & HW_SCORED) {
-                    score += ts;
-                    const uint32_t hi_turn = max(hw & HIGH_MASK, (uint32_t)ts);
-                    hw = (hw & ~HIGH_MASK) | hi_turn;
-                }
+                hw |= ts >= 500 ? HW_SCORED : 0u;  // entry turn (engine.py:266-267)
+                const int banked = (hw & HW_SCORED) ? ts : 0;  // select, not a branch: ts >= 0
+                score += banked;
+                hw = (hw & ~HIGH_MASK) | max(hw & HIGH_MASK, (uint32_t)banked);
                 const uint4 l0 = make_uint4((uint32_t)rng.lo, (uint32_t)(rng.lo >> 32), (uint32_t)rng.hi,
                                             (uint32_t)(rng.hi >> 32));
                 const uint4 l1 = make_uint4(saved, (uint32_t)score, hw, c_fr);
@@ -425,16 +423,16 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                     __stcg(sp + 2, l2);
                 }
                 if (K2) {
-                    bool over = fin;  // the seat that did not trigger has had its final turn
-                    if (!fin) {
-                        if (score >= target) {  // this turn triggers the final round (engine.py:466-471)
-                            trigger = seat;
-                            stb = score;
-                        } else if (seat == 1) {  // next round unless the safety limit is reached
-                            over = round >= max_rounds;
-                            if (!over) round++;
-                        }
-                    }
+                    // Branch free.  fin: the seat that did not trigger has had its final turn;
+                    // else this turn may trigger the final round (engine.py:466-471); else seat 1
+                    // closes the round, and the game unless the safety limit allows another one.
+                    const bool trig_now = !fin && score >= target;
+                    const bool closes = !fin && !trig_now && seat == 1;
+                    const bool capped = closes && round >= max_rounds;
+                    trigger = trig_now ? seat : trigger;
+                    stb = trig_now ? score : stb;
+                    round += (closes && !capped) ? 1 : 0;
+                    const bool over = fin || capped;
                     // the other seat's mutable lines come out of the slots, this seat's go in
                     const uint4 p0 = lds128(stage), p1 = lds128(stage + STAGE_STRIDE);
                     const uint4 p2 = lds128(stage + 2u * STAGE_STRIDE);
