@@ -459,23 +459,18 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                 } else {
                     // Who plays next.  Without a trigger event it is the seat predicted (and
                     // prefetched) at the start of this turn.
-                    int next = nseat;
-                    bool over;
-                    if (fin) {                       // final round (engine.py:533-548)
-                        stb = max(stb, score);
-                        over = next >= k;
-                    } else if (score >= target) {    // this turn triggers it (engine.py:466-471)
-                        trigger = seat;
-                        stb = score;
-                        next = seat == 0 ? 1 : 0;
-                        over = next >= k;
-                    } else {                         // next seat, or next round unless the safety
-                        over = false;                // limit is reached (engine.py:455)
-                        if (next == 0) {
-                            over = round >= max_rounds;
-                            if (!over) round++;
-                        }
-                    }
+                    // Branch free: final round (engine.py:533-548) | this turn triggers it
+                    // (engine.py:466-471) | next seat, or next round unless the safety limit is
+                    // reached (engine.py:455).
+                    const bool trig_now = !fin && score >= target;
+                    const bool plain = !fin && !trig_now;
+                    stb = fin ? max(stb, score) : (trig_now ? score : stb);
+                    trigger = trig_now ? seat : trigger;
+                    const int next = trig_now ? (seat == 0 ? 1 : 0) : nseat;
+                    const bool closes = plain && next == 0;
+                    const bool capped = closes && round >= max_rounds;
+                    round += (closes && !capped) ? 1 : 0;
+                    const bool over = capped || (!plain && next >= k);
                     if (over || (err & FB_ROW_ROLL_LIMIT)) {
                         P.header[g] = (uint32_t)round | (err & HDR_LONG) |
                                       (((trigger < 0 ? FB_ROW_SAFETY_LIMIT : 0u) | (err & 0xffu)) << 16);
