@@ -18,10 +18,12 @@
 //   game header 4 B  n_rounds | flags << 16 | HDR_LONG, written when the game ends; the seed
 //                    kernels pre-set HDR_LONG on games that are certain to run to the safety
 //                    limit so that play_kernel starts them first (longest-first scheduling)
-// The active seat lives in registers.  A turn switch stores lines 0-2 of the outgoing seat
-// (three 16-byte st.cg) and takes the incoming seat from this lane's shared-memory staging
+// The active seat lives in registers.  Generic k: a turn switch stores lines 0-2 of the outgoing
+// seat (three 16-byte st.cg) and takes the incoming seat from this lane's shared-memory staging
 // slots, which a cp.async prefetch filled during the turn that just ended; the records of the
-// games in flight stay L2 resident.
+// games in flight stay L2 resident.  Two seats (K2): the seat that is not playing lives in the
+// lane's shared-memory slots for the whole game (a switch swaps the three mutable lines and
+// reloads the two constant ones); global memory is touched when a game starts and when it ends.
 //
 // play_kernel   one game per lane, loop body = ONE ROLL, straight-line; persistent CTAs
 //               (one per SM); a lane whose game ended takes the next game from its warp's
@@ -108,8 +110,8 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
 }
 
 // K2: two-seat games (every H2H block and the k=2 tournament cells).  The other seat always plays
-// next, so the turn switch needs no seat-order logic, the staged record is always the right one
-// and the record just parked is the one to prefetch.
+// next, so the turn switch needs no seat-order logic and both seats fit the lane's registers plus
+// seven shared-memory lines (stage_lines).
 template <bool LIMITS, bool K2>
 __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams P, const ScoreLut* __restrict__ lut_g) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
