@@ -207,10 +207,10 @@ def tallies_to_outcome(tallies: np.ndarray, ids: Sequence[int], games: Tuple[int
                                   (T_COMPLETED, 2, wins.completed_exposures),
                                   (T_SAFETY, 3, wins.safety_limit_exposures)):
         rows = touched(col, seen_col)
-        target.update(column(rows, keys_of(rows), col))
+        dict.update(target, column(rows, keys_of(rows), col))     # fresh Counter: plain insert, not add
     winners = touched(T_WINS, 0)
     win_keys = keys_of(winners)                  # one key list shared by the 23 winner dicts
-    wins.update(column(winners, win_keys, T_WINS))
+    dict.update(wins, column(winners, win_keys, T_WINS))
     block = t[winners, T_SUMS:T_SUMS + 2 * len(METRIC_LABELS)].astype(np.float64).T.tolist()
     for m, label in enumerate(METRIC_LABELS):
         sums[label].update(zip(win_keys, block[m]))
