@@ -861,7 +861,7 @@ static size_t matchup_scratch_bytes(uint64_t n) {
 
 static int run_matchups(const fb_lag_request_t& rq, const int* lags, int n_lags, const uint32_t* header,
                         const int32_t* perm, const int32_t* strategy_ids_dev, uint64_t n_games, int k,
-                        cudaStream_t stream) {
+                        int n_tally_ids, cudaStream_t stream) {
     const uint64_t n = n_games;
     if (rq.scratch_bytes < matchup_scratch_bytes(n))
         return fail(FB_ERR_WORKSPACE, "matchup scratch too small: need %zu bytes", matchup_scratch_bytes(n));
@@ -892,6 +892,10 @@ static int run_matchups(const fb_lag_request_t& rq, const int* lags, int n_lags,
     M.n_lags = n_lags;
     for (int z = 0; z < n_lags; z++) M.lags[z] = lags[z];
     M.min_obs = (uint32_t)rq.matchup_min_observations;
+    int id_bits = 1;  // every id is < n_tally_ids
+    while (id_bits < 32 && (1ll << id_bits) < (long long)n_tally_ids) id_bits++;
+    M.id_bits = id_bits;
+    const int key_bits = k <= 2 ? 2 * id_bits : 64;
     M.capacity = rq.matchup_capacity;
     M.participants = rq.matchup_participants_dev;
     M.count = rq.matchup_count_dev;
@@ -905,9 +909,9 @@ static int run_matchups(const fb_lag_request_t& rq, const int* lags, int n_lags,
     cub::DoubleBuffer<uint64_t> keys(key_a, key_b);
     cub::DoubleBuffer<uint32_t> vals(game_a, game_b);
     size_t need = 0;
-    FB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, keys, vals, (int)n, 0, 64, stream));
+    FB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, keys, vals, (int)n, 0, key_bits, stream));
     if (need > cub_have) return fail(FB_ERR_WORKSPACE, "radix sort needs %zu temporary bytes, %zu reserved", need, cub_have);
-    FB_CUDA(cub::DeviceRadixSort::SortPairs(cub_temp, need, keys, vals, (int)n, 0, 64, stream));
+    FB_CUDA(cub::DeviceRadixSort::SortPairs(cub_temp, need, keys, vals, (int)n, 0, key_bits, stream));
     g_launches.fetch_add(1);
     M.key = keys.Current();
     M.game = vals.Current();
@@ -1085,7 +1089,7 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
         if (rc) return rc;
     }
     if (lag->matchup_min_observations > 0)
-        return run_matchups(*lag, L.lags, L.n_lags, w.header, perm, strategy_ids_dev, n_games, k, stream);
+        return run_matchups(*lag, L.lags, L.n_lags, w.header, perm, strategy_ids_dev, n_games, k, n_tally_ids, stream);
     return FB_OK;
 }
 

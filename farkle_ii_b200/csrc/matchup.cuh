@@ -9,7 +9,8 @@
 //
 // Pipeline (all on the launch's stream, data already in HBM from the play pass):
 //   matchup_key_kernel     one thread per game: sort the k ids in registers, 64-bit key
-//                          (k <= 2: the ids themselves, injective; else a mixing hash)
+//                          (k <= 2: the ids themselves packed into 2 * id_bits bits, injective, so
+//                          the radix sort runs over those bits only; else a 64-bit mixing hash)
 //   cub::DeviceRadixSort   (key, game ordinal) pairs; LSD radix sort is stable, ordinals start
 //                          ascending, so equal keys stay in (shuffle, game) order
 //   matchup_flag_kernel    segment starts; for hashed keys equal-key neighbours are compared id by
@@ -32,6 +33,7 @@ struct MatchupParams {
     int n_lags;
     int lags[FB_MAX_LAGS];
     uint32_t min_obs;
+    int id_bits;  // k <= 2: ids are < 2^id_bits and the key is ids[0] << id_bits | ids[1] (fewer sort passes)
     // scratch
     uint64_t* key;         // [n] sorted keys
     uint32_t* game;        // [n] game ordinal at sorted position
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(256) matchup_key_kernel(const MatchupParams M,
     matchup_sorted_ids(M, g, ids);
     uint64_t key;
     if (M.k <= 2) {
-        key = ((uint64_t)(uint32_t)ids[0] << 32) | (uint32_t)(M.k == 2 ? ids[1] : 0);
+        key = ((uint64_t)(uint32_t)ids[0] << M.id_bits) | (uint32_t)(M.k == 2 ? ids[1] : 0);
     } else {
         key = 0x9E3779B97F4A7C15ull;
         for (int s = 0; s < M.k; s++) {
