@@ -4,6 +4,7 @@ from __future__ import annotations
 
 import ctypes
 import re
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -167,3 +168,31 @@ def test_workload_planner_kats():
     for bad in (dict(k=1), dict(strategy_count=7), dict(batch_count=1), dict(resolution_delta=1.5)):
         with pytest.raises(ValueError):
             plan_tournament_workload(**{**dict(root_seed=0, k=2, strategy_count=10, resolution_delta=0.1), **bad})
+
+
+def test_lag_request_struct_layout_matches_header(tmp_path):
+    """`_native.LagRequest` (ctypes) against `fb_lag_request_t` as a C compiler lays it out from
+    include/farkle_b200.h: same size, same offset for every field."""
+    import ctypes
+    import shutil
+    import subprocess
+
+    from farkle_ii_b200 import _native
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    fields = [name for name, _ in _native.LagRequest._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "farkle_b200.h"\nint main(void) {\n'
+        '  printf("%zu\\n", sizeof(fb_lag_request_t));\n'
+        + "".join(f'  printf("%zu\\n", offsetof(fb_lag_request_t, {f}));\n' for f in fields)
+        + "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    include = Path(__file__).resolve().parents[1] / "include"
+    subprocess.run([gcc, "-std=c11", f"-I{include}", str(src), "-o", str(exe)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(_native.LagRequest)
+    assert out[1:] == [getattr(_native.LagRequest, f).offset for f in fields]
+    assert ctypes.sizeof(_native.LagRequest) == 96
