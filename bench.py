@@ -165,6 +165,45 @@ def cpu_sample(table: np.ndarray, seconds_target: float, threads: int) -> dict:
             "seconds": dt, "games": games}
 
 
+def python_reference_sample(k: int, root: int, shuffles: int, n_jobs: int, warm: bool = False) -> dict | None:
+    """The UNMODIFIED reference's own pool path (`run_tournament.run_tournament`, n_jobs workers)
+    timed on this box's host cores by scripts/time_reference.py in a process of its own, from the
+    staged checkout baseline/_ref/ (scripts/stage_reference.sh).  None when it is not staged."""
+    cmd = [sys.executable, str(ROOT / "scripts" / "time_reference.py"), "--k", str(k), "--root", str(root),
+           "--shuffles", str(shuffles), "--n-jobs", str(n_jobs)] + (["--warm"] if warm else [])
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
+        res = json.loads(line)
+    except Exception as exc:  # the baseline is reported, never required
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+    return None if "unavailable" in res else res
+
+
+def python_reference_leg(threads: int) -> dict:
+    """`cpu_baseline_reference`: J = 1 (one shuffle) and J = all host cores (one shuffle per core) of
+    the k=2 full-grid cell, root 42 (SURVEY.md section 8d recipe)."""
+    one = python_reference_sample(2, ROOTS[0], 1, 1)
+    if one is None:
+        return {"unavailable": "reference checkout not staged (scripts/stage_reference.sh -> baseline/_ref)"}
+    if "unavailable" in one:
+        return one
+    many = python_reference_sample(2, ROOTS[0], threads, threads)
+    leg = {"kind": "reference", "unit": "games/s",
+           "impl": one["impl"], "call": "run_tournament.run_tournament(config=TournamentConfig(n_players=2, "
+           "deterministic_batch_size=1), strategies=<5,160 grid>, global_seed=42, n_jobs=J, collect_metrics=True, "
+           "row_output_directory=None)  [simulation/run_tournament.py:1050]",
+           "n_jobs_1": {"value": one["games_per_s"], "cores": 1, "games": one["games"], "seconds": one["seconds"]}}
+    if many and "unavailable" not in many:
+        leg["n_jobs_all"] = {"value": many["games_per_s"], "cores": many["n_jobs"], "games": many["games"],
+                             "seconds": many["seconds"], "wins_total": many["wins_total"]}
+        leg["value"], leg["cores"] = many["games_per_s"], many["n_jobs"]
+        leg["sample"] = (f"full grid root {ROOTS[0]} k=2: shuffles 0..{many['shuffles'] - 1} ({many['games']} games, "
+                         f"{many['seconds']:.1f} s) on {many['n_jobs']} worker processes; 1 worker: shuffle 0 "
+                         f"({one['games']} games, {one['seconds']:.1f} s)")
+    return leg
+
+
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -179,6 +218,7 @@ def run_reference_arm(args) -> None:
     secs = sum(r["seconds"] for r in results)
     value = games / secs
     base = {k_: results[-1][k_] for k_ in ("unit", "cores", "kind", "sample")}
+    pyref = python_reference_leg(threads) if args.ref_shuffles != 0 else {"unavailable": "skipped (--ref-shuffles 0)"}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "games/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -188,8 +228,12 @@ def run_reference_arm(args) -> None:
         "cpu_baseline": {"value": value, **base},
         "e2e": {"value": value, "unit": "games/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
-        "note": ("CPU arm = C restatement of the reference (the Python reference itself runs "
-                 "~200-300 games/s/core: BASELINE.md §1-2); bounded sample per step"),
+        "cpu_baseline_reference": pyref,
+        "note": ("value / cpu_baseline = C restatement of the reference (oracle/, pthreads over shuffles, "
+                 "all host cores), bounded sample per step: the HARDER baseline.  cpu_baseline_reference "
+                 "= the unmodified Python reference's own process-pool path timed on the same cores "
+                 "(one shuffle per core, one sample: a shuffle costs ~11 core-seconds in Python, so "
+                 "K+W such samples would not fit the arm's time budget)"),
     }
     print(json.dumps(line))
 
@@ -220,6 +264,8 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--shuffles", type=int, default=SHUFFLES, help=argparse.SUPPRESS)
+    ap.add_argument("--ref-shuffles", type=int, default=-1,
+                    help="0 skips the Python-reference CPU leg (cpu_baseline_reference)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -394,8 +440,10 @@ def main() -> None:
         "bound": "issue", "kernel": f"play_kernel (k={dom} cell, {kern[dom]['games']} games/launch)",
         "achieved": achieved / 1e12, "peak": peak_measured / 1e12, "unit": "Tlaneop/s",
         "frac": achieved / peak_measured,
-        "peak_source": ("measured: fb_measure_issue_peak (register-only mad/xor/add chains, "
-                        "1,024 threads/SM); MEASURED_PEAKS.json holds no integer peak"),
+        "peak_source": ("measured: fb_measure_issue_peak = best of four register-only integer-chain "
+                        "probes at 1,024 threads/SM (the LOP3 + IMAD.IADD one issues at ~0.98 IPC: "
+                        "profiles/r02_issue_peak.md); MEASURED_PEAKS.json holds no integer peak"),
+        "peak_variants": {str(v): eng.measure_issue_peak_variant(v) / 1e12 for v in range(5)},
         "peak_nominal": nominal_peak / 1e12,
         "model": (f"algorithmic lane-instructions = {W_OPS}*rng_words + {D_OPS}*dice + "
                   f"{R_OPS}*rolls (SURVEY.md §8d), counts returned by the kernel"),
@@ -416,6 +464,45 @@ def main() -> None:
     if cpu:
         cpu.pop("seconds", None)
         cpu.pop("games", None)
+    pyref = None
+    if world == 1 and args.ref_shuffles != 0:
+        pyref = python_reference_leg(os.cpu_count() or 1)
+
+    # ---- parity of what was just timed: one deterministic batch per cell against the oracle, the
+    # step's own tallies against the path's invariants, and (when the Python reference ran) the
+    # games it completed on its shuffles against the GPU's count for the same shuffles
+    import oracle
+
+    oracle.build()
+    slot = 37
+    parity = {"slot": slot, "equal": True, "cells": []}
+    for k in CELLS_K:
+        root = ROOTS[(args.steps - 1) % 2]
+        s0 = shuffle0 + slot * SHUFFLES_PER_BATCH
+        got = eng.play_tournament(root, k, s0, SHUFFLES_PER_BATCH, table_dev)
+        want_t, want_tot, _ = oracle.play_tournament(root, k, s0, SHUFFLES_PER_BATCH, table_host,
+                                                     n_threads=os.cpu_count() or 1)
+        same = bool(np.array_equal(got.tallies.cpu().numpy().reshape(want_t.shape), want_t) and
+                    np.array_equal(got.totals.cpu().numpy(), want_tot))
+        # invariants of the full timed cell (tallies[k] / totals[k] hold its last launch)
+        t_full, tot_full = tallies[k].cpu().numpy()[0], totals[k].cpu().numpy()
+        inv = bool(t_full[:, 0].sum() == tot_full[1] and t_full[:, 1].sum() == k * tot_full[0] and
+                   t_full[:, 2].sum() + t_full[:, 3].sum() == k * tot_full[0] and
+                   tot_full[0] == n_sh * (N_STRATEGIES // k) and tot_full[7] == 0)
+        parity["cells"].append({"root": root, "k": k, "shuffles": [int(s0), int(s0 + SHUFFLES_PER_BATCH)],
+                                "games": int(want_tot[0]), "batch_equals_oracle": same,
+                                "full_cell_invariants": inv})
+        parity["equal"] = parity["equal"] and same and inv
+    if pyref and "n_jobs_all" in pyref:
+        n_ref = pyref["n_jobs_all"]["cores"]
+        got = eng.play_tournament(ROOTS[0], 2, 0, n_ref, table_dev)
+        tot = got.totals.cpu().numpy()
+        ok = bool(int(tot[0]) == pyref["n_jobs_all"]["games"] and int(tot[1]) == pyref["n_jobs_all"]["wins_total"])
+        parity["python_reference"] = {"root": ROOTS[0], "k": 2, "shuffles": [0, n_ref], "games": int(tot[0]),
+                                      "games_completed_gpu": int(tot[1]),
+                                      "games_completed_reference": pyref["n_jobs_all"]["wins_total"], "equal": ok}
+        parity["equal"] = parity["equal"] and ok
+    parity["checker"] = "oracle/farkle_oracle.c (pinned to the reference by tests/test_oracle_golden.py)"
     line = {
         "metric": METRIC, "value": value, "unit": "games/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -434,6 +521,8 @@ def main() -> None:
         "roofline_hbm": {**roofline["hbm"], "traffic": traffic,
                          "note": "same kernel against the HBM roofline: it is not the binding one"},
         "cpu_baseline": cpu,
+        "cpu_baseline_reference": pyref,
+        "parity_check": parity,
         "published_reference": {"games_per_s_1_worker": 279.1, "games_per_s_12_workers": 1142.9,
                                 "hardware": "Ryzen 7 3700X, fast grid k=2 (BASELINE.md §1)"},
     }
@@ -441,6 +530,8 @@ def main() -> None:
     json_out.flush()
     if world > 1:
         dist.destroy_process_group()
+    if not parity["equal"]:
+        raise SystemExit("bench.py: parity check failed: " + json.dumps(parity))
 
 
 if __name__ == "__main__":

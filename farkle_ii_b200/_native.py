@@ -30,7 +30,7 @@ SYMBOLS = (
     "fb_roll_dice", "fb_default_score", "fb_permute_shuffles", "fb_play_tournament",
     "fb_play_tournament_seats", "fb_play_tournament_lags", "fb_matchup_scratch_bytes",
     "fb_play_h2h", "fb_h2h_resolve", "fb_play_games", "fb_run_tournament_host",
-    "fb_measure_issue_peak", "fb_last_play_kernel_ms", "fb_play_kernel_ms_history",
+    "fb_measure_issue_peak", "fb_measure_issue_peak_variant", "fb_last_play_kernel_ms", "fb_play_kernel_ms_history",
     "fb_kernel_launch_count",
 )
 
@@ -120,6 +120,7 @@ def _declare(L: C.CDLL) -> None:
     L.fb_run_tournament_host.argtypes = [_u64, _int, _u64, _int, _vp, _vp, _int, _int, _i32, _i32,
                                          _int, _vp, _vp, _vp, _int]
     L.fb_measure_issue_peak.argtypes = [_int, C.POINTER(C.c_double)]
+    L.fb_measure_issue_peak_variant.argtypes = [_int, _int, C.POINTER(C.c_double)]
     L.fb_last_play_kernel_ms.restype = C.c_float
     L.fb_play_kernel_ms_history.argtypes = [C.POINTER(C.c_float), _int]
     L.fb_kernel_launch_count.restype = _u64

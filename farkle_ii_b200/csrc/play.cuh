@@ -65,6 +65,7 @@ struct PlayParams {
     uint32_t* header;       // [n_games]
     const int32_t* limits;  // [n_games][2] {target, max_rounds} or nullptr
     int32_t target_score, max_rounds;
+    int32_t roll_limit;  // ROLL_LIMIT, or the FB_TEST_ROLL_LIMIT test knob (launch_play)
     uint32_t n_games;
     int k;
     unsigned long long* totals;  // [FB_TOTALS_WIDTH] or nullptr (dice / rng words only)
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
             bool turn_over = farkle || (!hot && !keep);
             ts = farkle ? 0 : ts2;
             dice = ndice;
-            if (!turn_over && rolls_turn >= ROLL_LIMIT) {  // engine.py:242-243 raises
+            if (!turn_over && rolls_turn >= P.roll_limit) {  // engine.py:242-243 raises
                 err |= FB_ROW_ROLL_LIMIT;
                 turn_over = true;
             }
@@ -560,6 +561,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
         const uint32_t rounds = hdr & 0xffffu;
         uint32_t flags = (hdr >> 16) & 0xffu;
         const bool safety = flags & FB_ROW_SAFETY_LIMIT;
+        if (rounds > (uint32_t)FB_MAX_ROUNDS) flags |= FB_ROW_I16_OVERFLOW;  // n_rounds is an int16 column
         const Seat* seats = F.seats + (size_t)g * k;
         // pass 1: winner = highest score, ties to the lower seat (stable sort, engine.py:483)
         int best = -1;

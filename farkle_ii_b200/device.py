@@ -18,6 +18,7 @@ from . import _native
 from .layout import (
     LAG_WIDTH,
     MATCHUP_LAG_WIDTH,
+    MAX_ROUNDS,
     SEAT_TALLY_WIDTH,
     STRATEGY_DTYPE,
     TALLY_WIDTH,
@@ -44,6 +45,15 @@ def get_engine(device: int | None = None) -> "Engine":
                 "run one process per GPU (torchrun) instead of switching devices")
         eng = _engines[device] = Engine(device)
     return eng
+
+
+def _check_rounds(values) -> None:
+    """Per-game ``max_rounds`` values obey the bound the C ABI enforces on its scalar argument
+    (``FB_MAX_ROUNDS``: ``n_rounds`` is an int16 column; the reference fails at the Arrow
+    conversion of such a row, simulation/simulation.py:566-573)."""
+    v = np.asarray(values, dtype=np.int64)
+    if v.size and int(v.max()) > MAX_ROUNDS:
+        raise _native.NativeError(f"max_rounds={int(v.max())} above {MAX_ROUNDS}: n_rounds is an int16 column")
 
 
 def _ptr(t: torch.Tensor | None) -> C.c_void_p | None:
@@ -128,6 +138,13 @@ class Engine:
         out = C.c_double()
         with torch.cuda.device(self.device):
             _native.check(self.lib.fb_measure_issue_peak(iters, C.byref(out)))
+        return out.value
+
+    def measure_issue_peak_variant(self, variant: int, iters: int = 20000) -> float:
+        """One probe variant (see ``fb_measure_issue_peak_variant`` in include/farkle_b200.h)."""
+        out = C.c_double()
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.fb_measure_issue_peak_variant(variant, iters, C.byref(out)))
         return out.value
 
     def run_tournament_host(self, root_seed: int, k: int, shuffle0: int, n_shuffles: int,
@@ -278,6 +295,7 @@ class Engine:
             rows = torch.empty((max(n_games, 1), row_stride(k)), dtype=torch.uint8,
                                device=self.device)[:n_games]
         ov = list(overrides)
+        _check_rounds([o[2] for o in ov])
         d_os = d_og = d_om = None
         if ov:
             d_os = self.to_device(np.array([o[0] for o in ov], dtype=np.uint64))
@@ -340,6 +358,8 @@ class Engine:
             np.ascontiguousarray(seat_strategy_ids, dtype=np.int32).reshape(n, k))
         d_ts = None if target_scores is None else self.to_device(
             np.ascontiguousarray(target_scores, dtype=np.int32))
+        if max_rounds_v is not None:
+            _check_rounds(max_rounds_v)
         d_mr = None if max_rounds_v is None else self.to_device(
             np.ascontiguousarray(max_rounds_v, dtype=np.int32))
         rows = torch.empty((max(n, 1), row_stride(k)), dtype=torch.uint8, device=self.device)[:n]

@@ -10,6 +10,7 @@ MATCHUP_LAG_WIDTH = 6  # pairs, n_rounds {sx, sy, sx2, sy2, sxy}
 SEAT_TALLY_WIDTH = 4  # raw_wins, raw_exposures, raw_completed_exposures, raw_safety_limit_exposures
 N_METRICS = 11
 MAX_PLAYERS = 12
+MAX_ROUNDS = 32767  # FB_MAX_ROUNDS: n_rounds is an int16 column (utils/schema_helpers.py:23-42)
 TOTALS_WIDTH = 8 + MAX_PLAYERS
 
 # tally columns (run_tournament.py:177-195, 109-121)

@@ -183,6 +183,11 @@ typedef struct fb_lag_request {
  *   8..8+FB_MAX_PLAYERS-1  wins by 0-based seat
  */
 #define FB_MAX_PLAYERS 12
+/* Largest max_rounds a launch accepts: n_rounds is an int16 row column
+ * (utils/schema_helpers.py:23-42) and 16 bits of the game header.  Scalar arguments above it
+ * return FB_ERR_BAD_ARG; per-game values above it are cut to FB_MAX_ROUNDS + 1 and a game
+ * that actually plays that many rounds is reported with FB_ROW_I16_OVERFLOW.             */
+#define FB_MAX_ROUNDS 32767
 #define FB_TOTALS_WIDTH (8 + FB_MAX_PLAYERS)
 
 /* ---- library ---------------------------------------------------------------*/
@@ -369,11 +374,17 @@ float fb_last_play_kernel_ms(void);
  * to max_entries durations (the library keeps the last 64) and returns how many were
  * written (negative fb_status on error).  Blocks until those kernels have finished.      */
 int fb_play_kernel_ms_history(float* out_ms, int max_entries);
-/* Roofline probe: runs a register-only kernel of independent 32-bit integer
- * mad / xor / add chains on every SM (1,024 threads per SM, `iters` iterations of
- * 32 lane instructions each, half on the FMA pipe and half on the ALU pipe) and
- * returns the measured lane-instructions per second.  Synchronous.           */
+/* Roofline probe: register-only kernels of independent 32-bit integer chains on every SM
+ * (1,024 threads per SM, no memory), returning measured lane-instructions per second.
+ * Synchronous.  fb_measure_issue_peak reports the best of the mixed-pipe variants
+ * (half IMAD on the FMA-heavy pipe, half LOP3/IADD3 on the ALU pipe): the issue peak the
+ * path is held against (MEASURED_PEAKS.json has no integer peak).
+ * fb_measure_issue_peak_variant runs one variant: 0 chain-major mad/xor/mad/add (each
+ * instruction depends on its predecessor), 1 op-major over 8 chains, 2 op-major over 16
+ * chains with the pipes interleaved, 3 xor/add chains (LOP3 + IMAD.IADD alternating: the
+ * one that reaches ~0.98 instructions per cycle and scheduler), 4 mad only (one pipe).   */
 int fb_measure_issue_peak(int iters, double* lane_ops_per_second);
+int fb_measure_issue_peak_variant(int variant, int iters, double* lane_ops_per_second);
 /* Number of kernels this library has launched since fb_init (all threads).  */
 uint64_t fb_kernel_launch_count(void);
 

@@ -388,6 +388,14 @@ void fo_default_score(const uint8_t faces[6], int32_t turn_score_pre, const fb_s
 /* Player turn and game — game/engine.py:208-273, 436-550                     */
 /* ------------------------------------------------------------------------- */
 #define ROLL_LIMIT 1000 /* game/engine.py:36 */
+/* Test knob shared with the CUDA library (FB_TEST_ROLL_LIMIT=n, 1 <= n <= 1000): lets the tests reach
+ * the RuntimeError path of engine.py:242-243, which real play practically never does. */
+static int g_roll_limit = ROLL_LIMIT; /* refreshed at every exported play call */
+static void refresh_roll_limit(void) {
+    const char* e = getenv("FB_TEST_ROLL_LIMIT");
+    const int v = e ? atoi(e) : ROLL_LIMIT;
+    g_roll_limit = (v >= 1 && v <= ROLL_LIMIT) ? v : ROLL_LIMIT;
+}
 
 typedef struct {
     pcg_t rng;
@@ -424,8 +432,9 @@ static int strategy_decide(const player_t* p, int turn_score, int dice_left, int
 static int take_turn(player_t* p, int final_round, int score_to_beat, uint64_t* rolls_ctr) {
     p->n_turns++;
     int dice = 6, turn_score = 0, rolls_this_turn = 0;
+    const int limit = g_roll_limit;
     while (dice > 0) {
-        if (rolls_this_turn >= ROLL_LIMIT) return 1;
+        if (rolls_this_turn >= limit) return 1;
         uint8_t roll[6];
         p->n_rolls++; /* _roll :85-101 */
         (*rolls_ctr)++;
@@ -673,6 +682,7 @@ int fo_play_tournament(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuff
                        const int32_t* ov_max_rounds, int n_overrides, int shuffles_per_slot,
                        int64_t* tallies, int64_t* totals, void* rows, int want_game_seeds,
                        int n_threads) {
+    refresh_roll_limit();
     if (k < 1 || k > FB_MAX_PLAYERS || n_strategies % k != 0 || n_shuffles < 0) return -2;
     if (n_threads < 1) n_threads = 1;
     if (n_threads > n_shuffles && n_shuffles > 0) n_threads = n_shuffles;
@@ -716,6 +726,7 @@ int fo_play_games(const uint64_t* coords /*[n][7]*/, uint64_t n_games, int k,
                   const fb_strategy_t* seat_strategies, const int32_t* seat_strategy_ids,
                   const int32_t* target_score_v, int32_t target_score, const int32_t* max_rounds_v,
                   int32_t max_rounds, void* rows, int64_t* totals) {
+    refresh_roll_limit();
     if (k < 1 || k > FB_MAX_PLAYERS) return -2;
     const size_t stride = row_stride(k);
     uint8_t* rowbuf = (uint8_t*)calloc(1, stride);
@@ -750,6 +761,7 @@ int fo_play_h2h_block(uint64_t root_seed, uint64_t pair_id, int order, const fb_
                       const fb_strategy_t* seat2, int32_t n_completed_required,
                       int32_t max_attempts, int32_t chunk_games, int32_t target_score,
                       int32_t max_rounds, int32_t progress[5], uint8_t* outcome_out) {
+    refresh_roll_limit();
     int attempted = progress[0], completed = progress[1], safety = progress[2];
     int w1 = progress[3], w2 = progress[4];
     int stop = attempted + chunk_games < max_attempts ? attempted + chunk_games : max_attempts;

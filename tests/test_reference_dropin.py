@@ -1,10 +1,12 @@
-"""Drop-in proof: the UNMODIFIED reference driver (`farkle.simulation.run_tournament.run_tournament`,
-imported from /root/reference) runs with this repo's seam functions installed and must write the
-same checkpoint, metrics and rows as it does on its own.
+"""Drop-in proof: the UNMODIFIED reference (`farkle.simulation.run_tournament.run_tournament`, its L4
+runner `farkle.simulation.runner.run_tournament(cfg)` and the H2H stage `execute_h2h_schedule`) runs
+with this repo's seam functions installed and must write the same checkpoint, metrics, rows and
+sidecars as it does on its own.
 
-Only runs where /root/reference exists (the build container); compute calls are served by the
-oracle-backed engine here — GPU parity of the same calls is covered by tests/test_gpu_parity.py and
-tests/test_host_surface.py[cuda].
+The reference is imported from the checkout `tests/refpath.py` finds: /root/reference in the build
+container, the staged copy `baseline/_ref/` (scripts/stage_reference.sh) on the GPU box.  Every test
+runs twice: `oracle-backed` (CPU box: compute calls served by tests/oracle_engine.py, host logic
+only) and `cuda` (marked gpu: the real CUDA engine through the C ABI, nothing monkeypatched).
 """
 
 from __future__ import annotations
@@ -16,22 +18,45 @@ from pathlib import Path
 
 import pytest
 
-REF = Path("/root/reference/src")
-pytestmark = pytest.mark.skipif(not REF.exists(), reason="reference checkout not present on this box")
+from refpath import numba_cache_env, reference_root
+
+REF_ROOT = reference_root()
+REF = (REF_ROOT or Path("/nonexistent")) / "src"
+pytestmark = pytest.mark.skipif(REF_ROOT is None, reason="reference checkout not present on this box "
+                                "(run scripts/stage_reference.sh where /root/reference exists)")
+
+BACKENDS = [pytest.param("oracle", id="oracle-backed"),
+            pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+
+
+@pytest.fixture(params=BACKENDS)
+def backend(request):
+    return request.param
 
 
 @pytest.fixture()
-def ref_rt(monkeypatch):
-    os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/nbcache")
+def ref_rt(monkeypatch, backend):
+    numba_cache_env()
     monkeypatch.syspath_prepend(str(REF))
     import farkle.simulation.run_tournament as rt
 
-    from farkle_ii_b200 import device as fdev
-    from oracle_engine import OracleEngine
+    if backend == "oracle":
+        from farkle_ii_b200 import device as fdev
+        from oracle_engine import OracleEngine
 
-    eng = OracleEngine()
-    monkeypatch.setattr(fdev, "get_engine", lambda device=None: eng)
+        eng = OracleEngine()
+        monkeypatch.setattr(fdev, "get_engine", lambda device=None: eng)
     yield rt
+    for name in [m for m in sys.modules if m == "farkle" or m.startswith("farkle.")]:
+        sys.modules.pop(name)
+
+
+@pytest.fixture()
+def ref_env(monkeypatch):
+    """The reference importable, no engine involved."""
+    numba_cache_env()
+    monkeypatch.syspath_prepend(str(REF))
+    yield
     for name in [m for m in sys.modules if m == "farkle" or m.startswith("farkle.")]:
         sys.modules.pop(name)
 
@@ -145,7 +170,7 @@ def test_h2h_block_runner_against_reference(ref_rt, tmp_path):
             block = dict(want)          # resume from the reference's progress
 
 
-def test_seat_count_semantics_match_reference_seat_analysis(ref_rt, tmp_path):
+def test_seat_count_semantics_match_reference_seat_analysis(ref_env, tmp_path):
     """`seat_counts_from_rows` (the host restatement the GPU seat tallies are tested against) equals
     the reference's `_iter_seat_count_tables` on a curated Parquet of the same games."""
     import numpy as np
@@ -174,7 +199,7 @@ def test_seat_count_semantics_match_reference_seat_analysis(ref_rt, tmp_path):
     assert frt.seat_counts_from_rows(rows, batch) == want
 
 
-def test_plan_and_limits_match_reference_modules(ref_rt):
+def test_plan_and_limits_match_reference_modules(ref_env):
     """`shuffle_plan` / `limits` against the reference's `workload_planner` / `game_profile`:
     every float of the plan bit-identical, same identity hash, same rejections."""
     import itertools
@@ -224,25 +249,34 @@ def test_plan_and_limits_match_reference_modules(ref_rt):
         assert msgs[0] == msgs[1]
 
 
-_RUNNER_SCRIPT = """
+_PRELUDE = """
 import os, sys
 os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/nbcache")
-ref_src, overlay, use_shim, repo = sys.argv[1], sys.argv[2], sys.argv[3] == "1", sys.argv[4]
+ref_src, engine, repo = sys.argv[1], sys.argv[2], sys.argv[3]
 sys.path.insert(0, ref_src)
 from pathlib import Path
-from farkle.config import load_app_config
-from farkle.simulation import runner
-if use_shim:
+if engine != "none":
     sys.path.insert(0, repo)
     sys.path.insert(0, os.path.join(repo, "tests"))
+    if engine == "oracle":
+        from farkle_ii_b200 import device as fdev
+        from oracle_engine import OracleEngine
+        eng = OracleEngine()
+        fdev.get_engine = lambda device=None: eng
+"""
+
+_RUNNER_SCRIPT = _PRELUDE + """
+from farkle.config import load_app_config
+from farkle.simulation import runner
+if engine != "none":
     import farkle.simulation.run_tournament as rt
-    from farkle_ii_b200 import device as fdev, reference_shim
-    from oracle_engine import OracleEngine
-    eng = OracleEngine()
-    fdev.get_engine = lambda device=None: eng
+    from farkle_ii_b200 import reference_shim
     reference_shim.install(rt)
-cfg = load_app_config(Path(ref_src).parent / "configs" / "fast_config.yaml", Path(overlay))
+cfg = load_app_config(Path(ref_src).parent / "configs" / "fast_config.yaml", Path(sys.argv[4]))
 print("games", runner.run_tournament(cfg))
+if engine == "cuda":
+    from farkle_ii_b200.device import get_engine
+    print("gpu_launches", get_engine().kernel_launch_count())
 """
 
 _OVERLAY = """
@@ -270,12 +304,9 @@ resources:
 """
 
 
-def test_runner_artifact_tree_is_byte_identical(tmp_path):
-    """The reference's L4 runner (`farkle run`: `simulation.runner.run_tournament(cfg)`, fast grid,
-    k = 2 and 4, rows + expanded metrics, artifact contract v3) writes the SAME BYTES in every file
-    -- row shards, manifests, metrics / checkpoint Parquets, checkpoint pickle, hash-bound sidecars,
-    workload plan, `simulation.done.json` -- with this repo's seams installed as it does alone.
-    Runs an unmodified, git-initialised copy of the checkout in two subprocesses."""
+def _git_copy(tmp_path: Path) -> tuple[Path, list[str]]:
+    """An unmodified, git-initialised copy of the checkout (the runner binds artifacts to the
+    code identity of its work tree, utils/authenticated_contract.py:404-417)."""
     import shutil
     import subprocess
 
@@ -286,25 +317,147 @@ def test_runner_artifact_tree_is_byte_identical(tmp_path):
     for name in ("src", "configs", "pyproject.toml"):
         src = REF.parent / name
         (shutil.copytree if src.is_dir() else shutil.copy)(src, ref / name)
+    git = ["git", "-c", "user.email=t@example.org", "-c", "user.name=t"]
+    return ref, git
+
+
+def _commit(ref: Path, git: list[str]) -> None:
+    import subprocess
+
+    subprocess.run([*git, "init", "-q"], cwd=ref, check=True)
+    subprocess.run([*git, "add", "-A"], cwd=ref, check=True)
+    subprocess.run([*git, "commit", "-qm", "reference copy"], cwd=ref, check=True)
+
+
+def _same_tree(root_a: Path, root_b: Path) -> list[Path]:
+    files = sorted(p.relative_to(root_a) for p in root_a.rglob("*") if p.is_file())
+    assert files == sorted(p.relative_to(root_b) for p in root_b.rglob("*") if p.is_file())
+    different = [str(f) for f in files if (root_a / f).read_bytes() != (root_b / f).read_bytes()]
+    assert different == []
+    return files
+
+
+def test_runner_artifact_tree_is_byte_identical(tmp_path, backend):
+    """The reference's L4 runner (`farkle run`: `simulation.runner.run_tournament(cfg)`, fast grid,
+    k = 2 and 4, rows + expanded metrics, artifact contract v3) writes the SAME BYTES in every file
+    -- row shards, manifests, metrics / checkpoint Parquets, checkpoint pickle, hash-bound sidecars,
+    workload plan, `simulation.done.json` -- with this repo's seams installed as it does alone.
+    Runs an unmodified, git-initialised copy of the checkout in two subprocesses."""
+    import subprocess
+
+    ref, git = _git_copy(tmp_path)
     outs = {}
     for tag in ("cpu", "gpu"):
         outs[tag] = tmp_path / f"out_{tag}"
         (ref / f"overlay_{tag}.yaml").write_text(_OVERLAY.format(prefix=outs[tag] / "res"))
     (ref / "drive.py").write_text(_RUNNER_SCRIPT)
-    git = ["git", "-c", "user.email=t@example.org", "-c", "user.name=t"]
-    subprocess.run([*git, "init", "-q"], cwd=ref, check=True)
-    subprocess.run([*git, "add", "-A"], cwd=ref, check=True)
-    subprocess.run([*git, "commit", "-qm", "reference copy"], cwd=ref, check=True)
+    _commit(ref, git)
     repo = str(Path(__file__).resolve().parents[1])
-    for tag, shim in (("cpu", "0"), ("gpu", "1")):
-        done = subprocess.run([sys.executable, str(ref / "drive.py"), str(ref / "src"),
-                               str(ref / f"overlay_{tag}.yaml"), shim, repo],
-                              cwd=ref, capture_output=True, text=True, timeout=600)
+    for tag, engine in (("cpu", "none"), ("gpu", backend)):
+        done = subprocess.run([sys.executable, str(ref / "drive.py"), str(ref / "src"), engine, repo,
+                               str(ref / f"overlay_{tag}.yaml")],
+                              cwd=ref, capture_output=True, text=True, timeout=900)
         assert done.returncode == 0, done.stderr[-2000:]
         assert "games 720" in done.stdout            # 12 shuffles x (40 + 20) games
-    root_a, root_b = outs["cpu"] / "res_seed_42", outs["gpu"] / "res_seed_42"
-    files = sorted(p.relative_to(root_a) for p in root_a.rglob("*") if p.is_file())
-    assert files == sorted(p.relative_to(root_b) for p in root_b.rglob("*") if p.is_file())
+        if engine == "cuda":                          # the CUDA library really did the playing
+            assert int(done.stdout.split("gpu_launches")[1].split()[0]) > 0
+    files = _same_tree(outs["cpu"] / "res_seed_42", outs["gpu"] / "res_seed_42")
     assert len(files) > 60 and any(f.name == "simulation.done.json" for f in files)
-    different = [str(f) for f in files if (root_a / f).read_bytes() != (root_b / f).read_bytes()]
-    assert different == []
+
+
+# The H2H stage: frozen family -> plan_h2h_schedule -> execute_h2h_schedule, all the reference's
+# own code (the family artifacts are written with its public artifact helpers the way its unit
+# tests do, tests/unit/analysis/test_h2h_schedule.py:41-108); only `block_runner` differs.
+_H2H_SCRIPT = _PRELUDE + """
+import json
+import pandas as pd, pyarrow as pa, pyarrow.parquet as pq
+from farkle.analysis.h2h_schedule import execute_h2h_schedule, plan_h2h_schedule
+from farkle.config import AppConfig, ArtifactScope, IOConfig, SimConfig
+from farkle.simulation.simulation import generate_strategy_grid
+from farkle.simulation.strategies import build_strategy_manifest
+from farkle.utils.artifact_contract import make_artifact_sidecar
+from farkle.utils.artifacts import write_json_artifact_atomic, write_parquet_artifact_atomic
+
+out, runner_kind = Path(sys.argv[4]), sys.argv[5]
+roots = (11, 22)
+cfg = AppConfig(io=IOConfig(results_dir_prefix=out / "results"),
+                sim=SimConfig(seed=roots[0], seed_list=list(roots), n_players_list=[2, 4]))
+cfg.screening.practical_delta_by_k = {2: 0.03, 4: 0.03}
+cfg.screening.delta_across_k = 0.03
+cfg.head2head.total_game_cap = None
+cfg.head2head.n_jobs = 1
+cfg.head2head.practical_delta = 0.25          # small power-planned blocks
+cfg.resources.scheduler_memory_budget_mb = 2048   # torch alone exceeds the 768 MiB library default
+cfg.resources.process_tree_warning_threshold_mb = 8192
+cfg.resources.aggregate_memory_hard_limit_mb = 12288
+cfg.resources.minimum_system_available_memory_mb = 256
+cfg.head2head.seat1_advantage_scenarios = (0.0,)
+candidates = (17, 1203, 2999, 4100)           # ids of the default grid
+family_hash = "a" * 64
+membership = pd.DataFrame({"strategy": list(candidates), "final_family": [True] * len(candidates),
+                           "family_hash": [family_hash] * len(candidates)})
+membership["strategy"] = pd.array(membership["strategy"].tolist(), dtype="Int32")
+manifest = {"family_hash": family_hash, "candidates": list(candidates),
+            "candidate_count": len(candidates), "root_seeds": list(roots), "single_root_execution": False}
+common = dict(producer="test", scope=ArtifactScope.H2H_2P, source_scope=ArtifactScope.CROSS_SEED,
+              operation="candidate_family_freeze", player_counts=[2], required_player_counts=[2],
+              missing_cell_policy="fail", seed_scope="both_roots_combined")
+mp = cfg.h2h_candidate_family_path()
+write_parquet_artifact_atomic(pa.Table.from_pandas(membership, preserve_index=False), mp,
+    sidecar=make_artifact_sidecar(cfg, mp, consistency_columns=membership.columns.tolist(), **common))
+jp = cfg.h2h_candidate_family_manifest_path()
+write_json_artifact_atomic(manifest, jp,
+    sidecar=make_artifact_sidecar(cfg, jp, consistency_columns=list(manifest), **common))
+plan_h2h_schedule(cfg)
+strategies = generate_strategy_grid()[0]
+sm = cfg.strategy_manifest_root_path()
+sm.parent.mkdir(parents=True, exist_ok=True)
+build_strategy_manifest(strategies).to_parquet(sm)
+schedule = pq.read_table(cfg.h2h_block_manifest_path()).to_pandas()
+print("blocks", len(schedule), "required", int(schedule["n_completed_required"].iloc[0]))
+kw = {}
+if runner_kind == "single":
+    from farkle_ii_b200 import h2h
+    kw = dict(n_jobs=1, block_runner=h2h.gpu_block_runner)
+elif runner_kind == "batched":
+    from farkle_ii_b200 import h2h
+    kw = dict(n_jobs=1, block_runner=h2h.BatchedBlockRunner(schedule.to_dict(orient="records"), chunk_games=int(sys.argv[6])))
+art = execute_h2h_schedule(cfg, chunk_games=int(sys.argv[6]), **kw)
+counts = pq.read_table(art.order_counts).to_pandas()
+print("completed", int(counts["games_completed"].sum()), "attempted", int(counts["games_attempted"].sum()))
+if engine == "cuda":
+    from farkle_ii_b200.device import get_engine
+    print("gpu_launches", get_engine().kernel_launch_count())
+"""
+
+
+@pytest.mark.parametrize("runner_kind,chunk", [("single", 5000), ("batched", 9)])
+def test_h2h_stage_with_gpu_block_runner(tmp_path, backend, runner_kind, chunk):
+    """`execute_h2h_schedule` (analysis/h2h_schedule.py:1597) — the reference's whole H2H execution
+    stage, on a schedule its own `plan_h2h_schedule` produced — writes the same block Parquets,
+    sidecars, execution state and order counts with this repo's `BlockRunner` (one block per call,
+    and the batched runner that advances every pending block per launch) as with its own
+    `_simulate_block`.  `chunk` 9 forces several durable checkpoints per block."""
+    import subprocess
+
+    ref, git = _git_copy(tmp_path)
+    (ref / "drive_h2h.py").write_text(_H2H_SCRIPT)
+    _commit(ref, git)
+    repo = str(Path(__file__).resolve().parents[1])
+    outs = {"cpu": tmp_path / "out_cpu", "gpu": tmp_path / "out_gpu"}
+    seen = {}
+    for tag, engine, kind in (("cpu", "none", "reference"), ("gpu", backend, runner_kind)):
+        done = subprocess.run([sys.executable, str(ref / "drive_h2h.py"), str(ref / "src"), engine, repo,
+                               str(outs[tag]), kind, str(chunk)],
+                              cwd=ref, capture_output=True, text=True, timeout=900)
+        assert done.returncode == 0, done.stderr[-3000:]
+        seen[tag] = [ln for ln in done.stdout.splitlines() if ln.startswith(("blocks", "completed"))]
+        if engine == "cuda":
+            assert int(done.stdout.split("gpu_launches")[1].split()[0]) > 0
+    assert seen["cpu"] == seen["gpu"] and len(seen["cpu"]) == 2
+    # timing telemetry aside, every artifact of the stage is byte-identical
+    files_a = sorted(p.relative_to(outs["cpu"]) for p in outs["cpu"].rglob("*") if p.is_file())
+    files_b = sorted(p.relative_to(outs["gpu"]) for p in outs["gpu"].rglob("*") if p.is_file())
+    assert files_a == files_b and any("h2h" in str(f) for f in files_a)
+    different = [str(f) for f in files_a if (outs["cpu"] / f).read_bytes() != (outs["gpu"] / f).read_bytes()]
+    assert different == [], different
