@@ -279,6 +279,8 @@ class Engine:
                 n_tally_ids = n_strategies
             else:
                 n_tally_ids = int(np.asarray(strategy_ids).max()) + 1
+        if want_tallies and n_tally_ids < 1:
+            raise _native.NativeError(f"n_tally_ids={n_tally_ids} must be >= 1")
         gps = n_strategies // k if k > 0 else 0
         n_games = n_shuffles * gps
         n_slots = 1 if shuffles_per_slot <= 0 else -(-n_shuffles // shuffles_per_slot)
