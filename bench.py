@@ -44,6 +44,7 @@ SHUFFLES = 4300                      # workload_planner: delta 0.03 -> 4265 -> 4
 SHUFFLES_PER_BATCH = 43
 CELLS_K = (2, 4)
 ROOTS = (42, 43)
+MEGA_K, MEGA_ROOT = (2, 3, 4, 5, 6, 8, 10, 12), 102   # configs/farkle_mega_config.yaml:10-14
 # algorithmic lane-instruction model of SURVEY.md §8d (play kernel: words, dice, rolls)
 W_OPS, D_OPS, R_OPS, S_OPS = 28, 8, 90, 1000
 METRIC = "simulated games/sec at 1/2/4/8 B200 (bit-exact tallies) vs reference CPU n_jobs"
@@ -246,6 +247,8 @@ def workload_config(n_gpus: int) -> dict:
         "n_strategies": N_STRATEGIES, "k": list(CELLS_K), "roots": list(ROOTS),
         "shuffles_per_cell_per_gpu": SHUFFLES, "shuffles_per_batch": SHUFFLES_PER_BATCH,
         "games_per_step_per_gpu": sum(SHUFFLES * (N_STRATEGIES // k) for k in CELLS_K),
+        "pipeline": ("one fb_play_tournament_cells call per step: [k=2 cell, k=4 cell] + the next step's k=2 "
+                     "cell as look-ahead (prepared, not played)"),
         "sharding": (f"rank r plays shuffles [r*{SHUFFLES},(r+1)*{SHUFFLES}) of each cell; "
                      "one int64 all-reduce of the tally tensor per cell" if n_gpus > 1
                      else "single GPU"),
@@ -264,6 +267,10 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--shuffles", type=int, default=SHUFFLES, help=argparse.SUPPRESS)
+    ap.add_argument("--unpipelined", action="store_true",
+                    help="one fb_play_tournament call per cell instead of the pipelined cell list")
+    ap.add_argument("--strong-reps", type=int, default=3,
+                    help="timed repetitions of the strong-scaling leg (mega root over the ranks); 0 skips it")
     ap.add_argument("--ref-shuffles", type=int, default=-1,
                     help="0 skips the Python-reference CPU leg (cpu_baseline_reference)")
     args = ap.parse_args()
@@ -300,13 +307,22 @@ def main() -> None:
     totals = {k: torch.zeros(TOTALS_WIDTH, dtype=torch.int64, device=eng.device) for k in CELLS_K}
 
     def step(i: int) -> None:
-        root = ROOTS[i % len(ROOTS)]
+        # One call per step with the step's cells (fb_play_tournament_cells): the permutations and
+        # seat seeding of a cell run under the tail / finish / tally passes of the cell before it.
+        # The first cell of the NEXT step is passed as look-ahead, as a runner walking its list of
+        # (root, k) cells does; every step therefore still prepares and plays two cells.
+        root, nxt = ROOTS[i % len(ROOTS)], ROOTS[(i + 1) % len(ROOTS)]
         for k in CELLS_K:
             tallies[k].zero_()
             totals[k].zero_()
-            eng.play_tournament(root, k, shuffle0, n_sh, table_dev, tallies=tallies[k],
-                                totals=totals[k])
-            if world > 1:
+        if args.unpipelined:
+            for k in CELLS_K:
+                eng.play_tournament(root, k, shuffle0, n_sh, table_dev, tallies=tallies[k], totals=totals[k])
+        else:
+            eng.play_cells([(root, k, shuffle0, n_sh, tallies[k], totals[k]) for k in CELLS_K], table_dev,
+                           ahead=(nxt, CELLS_K[0], shuffle0, n_sh))
+        if world > 1:
+            for k in CELLS_K:
                 dist.all_reduce(tallies[k])
 
     def sync_all() -> None:
@@ -407,6 +423,58 @@ def main() -> None:
     rows_d2h = sum(rows_pin[k].numel() for k in CELLS_K)
     h2d = len(CELLS_K) * table_host.nbytes
     d2h = len(CELLS_K) * (N_STRATEGIES * TALLY_WIDTH * 8 + TOTALS_WIDTH * 8)
+
+    # ---- strong scaling of a FIXED workload: one mega-config root (configs/farkle_mega_config.yaml:
+    # full grid, k in {2,3,4,5,6,8,10,12}, 4,300 shuffles each = 39,013,900 games).  The cells are dealt
+    # to the ranks along one line by estimated cost (run_tournament.plan_cells), every rank plays its
+    # segments through the pipelined cell list, ONE all-reduce merges the stacked tallies.  Rank 0
+    # also plays the whole root alone (the other GPUs idle) so that both times come from this run.
+    from farkle_ii_b200 import run_tournament as frt
+
+    strong = None
+    if args.strong_reps > 0:
+        mega = [(MEGA_ROOT, k, SHUFFLES) for k in MEGA_K]
+
+        def play(segments, table):
+            eng.play_cells(segments, table)
+
+        def timed(reps, **kw):
+            out = frt.run_cells(mega, table_dev, batch_size=SHUFFLES_PER_BATCH, play_cells=play, **kw)  # warm-up
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                out = frt.run_cells(mega, table_dev, batch_size=SHUFFLES_PER_BATCH, play_cells=play, **kw)
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps, out
+
+        sync_all()
+        n_ms, (t_all, tot_all) = timed(args.strong_reps, rank=rank, world=world)
+        if world > 1:
+            t = torch.tensor([n_ms], dtype=torch.float64, device=eng.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            n_ms = float(t.item())
+            dist.barrier()
+        one_ms, same = n_ms, True
+        if world > 1 and rank == 0:
+            one_ms, (t_one, tot_one) = timed(max(1, args.strong_reps - 1), rank=0, world=1,
+                                             plan=frt.plan_cells(mega, N_STRATEGIES, 1, batch_size=SHUFFLES_PER_BATCH))
+            same = bool(torch.equal(t_one, t_all) and torch.equal(tot_one, tot_all))
+        if world > 1:
+            dist.barrier()
+        mega_games = sum(SHUFFLES * (N_STRATEGIES // k) for k in MEGA_K)
+        strong = {"workload": f"mega-config root {MEGA_ROOT}: full grid, k in {list(MEGA_K)}, {SHUFFLES} shuffles each "
+                              f"({mega_games} games), fixed total work",
+                  "n_gpus": world, "n1_ms": one_ms, "nN_ms": n_ms, "speedup": one_ms / n_ms,
+                  "efficiency": one_ms / n_ms / world, "games_per_s": mega_games / (n_ms * 1e-3),
+                  "identical_tallies_n1_vs_nN": same, "games_attempted": int(tot_all[:, 0].sum().item()),
+                  "reps": args.strong_reps,
+                  "plan": [[(sg.k, sg.shuffle0, sg.n_shuffles) for sg in segs]
+                           for segs in frt.plan_cells(mega, N_STRATEGIES, world, batch_size=SHUFFLES_PER_BATCH)],
+                  "timing": "CUDA events on every rank around all launches + the all-reduce, max over ranks; "
+                            "n1_ms: rank 0 plays the whole root alone in the same run"}
+        assert strong["games_attempted"] == mega_games
 
     if rank != 0:
         if world > 1:
@@ -523,6 +591,7 @@ def main() -> None:
         "cpu_baseline": cpu,
         "cpu_baseline_reference": pyref,
         "parity_check": parity,
+        "strong": strong,
         "published_reference": {"games_per_s_1_worker": 279.1, "games_per_s_12_workers": 1142.9,
                                 "hardware": "Ryzen 7 3700X, fast grid k=2 (BASELINE.md §1)"},
     }
@@ -532,6 +601,8 @@ def main() -> None:
         dist.destroy_process_group()
     if not parity["equal"]:
         raise SystemExit("bench.py: parity check failed: " + json.dumps(parity))
+    if strong and not strong["identical_tallies_n1_vs_nN"]:
+        raise SystemExit("bench.py: the N-rank tallies of the strong-scaling leg differ from the 1-rank ones")
 
 
 if __name__ == "__main__":

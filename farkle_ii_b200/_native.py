@@ -28,7 +28,8 @@ SYMBOLS = (
     "fb_abi_version", "fb_last_error", "fb_init", "fb_device_info", "fb_row_stride",
     "fb_workspace_bytes", "fb_seedseq_generate", "fb_coordinate_seeds", "fb_seed_streams",
     "fb_roll_dice", "fb_default_score", "fb_permute_shuffles", "fb_play_tournament",
-    "fb_play_tournament_seats", "fb_play_tournament_lags", "fb_matchup_scratch_bytes",
+    "fb_play_tournament_seats", "fb_play_tournament_lags", "fb_cells_workspace_bytes",
+    "fb_play_tournament_cells", "fb_matchup_scratch_bytes",
     "fb_play_h2h", "fb_h2h_resolve", "fb_play_games", "fb_run_tournament_host",
     "fb_measure_issue_peak", "fb_measure_issue_peak_variant", "fb_last_play_kernel_ms", "fb_play_kernel_ms_history",
     "fb_kernel_launch_count",
@@ -47,6 +48,13 @@ class LagRequest(C.Structure):
         ("scratch_dev", C.c_void_p), ("scratch_bytes", C.c_size_t),
         ("n_matchups_host", C.c_void_p), ("first_seen_dev", C.c_void_p),
     ]
+
+
+class Cell(C.Structure):
+    """``fb_cell_t`` (include/farkle_b200.h)."""
+
+    _fields_ = [("root_seed", C.c_uint64), ("shuffle0", C.c_uint64), ("k", C.c_int32),
+                ("n_shuffles", C.c_int32), ("tallies_dev", C.c_void_p), ("totals_dev", C.c_void_p)]
 
 
 class NativeError(RuntimeError):
@@ -110,6 +118,10 @@ def _declare(L: C.CDLL) -> None:
     L.fb_play_tournament_lags.argtypes = [_u64, _int, _u64, _int, _vp, _vp, _int, _int, _i32, _i32,
                                           _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _int, _vp,
                                           C.POINTER(LagRequest), _vp, _sz, _vp]
+    L.fb_cells_workspace_bytes.argtypes = [C.POINTER(Cell), _int, _int]
+    L.fb_cells_workspace_bytes.restype = _sz
+    L.fb_play_tournament_cells.argtypes = [C.POINTER(Cell), _int, _int, _vp, _vp, _int, _int, _i32, _i32,
+                                           _int, _vp, _sz, _vp]
     L.fb_matchup_scratch_bytes.argtypes = [_u64]
     L.fb_matchup_scratch_bytes.restype = _sz
     L.fb_play_h2h.argtypes = [_u64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _i32, _i32, _vp,

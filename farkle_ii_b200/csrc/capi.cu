@@ -58,6 +58,20 @@ struct Ctx {
     // fb_run_tournament_host: compute / copy streams and the events that hand the row buffers over
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
     cudaEvent_t ev_played[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    // fb_play_tournament_cells: preparation stream, hand-over events per workspace slot, and the
+    // cell a previous call prepared ahead of time
+    cudaStream_t s_prep = nullptr;
+    cudaEvent_t ev_cells_entry = nullptr, ev_cell_prepared[2] = {nullptr, nullptr},
+                ev_cell_played[2] = {nullptr, nullptr};
+    struct Ahead {
+        bool valid = false;
+        uint64_t root_seed = 0, shuffle0 = 0;
+        int k = 0, n_shuffles = 0, n_strategies = 0, slot = 0;
+        int32_t target_score = 0, max_rounds = 0;
+        const void* strategies = nullptr;
+        const void* workspace = nullptr;
+        size_t workspace_bytes = 0;
+    } ahead;
 };
 Ctx g_ctx;
 std::mutex g_mu;
@@ -1018,6 +1032,11 @@ static int run_matchups(const fb_lag_request_t& rq, const int* lags, int n_lags,
     return FB_OK;
 }
 
+// A tournament launch has two phases that fb_play_tournament_cells runs on different streams:
+// PREPARE (permutations, seat seeding: touches only the workspace) and PLAY (play, finish, tally
+// gather: reads the workspace, accumulates into the caller's tallies / totals / rows).
+enum { PHASE_PREPARE = 1, PHASE_PLAY = 2, PHASE_ALL = 3 };
+
 static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
                                 const fb_strategy_t* strategies_dev, const int32_t* strategy_ids_dev,
                                 int n_strategies, int n_tally_ids, int32_t target_score, int32_t max_rounds,
@@ -1026,7 +1045,8 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
                                 int64_t* tallies_dev, int64_t* totals_dev, void* rows_dev, int want_game_seeds,
                                 void* workspace_dev, size_t workspace_bytes, void* stream_v,
                                 uint32_t ordinal_base, int64_t* seat_tallies_dev = nullptr,
-                                const fb_lag_request_t* lag = nullptr, bool ids_trusted = false) {
+                                const fb_lag_request_t* lag = nullptr, bool ids_trusted = false,
+                                int phase = PHASE_ALL) {
     FB_REQUIRE_INIT();
     if (seat_tallies_dev && !tallies_dev) return fail(FB_ERR_BAD_ARG, "seat tallies need tallies_dev");
     LagParams L{};
@@ -1083,11 +1103,14 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
         return fail(FB_ERR_WORKSPACE, "workspace too small: need %zu bytes",
                     ws_core_bytes(k, n_games) + 2 * perm_bytes);
     int32_t* perm = reinterpret_cast<int32_t*>(w.extra);
-    int32_t* inv = tallies_dev ? reinterpret_cast<int32_t*>(w.extra + perm_bytes) : nullptr;
+    // (a cell prepared ahead does not know yet whether its play phase will want tallies)
+    int32_t* inv = (tallies_dev || phase != PHASE_ALL) ? reinterpret_cast<int32_t*>(w.extra + perm_bytes) : nullptr;
     uint4* prefix = reinterpret_cast<uint4*>(w.prefix);
-    int rc = permute_shuffles(root_seed, k, shuffle0, n_shuffles, n_strategies, perm, inv, prefix, stream);
-    if (rc) return rc;
+    int rc = FB_OK;
     int32_t* limits = n_overrides > 0 ? w.limits : nullptr;
+    if (phase & PHASE_PREPARE) {
+    rc = permute_shuffles(root_seed, k, shuffle0, n_shuffles, n_strategies, perm, inv, prefix, stream);
+    if (rc) return rc;
     FB_CUDA(cudaMemsetAsync(w.counter, 0, 4 * sizeof(unsigned int), stream));
     if (tallies_dev && strategy_ids_dev && !ids_trusted) {
         // explicit ids address the tally buffers: one pass over the table, one flag back
@@ -1106,6 +1129,8 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
         strategies_dev, w.seats, w.game_seed, limits, w.header, w.long_list, w.counter, prefix);
     rc = launch_check("seed_tournament_kernel");
     if (rc) return rc;
+    }  // PHASE_PREPARE
+    if (!(phase & PHASE_PLAY)) return FB_OK;
     PlayParams P{};
     P.seats = w.seats;
     P.header = w.header;
@@ -1134,12 +1159,7 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
     F.row_words = (int)(fb_row_stride(k) / 4);
     F.ordinal_base = ordinal_base;
     if (!F.tallies) return launch_play(P, F, stream);
-    // tallies: exposures per slot now, winner metrics by gather after the finish pass
-    const int n_slots = shuffles_per_slot > 0 ? (n_shuffles + shuffles_per_slot - 1) / shuffles_per_slot : 1;
-    exposure_kernel<<<dim3(blocks_for((uint64_t)n_strategies, 256), (unsigned)n_slots), 256, 0, stream>>>(
-        F.tallies, strategy_ids_dev, n_strategies, n_tally_ids, n_shuffles, shuffles_per_slot);
-    rc = launch_check("exposure_kernel");
-    if (rc) return rc;
+    // tallies: exposures and winner metrics by gather after the finish pass
     F.mark_winner = 1;
     rc = launch_play(P, F, stream);
     if (rc) return rc;
@@ -1228,6 +1248,118 @@ int fb_play_tournament_lags(uint64_t root_seed, int k, uint64_t shuffle0, int n_
                                 override_max_rounds_dev, n_overrides, shuffles_per_slot, tallies_dev, totals_dev,
                                 rows_dev, want_game_seeds, workspace_dev, workspace_bytes, stream_v, 0u,
                                 seat_tallies_dev, lag);
+}
+
+static size_t cell_slot_bytes(int k, uint64_t n_games, int n_shuffles, int n_strategies) {
+    return align_up(ws_core_bytes(k, n_games) + 2 * align_up((size_t)n_shuffles * n_strategies * 4, 256), 256);
+}
+
+size_t fb_cells_workspace_bytes(const fb_cell_t* cells, int n_cells, int n_strategies) {
+    size_t slot = 0;
+    for (int i = 0; cells && i < n_cells; i++) {
+        const fb_cell_t& c = cells[i];
+        if (c.k < 1 || c.k > FB_MAX_PLAYERS || c.n_shuffles < 0 || n_strategies < c.k) return 0;
+        slot = std::max(slot, cell_slot_bytes(c.k, (uint64_t)c.n_shuffles * (uint64_t)(n_strategies / c.k),
+                                              c.n_shuffles, n_strategies));
+    }
+    return 2 * slot + 512;
+}
+
+int fb_play_tournament_cells(const fb_cell_t* cells, int n_cells, int n_ahead,
+                             const fb_strategy_t* strategies_dev, const int32_t* strategy_ids_dev,
+                             int n_strategies, int n_tally_ids, int32_t target_score, int32_t max_rounds,
+                             int shuffles_per_slot, void* workspace_dev, size_t workspace_bytes, void* stream_v) {
+    FB_REQUIRE_INIT();
+    if (n_cells < 0 || n_ahead < 0 || n_ahead > 1 || (n_cells + n_ahead > 0 && !cells))
+        return fail(FB_ERR_BAD_ARG, "bad cell list (n_cells >= 0, n_ahead 0 or 1)");
+    const int n_all = n_cells + n_ahead;
+    if (n_all == 0) return FB_OK;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!g_ctx.s_prep) {
+        int lo = 0, hi = 0;
+        FB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = least urgent
+        FB_CUDA(cudaStreamCreateWithPriority(&g_ctx.s_prep, cudaStreamNonBlocking, lo));
+        FB_CUDA(cudaEventCreateWithFlags(&g_ctx.ev_cells_entry, cudaEventDisableTiming));
+        for (int i = 0; i < 2; i++) {
+            FB_CUDA(cudaEventCreateWithFlags(&g_ctx.ev_cell_prepared[i], cudaEventDisableTiming));
+            FB_CUDA(cudaEventCreateWithFlags(&g_ctx.ev_cell_played[i], cudaEventDisableTiming));
+        }
+    }
+    // two workspace slots: cell i is prepared in one while cell i-1 is played out of the other
+    uint8_t* base = static_cast<uint8_t*>(workspace_dev);
+    const size_t shift = (256 - (reinterpret_cast<uintptr_t>(base) & 255)) & 255;
+    if (!base || workspace_bytes < shift + 512) return fail(FB_ERR_WORKSPACE, "workspace too small");
+    const size_t slot_bytes = ((workspace_bytes - shift) / 2) & ~(size_t)255;
+    uint8_t* slot_ptr[2] = {base + shift, base + shift + slot_bytes};
+    for (int i = 0; i < n_all; i++) {
+        const fb_cell_t& c = cells[i];
+        if (c.k < 1 || c.k > FB_MAX_PLAYERS || c.n_shuffles < 0 || n_strategies < c.k || n_strategies % c.k)
+            return fail(FB_ERR_BAD_ARG, "cell %d: bad k / shuffle count", i);
+        const size_t need = cell_slot_bytes(c.k, (uint64_t)c.n_shuffles * (uint64_t)(n_strategies / c.k),
+                                            c.n_shuffles, n_strategies);
+        if (need > slot_bytes)
+            return fail(FB_ERR_WORKSPACE, "workspace too small: cell %d needs %zu bytes per slot, %zu given "
+                        "(fb_cells_workspace_bytes)", i, need, slot_bytes);
+    }
+    auto run = [&](int i, int slot, int phase, cudaStream_t s) {
+        const fb_cell_t& c = cells[i];
+        return play_tournament_impl(c.root_seed, c.k, c.shuffle0, c.n_shuffles, strategies_dev, strategy_ids_dev,
+                                    n_strategies, n_tally_ids, target_score, max_rounds, nullptr, nullptr, nullptr, 0,
+                                    shuffles_per_slot, c.tallies_dev, c.totals_dev, nullptr, 0, slot_ptr[slot],
+                                    slot_bytes, s, 0u, nullptr, nullptr, /*ids_trusted=*/i > 0 || phase == PHASE_PLAY,
+                                    phase);
+    };
+    // Was the first cell prepared by the previous call (its n_ahead cell)?
+    Ctx::Ahead& ah = g_ctx.ahead;
+    int slot0 = 0;
+    bool first_ready = false;
+    if (ah.valid && n_cells > 0) {
+        const fb_cell_t& c = cells[0];
+        first_ready = ah.root_seed == c.root_seed && ah.shuffle0 == c.shuffle0 && ah.k == c.k &&
+                      ah.n_shuffles == c.n_shuffles && ah.n_strategies == n_strategies &&
+                      ah.target_score == target_score && ah.max_rounds == max_rounds &&
+                      ah.strategies == strategies_dev && ah.workspace == workspace_dev &&
+                      ah.workspace_bytes == workspace_bytes;
+        if (first_ready) slot0 = ah.slot;
+    }
+    ah.valid = false;
+    int rc = FB_OK;
+    // everything already queued on the caller's stream (table upload, zeroing of the tallies)
+    // comes before the first preparation
+    FB_CUDA(cudaEventRecord(g_ctx.ev_cells_entry, stream));
+    FB_CUDA(cudaStreamWaitEvent(g_ctx.s_prep, g_ctx.ev_cells_entry, 0));
+    // (explicit ids are validated in the PREPARE phase of the first cell; a cell prepared ahead was
+    // validated by the call that prepared it)
+    if (!first_ready) {
+        rc = run(0, slot0, PHASE_PREPARE, g_ctx.s_prep);
+        if (rc) return rc;
+        FB_CUDA(cudaEventRecord(g_ctx.ev_cell_prepared[slot0], g_ctx.s_prep));
+    }
+    for (int i = 0; i < n_all; i++) {
+        const int slot = (slot0 + i) & 1;
+        if (i + 1 < n_all) {  // prepare the next cell while this one is being played
+            const int nslot = slot ^ 1;
+            if (i >= 1) FB_CUDA(cudaStreamWaitEvent(g_ctx.s_prep, g_ctx.ev_cell_played[nslot], 0));
+            rc = run(i + 1, nslot, PHASE_PREPARE, g_ctx.s_prep);
+            if (rc) return rc;
+            FB_CUDA(cudaEventRecord(g_ctx.ev_cell_prepared[nslot], g_ctx.s_prep));
+        }
+        if (i >= n_cells) break;  // the look-ahead cell is only prepared
+        FB_CUDA(cudaStreamWaitEvent(stream, g_ctx.ev_cell_prepared[slot], 0));
+        rc = run(i, slot, PHASE_PLAY, stream);
+        if (rc) return rc;
+        FB_CUDA(cudaEventRecord(g_ctx.ev_cell_played[slot], stream));
+    }
+    if (n_ahead == 1) {
+        const fb_cell_t& c = cells[n_cells];
+        ah.valid = true;
+        ah.root_seed = c.root_seed; ah.shuffle0 = c.shuffle0; ah.k = c.k; ah.n_shuffles = c.n_shuffles;
+        ah.n_strategies = n_strategies; ah.slot = (slot0 + n_cells) & 1;
+        ah.target_score = target_score; ah.max_rounds = max_rounds;
+        ah.strategies = strategies_dev; ah.workspace = workspace_dev; ah.workspace_bytes = workspace_bytes;
+    }
+    return FB_OK;
 }
 
 size_t fb_matchup_scratch_bytes(uint64_t n_games) { return matchup_scratch_bytes(n_games); }

@@ -32,9 +32,9 @@
 // finish_kernel one thread per finished game, dense and lane-parallel: ranks the seats,
 //               marks the winner in the header, emits the compact row (every byte of a row
 //               is written by one thread, L2 merges the sectors) and the launch totals.
-// exposure_kernel / tally_gather_kernel
-//               the per-strategy tallies: exposures per slot, winner metrics by gather over
-//               the inverse permutation (few atomics).
+// tally_gather_kernel
+//               the per-strategy tallies: exposures and winner metrics by gather over the
+//               inverse permutation (few atomics).
 #pragma once
 #include <cstdint>
 
@@ -646,25 +646,12 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
     }
 }
 
-// attempted / completed exposures of a tournament launch: strategy i is seated exactly once in
-// every shuffle (run_tournament.py:336-353), so slot j adds its shuffle count to both columns.
-__global__ void exposure_kernel(unsigned long long* tallies, const int32_t* strategy_ids, int n_strategies,
-                                int n_tally_ids, int n_shuffles, int shuffles_per_slot) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int slot = blockIdx.y;
-    if (i >= n_strategies) return;
-    const int per = shuffles_per_slot > 0 ? shuffles_per_slot : n_shuffles;
-    const int cnt = min(per, n_shuffles - slot * per);
-    const int sid = strategy_ids ? strategy_ids[i] : i;
-    unsigned long long* Ts = tallies + ((size_t)slot * n_tally_ids + sid) * FB_TALLY_WIDTH;
-    atomicAdd(&Ts[1], (unsigned long long)cnt);
-    atomicAdd(&Ts[2], (unsigned long long)cnt);
-}
-
-// Winner tallies by gather (run_tournament.py:375-391).  Every strategy is seated exactly once per
+// Tallies by gather (run_tournament.py:336-353,375-391).  Every strategy is seated exactly once per
 // shuffle, so thread (strategy i, chunk c) walks the chunk's shuffles, finds its game through the
 // inverse permutation, and — if it won — adds the winner metrics from its seat record into
-// registers; one RED per non-zero column at the end.  ~25x fewer L2 atomics than adding per game.
+// registers; one RED per non-zero column at the end (~25x fewer L2 atomics than adding per game).
+// Exposures need no game data at all: attempted = the chunk's shuffle count, completed = that
+// minus the safety-limit games met on the way.
 struct GatherParams {
     const Seat* seats;
     const uint32_t* header;  // rounds | flags << 16 | (winner seat + 1) << 24
@@ -733,10 +720,10 @@ __global__ void __launch_bounds__(128) tally_gather_kernel(const GatherParams G)
     }
     unsigned long long* T = G.tallies + ((size_t)(G.slotted ? c : 0) * G.n_tally_ids + sid) * FB_TALLY_WIDTH;
     if (wins) atomicAdd(&T[0], wins);
-    if (safety) {  // move exposures from "completed" (added by exposure_kernel) to "safety limit"
-        atomicAdd(&T[3], safety);
-        atomicAdd(&T[2], 0ull - safety);
-    }
+    const unsigned long long seated = (unsigned long long)(j1 - j0);
+    if (seated) atomicAdd(&T[1], seated);
+    if (seated - safety) atomicAdd(&T[2], seated - safety);
+    if (safety) atomicAdd(&T[3], safety);
 #pragma unroll
     for (int m = 0; m < 10; m++) {
         if (sum[m]) {

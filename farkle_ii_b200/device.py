@@ -97,6 +97,7 @@ class Engine:
         self.sm_count, self.clock_khz = sm.value, khz.value
         self.compute_capability = (major.value, minor.value)
         self._ws: torch.Tensor | None = None
+        self._cells_ws: torch.Tensor | None = None
 
     # ------------------------------------------------------------------ helpers
     def _stream(self) -> C.c_void_p:
@@ -347,6 +348,52 @@ class Engine:
             m_part, m_count, m_stats = m_part[:found], m_count[:found], m_stats[:found]
         return TournamentResult(tallies if want_tallies else None, totals, rows, n_games, k, seat_tallies,
                                 lag_stats, lag_edges, m_part, m_count, m_stats, first_seen)
+
+    def play_cells(self, cells, strategies: torch.Tensor | np.ndarray, *, ahead=None,
+                   strategy_ids=None, n_tally_ids: int | None = None, target_score: int = 10_000,
+                   max_rounds: int = 200, shuffles_per_slot: int = 0) -> None:
+        """Enqueue several tournament cells, pipelined (``fb_play_tournament_cells``).
+
+        ``cells``: sequence of ``(root_seed, k, shuffle0, n_shuffles, tallies, totals)`` with the
+        int64 device tensors each cell accumulates into (``tallies`` [slots, ids, 26], ``totals``
+        [20]; either may be ``None``).  ``ahead``: one more ``(root_seed, k, shuffle0, n_shuffles)``
+        that is only prepared (permutations, seat seeding), so that the next call starting with
+        exactly that cell plays at once.  Same results as one ``play_tournament`` per cell.
+        """
+        if isinstance(strategies, np.ndarray):
+            strategies = self.to_device(np.ascontiguousarray(strategies, dtype=STRATEGY_DTYPE))
+        n_strategies = strategies.numel() // 8
+        d_ids = None
+        if strategy_ids is not None:
+            d_ids = strategy_ids if isinstance(strategy_ids, torch.Tensor) else self.to_device(
+                np.ascontiguousarray(strategy_ids, dtype=np.int32))
+        if n_tally_ids is None:
+            n_tally_ids = n_strategies if strategy_ids is None else int(np.asarray(strategy_ids).max()) + 1
+        every = list(cells) + ([tuple(ahead) + (None, None)] if ahead is not None else [])
+        arr = (_native.Cell * max(len(every), 1))()
+        keep = []
+        for i, (root, k, s0, n, tallies, totals) in enumerate(every):
+            arr[i].root_seed, arr[i].shuffle0, arr[i].k, arr[i].n_shuffles = int(root), int(s0), int(k), int(n)
+            for name, t, shape_tail in (("tallies_dev", tallies, (n_tally_ids, TALLY_WIDTH)),
+                                        ("totals_dev", totals, (TOTALS_WIDTH,))):
+                if t is not None:
+                    if t.dtype != torch.int64 or not t.is_contiguous() or tuple(t.shape[-len(shape_tail):]) != shape_tail:
+                        raise _native.NativeError(f"cell {i}: {name} must be a contiguous int64 tensor [..., "
+                                                  f"{', '.join(map(str, shape_tail))}]")
+                    keep.append(t)
+                setattr(arr[i], name, None if t is None else t.data_ptr())
+        need = int(self.lib.fb_cells_workspace_bytes(arr, len(every), n_strategies))
+        if need == 0:
+            raise _native.NativeError("bad cell list (k must divide the strategy count)")
+        if self._cells_ws is None or self._cells_ws.numel() < need:
+            torch.cuda.synchronize(self.device)   # the library's preparation stream may still write the old one
+            self._cells_ws = None
+            self._cells_ws = self.empty(need)
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.fb_play_tournament_cells(
+                arr, len(every) - (1 if ahead is not None else 0), 1 if ahead is not None else 0,
+                _ptr(strategies), _ptr(d_ids), n_strategies, n_tally_ids, target_score, max_rounds,
+                shuffles_per_slot, _ptr(self._cells_ws), self._cells_ws.numel(), self._stream()))
 
     def play_games(self, coords: np.ndarray, k: int, seat_strategies: np.ndarray, *,
                    seat_strategy_ids=None, target_score: int = 10_000, max_rounds: int = 200,

@@ -569,6 +569,121 @@ def run_cell(root_seed: int, k: int, num_shuffles: int, table, *, batch_size: in
     return tallies, totals, seen
 
 
+# ---------------------------------------------------------------------------------------------
+# Several cells over several GPUs: strong scaling of a fixed workload (configs/farkle_mega_config.yaml:
+# k in {2,3,4,5,6,8,10,12}; SURVEY.md section 8e "balance by estimated rolls")
+# ---------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class CellSegment:
+    """A rank's contiguous share of one cell: whole deterministic batches."""
+
+    cell: int          # index into the cell list
+    root_seed: int
+    k: int
+    shuffle0: int
+    n_shuffles: int
+
+
+# Measured on one B200 (profiles/r01_other_configs.json, the eight cells of one mega-config root):
+# a full-grid 4,300-shuffle cell takes 13.9 + 18.2 / k ms within 2 % for every k of the config
+# (2 -> 23.0, 4 -> 18.5, 6 -> 17.0, 12 -> 15.5): seat-exposures are constant per cell, a seat's
+# turns cost the same at every table size, and the per-game part shrinks with the game count.
+CELL_MS_CONST, CELL_MS_PER_K = 13.9, 18.2
+CELL_MS_REFERENCE_EXPOSURES = 5160 * 4300
+SEGMENT_OVERHEAD_MS = 0.5       # kernel start-up and drain tail of one more launch
+
+
+def cell_cost_ms(k: int, n_strategies: int, n_shuffles: int) -> float:
+    """Estimated single-GPU time of ``n_shuffles`` shuffles of a k-player cell."""
+    scale = n_strategies * n_shuffles / CELL_MS_REFERENCE_EXPOSURES
+    return (CELL_MS_CONST + CELL_MS_PER_K / k) * scale
+
+
+def plan_cells(cells: Sequence[Tuple[int, int, int]], n_strategies: int, world: int, *, batch_size: int,
+               cost: Callable[[int, int, int], float] = cell_cost_ms,
+               segment_overhead_ms: float = SEGMENT_OVERHEAD_MS) -> List[List[CellSegment]]:
+    """Deal the cells ``(root_seed, k, num_shuffles)`` of a run to ``world`` ranks.
+
+    The unit of ownership stays the deterministic batch (run_tournament.py:974), so every rank plays
+    whole batches and disjoint coordinate ranges.  Cells are laid end to end, most expensive first,
+    and the line is cut into ``world`` pieces of (nearly) equal estimated time: a rank gets whole
+    cells plus at most two partial ones, instead of 1/world of EVERY cell (which leaves each launch
+    too small to fill a GPU: 4.4x on 8 GPUs in round 1).  The smallest makespan for which the greedy
+    fill fits is found by bisection; every extra launch is charged ``segment_overhead_ms``.
+    Deterministic: every rank computes the same plan.
+    """
+    if world < 1 or batch_size < 1:
+        raise ValueError("bad world / batch size")
+    order = sorted(range(len(cells)), key=lambda i: (-cost(cells[i][1], n_strategies, cells[i][2]), i))
+    per_batch = {i: cost(cells[i][1], n_strategies, min(batch_size, cells[i][2]) or 1) for i in order}
+    n_batches = {i: -(-cells[i][2] // batch_size) for i in order}
+
+    def fill(limit: float) -> List[List[CellSegment]] | None:
+        plan: List[List[CellSegment]] = [[] for _ in range(world)]
+        rank, room = 0, limit
+        for i in order:
+            root, k, shuffles = cells[i]
+            done = 0
+            while done < n_batches[i]:
+                take = min(n_batches[i] - done, int((room - segment_overhead_ms) / per_batch[i] + 1e-9))
+                if take < 1:
+                    rank += 1
+                    room = limit
+                    if rank == world:
+                        return None
+                    continue
+                s0 = done * batch_size
+                plan[rank].append(CellSegment(i, root, k, s0, min(take * batch_size, shuffles - s0)))
+                room -= segment_overhead_ms + take * per_batch[i]
+                done += take
+        return plan
+
+    total = sum(per_batch[i] * n_batches[i] for i in order)
+    lo, hi = total / world, total + (len(cells) + world) * segment_overhead_ms + 1.0
+    best = fill(hi)
+    assert best is not None
+    for _ in range(40):
+        mid = 0.5 * (lo + hi)
+        got = fill(mid)
+        if got is None:
+            lo = mid
+        else:
+            best, hi = got, mid
+    return best
+
+
+def run_cells(cells: Sequence[Tuple[int, int, int]], table, *, batch_size: int, play_cells: Callable[..., None],
+              rank: int = 0, world: int = 1, plan: Sequence[Sequence[CellSegment]] | None = None):
+    """Play this rank's share of ALL cells, then merge with ONE all-reduce.
+
+    ``play_cells(segments, table)`` receives ``(root_seed, k, shuffle0, n_shuffles, tallies, totals)``
+    tuples (``Engine.play_cells`` on a GPU: pipelined launches; the CPU tests pass a stand-in) and
+    accumulates into the int64 views it is given.  Returns ``(tallies [cells, 1, n, 26], totals
+    [cells, 20])`` summed over ranks: both live in one flat buffer, so the path's exchange step is
+    a single collective for the whole run instead of one per cell.
+    """
+    import torch
+    import torch.distributed as dist
+
+    from .layout import TOTALS_WIDTH
+
+    n = len(table) if isinstance(table, np.ndarray) else table.numel() // 8
+    dev = table.device if hasattr(table, "device") else "cpu"
+    n_cells = len(cells)
+    flat = torch.zeros(n_cells * (n * TALLY_WIDTH + TOTALS_WIDTH), dtype=torch.int64, device=dev)
+    tallies = flat[: n_cells * n * TALLY_WIDTH].view(n_cells, 1, n, TALLY_WIDTH)
+    totals = flat[n_cells * n * TALLY_WIDTH:].view(n_cells, TOTALS_WIDTH)
+    if plan is None:
+        plan = plan_cells(cells, n, world, batch_size=batch_size)
+    mine = plan[rank]
+    if mine:
+        play_cells([(sg.root_seed, sg.k, sg.shuffle0, sg.n_shuffles, tallies[sg.cell], totals[sg.cell])
+                    for sg in mine], table)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat)
+    return tallies, totals
+
+
 def _engine_launch(eng, want_kw: Mapping[str, Any]):
     def launch(root_seed, k, shuffle0, n_shuffles, table, tallies, totals):
         res = eng.play_tournament(root_seed, k, shuffle0, n_shuffles, table, tallies=tallies,

@@ -310,6 +310,35 @@ int fb_play_tournament_lags(uint64_t root_seed, int k, uint64_t shuffle0, int n_
                             size_t workspace_bytes, void* stream);
 
 /* Scratch bytes the matchup grouping of n_games games needs (sort buffers, segment tables). */
+/* ---- several (root, k) cells per call, pipelined --------------------------------------
+ * One cell of a tournament run: shuffles shuffle0 .. shuffle0 + n_shuffles - 1 of (root_seed, k)
+ * (the unit `run_tournament` is called with once per k, simulation/runner.py:1326-1754; a rank's
+ * share of a cell in a multi-GPU run).  tallies_dev / totals_dev are accumulated into, as in
+ * fb_play_tournament; either may be NULL.                                                     */
+typedef struct fb_cell {
+    uint64_t root_seed;
+    uint64_t shuffle0;
+    int32_t k;
+    int32_t n_shuffles;
+    int64_t* tallies_dev; /* int64 [slots][n_tally_ids][FB_TALLY_WIDTH] */
+    int64_t* totals_dev;  /* int64 [FB_TOTALS_WIDTH] */
+} fb_cell_t;
+/* Workspace for fb_play_tournament_cells: two slots, each large enough for the largest cell. */
+size_t fb_cells_workspace_bytes(const fb_cell_t* cells, int n_cells, int n_strategies);
+/* Plays cells[0 .. n_cells) in order on `stream` with the results of fb_play_tournament called
+ * once per cell, but pipelined: the permutations and seat seeding of cell i+1 run on an internal
+ * low-priority stream, in the other workspace slot, under the end-of-launch tail and the finish /
+ * tally passes of cell i (they only touch the workspace).  n_ahead = 1 additionally PREPARES
+ * cells[n_cells] without playing it; the next call on the same workspace whose first cell equals
+ * it (same strategies, limits) starts playing at once.  A runner that knows its cell list passes
+ * it whole; one that is driven cell by cell passes the next cell as look-ahead.  No rows, seat
+ * tallies, overrides or lag statistics on this entry point (use fb_play_tournament_lags).      */
+int fb_play_tournament_cells(const fb_cell_t* cells, int n_cells, int n_ahead,
+                             const fb_strategy_t* strategies_dev, const int32_t* strategy_ids_dev,
+                             int n_strategies, int n_tally_ids, int32_t target_score,
+                             int32_t max_rounds, int shuffles_per_slot, void* workspace_dev,
+                             size_t workspace_bytes, void* stream);
+
 size_t fb_matchup_scratch_bytes(uint64_t n_games);
 
 /* Head-to-head attempts.  Replaces the attempt loop of

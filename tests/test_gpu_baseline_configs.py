@@ -263,3 +263,54 @@ def test_staging_stress_many_tiny_launches(eng, warps, monkeypatch):
         assert res.rows_numpy().tobytes() == want_rows.tobytes(), (warps, case, k)
         assert np.array_equal(res.tallies.cpu().numpy(), want_t), (warps, case, k)
         assert np.array_equal(res.totals.cpu().numpy(), want_tot), (warps, case, k)
+
+
+# ------------------------------------------------------------------------ pipelined cell lists
+def test_play_cells_equals_one_launch_per_cell(eng, full_grid):
+    """`fb_play_tournament_cells` (cells pipelined over two workspace slots, preparation on a second
+    stream, optional look-ahead cell) gives exactly what one `fb_play_tournament` per cell gives:
+    mixed k, slotted tallies, accumulation into shared tensors, a look-ahead that is used, one that
+    is not, and one that is superseded by a different first cell."""
+    import torch
+
+    from farkle_ii_b200.layout import TALLY_WIDTH, TOTALS_WIDTH
+
+    n = len(full_grid)
+    table = eng.to_device(full_grid)
+    cells = [(7, 2, 0, 60), (7, 4, 10, 45), (8, 12, 3, 20), (7, 3, 500, 33), (9, 6, 0, 41), (9, 2, 60, 60)]
+
+    def fresh():
+        return (torch.zeros((2, n, TALLY_WIDTH), dtype=torch.int64, device=eng.device),
+                torch.zeros(TOTALS_WIDTH, dtype=torch.int64, device=eng.device))
+
+    want = []
+    for root, k, s0, cnt in cells:
+        t, tot = fresh()
+        eng.play_tournament(root, k, s0, cnt, table, shuffles_per_slot=43, tallies=t, totals=tot)
+        want.append((t.cpu(), tot.cpu()))
+    # (a) the whole list in one call
+    got = [fresh() for _ in cells]
+    eng.play_cells([c + g for c, g in zip(cells, got)], table, shuffles_per_slot=43)
+    for (t, tot), (wt, wtot) in zip(got, want):
+        assert torch.equal(t.cpu(), wt) and torch.equal(tot.cpu(), wtot)
+    # (b) cell by cell with the next one as look-ahead; the last look-ahead is never played, and the
+    # call after it starts with a different cell
+    got = [fresh() for _ in cells]
+    for i, c in enumerate(cells):
+        nxt = cells[i + 1] if i + 1 < len(cells) else (1234, 5, 0, 10)
+        eng.play_cells([c + got[i]], table, ahead=nxt, shuffles_per_slot=43)
+    again = fresh()
+    eng.play_cells([cells[0] + again], table, shuffles_per_slot=43)
+    for (t, tot), (wt, wtot) in zip(got + [again], want + [want[0]]):
+        assert torch.equal(t.cpu(), wt) and torch.equal(tot.cpu(), wtot)
+    # (c) two cells accumulating into the same tensors == the union; tallies-only and totals-only cells
+    t, tot = fresh()
+    eng.play_cells([(7, 2, 0, 30, t, tot), (7, 2, 30, 30, t, None), (7, 2, 30, 30, None, tot)], table,
+                   shuffles_per_slot=0)
+    assert torch.equal(t.cpu()[0], want[0][0].sum(dim=0)) and torch.equal(tot.cpu(), want[0][1])
+    # against the oracle as well, through explicit ids
+    ids = np.arange(n, dtype=np.int32)[::-1].copy()
+    t = torch.zeros((1, n, TALLY_WIDTH), dtype=torch.int64, device=eng.device)
+    eng.play_cells([(11, 5, 2, 9, t, None)], table, strategy_ids=ids)
+    want_t, _, _ = fo.play_tournament(11, 5, 2, 9, full_grid, strategy_ids=ids, n_threads=THREADS)
+    assert np.array_equal(t.cpu().numpy(), want_t)

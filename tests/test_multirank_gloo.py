@@ -119,3 +119,99 @@ def test_two_ranks_equal_one(tmp_path, num_shuffles, batch):
     assert played == list(range(num_shuffles))           # disjoint and complete
     if num_shuffles <= batch:
         assert len(r1["launches"]) == 0                  # a rank without work still reduces
+
+
+# ------------------------------------------------------------------- several cells, one collective
+def _oracle_play_cells(log):
+    def play_cells(segments, table):
+        import oracle
+
+        for root, k, s0, n, tallies, totals in segments:
+            log.append((root, k, s0, n))
+            t, tot, _ = oracle.play_tournament(root, k, s0, n, table, n_threads=1)
+            tallies += torch.from_numpy(t)
+            totals += torch.from_numpy(tot)
+    return play_cells
+
+
+_CELLS = [(5, 2, 40), (5, 4, 40), (6, 5, 23), (6, 2, 7)]
+
+
+def _cells_worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from farkle_ii_b200 import run_tournament as frt
+        from farkle_ii_b200.strategies import generate_strategy_grid, pack_strategies
+
+        table = pack_strategies(generate_strategy_grid(
+            score_thresholds=[250, 300, 350, 400], smart_five_opts=[True], smart_one_opts=[True],
+            consider_score_opts=[True], consider_dice_opts=[True], auto_hot_dice_opts=[True],
+            run_up_score_opts=[True])[0])
+        log: list = []
+        tallies, totals = frt.run_cells(_CELLS, table, batch_size=6, play_cells=_oracle_play_cells(log),
+                                        rank=rank, world=world)
+        np.savez(Path(out_dir) / f"cells{rank}.npz", tallies=tallies.numpy(), totals=totals.numpy(),
+                 log=np.array(log, dtype=np.int64).reshape(-1, 4))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cells_over_two_ranks_one_collective(tmp_path):
+    """`run_cells`: the cells of a run dealt to the ranks along one line (whole cells plus at most two
+    partial ones per rank, whole deterministic batches), one all-reduce of the stacked tensors:
+    every rank ends up with every cell's merged tallies, every shuffle is played exactly once."""
+    import oracle
+
+    oracle.build()
+    mp.spawn(_cells_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (np.load(tmp_path / f"cells{r}.npz") for r in (0, 1))
+    from farkle_ii_b200.strategies import generate_strategy_grid, pack_strategies
+
+    table = pack_strategies(generate_strategy_grid(
+        score_thresholds=[250, 300, 350, 400], smart_five_opts=[True], smart_one_opts=[True],
+        consider_score_opts=[True], consider_dice_opts=[True], auto_hot_dice_opts=[True],
+        run_up_score_opts=[True])[0])
+    for i, (root, k, shuffles) in enumerate(_CELLS):
+        want_t, want_tot, _ = oracle.play_tournament(root, k, 0, shuffles, table, n_threads=2)
+        for r in (r0, r1):
+            assert np.array_equal(r["tallies"][i], want_t) and np.array_equal(r["totals"][i], want_tot)
+    played = sorted((int(root), int(k), s) for r in (r0, r1) for root, k, s0, n in r["log"]
+                    for s in range(s0, s0 + n))
+    assert played == sorted((root, k, s) for root, k, shuffles in _CELLS for s in range(shuffles))
+    assert len(r0["log"]) and len(r1["log"])
+
+
+def test_plan_cells_properties():
+    """The planner alone: complete and disjoint cover in whole batches, balanced estimated load,
+    at most two partial cells per rank, identical plan on every call, mega config on 1..8 ranks."""
+    from farkle_ii_b200 import run_tournament as frt
+
+    ks = (2, 3, 4, 5, 6, 8, 10, 12)
+    for roots in ((102,), (102, 103)):
+        cells = [(r, k, 4300) for r in roots for k in ks]
+        single = sum(frt.cell_cost_ms(k, 5160, 4300) + frt.SEGMENT_OVERHEAD_MS for _, k, _ in cells)
+        for world in (1, 2, 3, 4, 8):
+            plan = frt.plan_cells(cells, 5160, world, batch_size=43)
+            assert plan == frt.plan_cells(cells, 5160, world, batch_size=43) and len(plan) == world
+            cover: dict = {}
+            for segs in plan:
+                partial = 0
+                for sg in segs:
+                    assert sg.shuffle0 % 43 == 0 and (sg.n_shuffles % 43 == 0 or sg.shuffle0 + sg.n_shuffles == 4300)
+                    assert (sg.root_seed, sg.k) == cells[sg.cell][:2]
+                    cover.setdefault(sg.cell, []).append((sg.shuffle0, sg.n_shuffles))
+                    partial += sg.n_shuffles != 4300
+                assert partial <= 2
+            for i in range(len(cells)):
+                runs = sorted(cover[i])
+                assert runs[0][0] == 0 and sum(n for _, n in runs) == 4300
+                assert all(a[0] + a[1] == b[0] for a, b in zip(runs, runs[1:]))
+            loads = [sum(frt.SEGMENT_OVERHEAD_MS + frt.cell_cost_ms(sg.k, 5160, sg.n_shuffles) for sg in segs)
+                     for segs in plan]
+            assert max(loads) <= single / world * 1.04 + 1.0       # within 4 % + 1 ms of perfect balance
+    # odd sizes: ragged last batch, more ranks than batches, empty list
+    plan = frt.plan_cells([(1, 2, 10), (1, 4, 3)], 80, 5, batch_size=4)
+    assert sorted((sg.cell, sg.shuffle0, sg.n_shuffles) for segs in plan for sg in segs) == \
+        [(0, 0, 4), (0, 4, 4), (0, 8, 2), (1, 0, 3)]
+    assert frt.plan_cells([], 80, 3, batch_size=4) == [[], [], []]
