@@ -269,6 +269,8 @@ def main() -> None:
     ap.add_argument("--shuffles", type=int, default=SHUFFLES, help=argparse.SUPPRESS)
     ap.add_argument("--unpipelined", action="store_true",
                     help="one fb_play_tournament call per cell instead of the pipelined cell list")
+    ap.add_argument("--parquet-batches", type=int, default=20,
+                    help="deterministic batches of the k=2 cell written to Parquet by the e2e_parquet leg; 0 skips it")
     ap.add_argument("--strong-reps", type=int, default=3,
                     help="timed repetitions of the strong-scaling leg (mega root over the ranks); 0 skips it")
     ap.add_argument("--ref-shuffles", type=int, default=-1,
@@ -476,6 +478,54 @@ def main() -> None:
                             "n1_ms: rank 0 plays the whole root alone in the same run"}
         assert strong["games_attempted"] == mega_games
 
+    # ---- rows mode all the way to disk (rank 0, N = 1 only): the Python surface's run_tournament()
+    # with a row directory -- games -> compact rows -> D2H -> Arrow -> one Parquet shard + manifest
+    # line per shuffle (the reference's on-disk contract, run_tournament.py:530-558) on a bounded
+    # sample of the k=2 cell.  The host encode, not the GPU, sets this rate.
+    e2e_parquet = None
+    if world == 1 and args.parquet_batches > 0:
+        import shutil
+        import tempfile
+
+        from farkle_ii_b200.strategies import generate_strategy_grid
+
+        strategies = generate_strategy_grid()[0]
+        n_pq = args.parquet_batches * SHUFFLES_PER_BATCH
+        out = Path(tempfile.mkdtemp(prefix="fb_rows_"))
+        try:
+            cfg = frt.TournamentConfig(n_players=2, num_shuffles=n_pq, deterministic_batch_size=SHUFFLES_PER_BATCH)
+            frt.run_tournament(config=frt.TournamentConfig(n_players=2, num_shuffles=SHUFFLES_PER_BATCH,
+                                                           deterministic_batch_size=SHUFFLES_PER_BATCH),
+                               global_seed=ROOTS[0], checkpoint_path=out / "warm" / "c.pkl",
+                               row_output_directory=out / "warm" / "rows", num_shuffles=SHUFFLES_PER_BATCH,
+                               strategies=strategies, resume=False)                      # warm-up: imports, pools
+            for key in frt.IO_STATS:
+                frt.IO_STATS[key] = 0
+            t0 = time.perf_counter()
+            frt.run_tournament(config=cfg, global_seed=ROOTS[0], checkpoint_path=out / "run" / "2p_checkpoint.pkl",
+                               row_output_directory=out / "run" / "rows", num_shuffles=n_pq, strategies=strategies,
+                               resume=False)
+            dt = time.perf_counter() - t0
+            shards = list((out / "run" / "rows").glob("rows_*.parquet"))
+            games_pq = n_pq * (N_STRATEGIES // 2)
+            stats = dict(frt.IO_STATS)
+            threads = min(32, os.cpu_count() or 1)
+            e2e_parquet = {
+                "value": games_pq / dt, "unit": "games/s", "games": games_pq, "seconds": dt,
+                "shards": len(shards), "bytes_on_disk": sum(p.stat().st_size for p in shards),
+                "writer_threads": threads,
+                "launch_wall_s": stats["launch_wall_s"], "arrow_build_cpu_s": stats["arrow_build_cpu_s"],
+                "parquet_write_cpu_s": stats["parquet_write_cpu_s"],
+                "bottleneck": max((("Parquet encode + fsync + rename", stats["parquet_write_cpu_s"] / threads),
+                                   ("Arrow build", stats["arrow_build_cpu_s"] / threads),
+                                   ("GPU launches + D2H", stats["launch_wall_s"])), key=lambda kv: kv[1])[0],
+                "sample": f"k=2 full grid root {ROOTS[0]}, shuffles 0..{n_pq - 1}: one shard per shuffle",
+                "call": "farkle_ii_b200.run_tournament.run_tournament(row_output_directory=...) -> "
+                        "rows_{root}_{k}p_{shuffle:012d}.parquet + manifest.jsonl (temp -> fsync -> rename)"}
+            assert len(shards) == n_pq
+        finally:
+            shutil.rmtree(out, ignore_errors=True)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -583,6 +633,7 @@ def main() -> None:
                      "d2h_bytes_per_step": d2h + rows_d2h, "steps": 2,
                      "call": "fb_run_tournament_host with rows_host: tallies + one compact row per game "
                              "into pinned host memory, D2H overlapped with the next chunk's kernels"},
+        "e2e_parquet": e2e_parquet,
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roofline,

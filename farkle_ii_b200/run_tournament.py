@@ -421,11 +421,25 @@ def _write_shard(out: Path, manifest_file: Path, table, manifest_extra: Mapping[
     _append_manifest(manifest_file, {"path": out.name, "rows": table.num_rows, **manifest_extra})
 
 
+# Where rows mode spends its host time (reset by the caller; bench.py's e2e_parquet leg reads it):
+# wall seconds inside the launches (kernels + D2H of the rows), CPU-seconds of the Arrow build and
+# of the Parquet encode + fsync + rename summed over the writer threads.
+IO_STATS: Dict[str, float] = {"launch_wall_s": 0.0, "arrow_build_cpu_s": 0.0, "parquet_write_cpu_s": 0.0,
+                              "shards": 0}
+_IO_LOCK = __import__("threading").Lock()
+
+
+def _now() -> float:
+    import time
+
+    return time.perf_counter()
+
+
 def _run_chunk_metrics(shuffle_tasks: Sequence[ShuffleTask | int], *, collect_rows: bool = False,
                        row_dir: Path | None = None, manifest_path: Path | None = None,
                        row_sidecar: object | None = None,
-                       shard_writer: Callable[[Path, Path, Any, Mapping[str, Any]], None] | None = None
-                       ) -> Tuple[Counter, MetricSums, MetricSums]:
+                       shard_writer: Callable[[Path, Path, Any, Mapping[str, Any]], None] | None = None,
+                       io_threads: int | None = None) -> Tuple[Counter, MetricSums, MetricSums]:
     """Play shuffles and accumulate metrics (run_tournament.py:473-585).
 
     In rows mode every shuffle leaves one Parquet shard
@@ -435,6 +449,11 @@ def _run_chunk_metrics(shuffle_tasks: Sequence[ShuffleTask | int], *, collect_ro
     ``run_streaming_shard`` so that hash-bound sidecars come out exactly as the reference
     writes them.  ``row_sidecar`` without such a writer is refused: the artifact contract is
     outside this path.
+
+    With the default writer the Arrow build and the Parquet encode of the shards run on
+    ``io_threads`` host threads (default: the host cores, at most 32; pyarrow and numpy release the
+    GIL) while the next launch is already playing; manifest lines are appended in shuffle order once
+    their shard is on disk.  A custom ``shard_writer`` is called sequentially, in order.
     """
     if row_sidecar is not None and shard_writer is None:
         raise NotImplementedError("row_sidecar needs a shard_writer that implements the artifact contract")
@@ -444,31 +463,73 @@ def _run_chunk_metrics(shuffle_tasks: Sequence[ShuffleTask | int], *, collect_ro
     sums_total: MetricSums = {m: defaultdict(float) for m in METRIC_LABELS}
     sq_total: MetricSums = {m: defaultdict(float) for m in METRIC_LABELS}
     want_rows = collect_rows and row_dir is not None
-    writer = shard_writer or _write_shard
     gps = state.cfg.games_per_shuffle
-    for a, b in _contiguous_runs(tasks):
-        run = tasks[a:b]
-        tallies, games, rows, seen = _launch_run(state, run, want_rows=want_rows)
-        wins, sums, sqs = tallies_to_outcome(tallies, state.ids, games, seen)
-        wins_total.absorb(wins)
-        for label in METRIC_LABELS:
-            for key, v in sums[label].items():
-                sums_total[label][key] += v
-            for key, v in sqs[label].items():
-                sq_total[label][key] += v
-        if not want_rows:
-            continue
-        rows = rows.copy()
-        rows["seats"]["strategy"] = state.ids[rows["seats"]["strategy"]]
-        for i, task in enumerate(run):
-            shard = rows[i * gps:(i + 1) * gps]
-            tbl = compact_rows_to_table(
-                shard, root_seed=task.root_seed, k=task.k, shuffle_index=task.shuffle_index,
-                game_index=np.arange(gps), deterministic_batch_id=task.deterministic_batch_id,
-                shuffle_seed=task.shuffle_seed)
-            out = Path(row_dir) / f"rows_{task.root_seed}_{task.k}p_{task.shuffle_index:012d}.parquet"
-            writer(out, Path(manifest_path or (Path(row_dir) / "manifest.jsonl")), tbl,
-                   shard_manifest_extra(state, task, out.name))
+    manifest_file = Path(manifest_path or (Path(row_dir) / "manifest.jsonl")) if want_rows else None
+    threads = io_threads if io_threads is not None else min(32, os.cpu_count() or 1)
+    pool = None
+    pending: List[Tuple[Any, Path, Mapping[str, Any]]] = []       # (future, shard path, manifest record)
+
+    def shard_table(shard: np.ndarray, task: ShuffleTask):
+        return compact_rows_to_table(
+            shard, root_seed=task.root_seed, k=task.k, shuffle_index=task.shuffle_index,
+            game_index=np.arange(gps), deterministic_batch_id=task.deterministic_batch_id,
+            shuffle_seed=task.shuffle_seed)
+
+    def build_and_write(shard: np.ndarray, task: ShuffleTask, out: Path) -> int:
+        import time
+
+        import pyarrow.parquet as pq
+
+        t0 = time.perf_counter()
+        tbl = shard_table(shard, task)
+        t1 = time.perf_counter()
+        _atomic_write(out, lambda p: pq.write_table(tbl, p))
+        t2 = time.perf_counter()
+        with _IO_LOCK:
+            IO_STATS["arrow_build_cpu_s"] += t1 - t0
+            IO_STATS["parquet_write_cpu_s"] += t2 - t1
+            IO_STATS["shards"] += 1
+        return tbl.num_rows
+
+    def drain() -> None:
+        for fut, out, extra in pending:
+            _append_manifest(manifest_file, {"path": out.name, "rows": fut.result(), **extra})
+        pending.clear()
+
+    try:
+        for a, b in _contiguous_runs(tasks):
+            run = tasks[a:b]
+            t_launch = _now()
+            tallies, games, rows, seen = _launch_run(state, run, want_rows=want_rows)
+            IO_STATS["launch_wall_s"] += _now() - t_launch
+            wins, sums, sqs = tallies_to_outcome(tallies, state.ids, games, seen)
+            wins_total.absorb(wins)
+            _add_sums(sums_total, sums)
+            _add_sums(sq_total, sqs)
+            if not want_rows:
+                continue
+            rows = rows.copy()
+            rows["seats"]["strategy"] = state.ids[rows["seats"]["strategy"]]
+            drain()                 # the previous launch's shards (written while this one played)
+            for i, task in enumerate(run):
+                shard = rows[i * gps:(i + 1) * gps]
+                out = Path(row_dir) / f"rows_{task.root_seed}_{task.k}p_{task.shuffle_index:012d}.parquet"
+                extra = shard_manifest_extra(state, task, out.name)
+                if shard_writer is not None:
+                    shard_writer(out, manifest_file, shard_table(shard, task), extra)
+                elif threads <= 1:
+                    _append_manifest(manifest_file, {"path": out.name, "rows": build_and_write(shard, task, out),
+                                                     **extra})
+                else:
+                    if pool is None:
+                        from concurrent.futures import ThreadPoolExecutor
+
+                        pool = ThreadPoolExecutor(max_workers=threads, thread_name_prefix="fb-shard")
+                    pending.append((pool.submit(build_and_write, shard, task, out), out, extra))
+        drain()
+    finally:
+        if pool is not None:
+            pool.shutdown(wait=True)
     return wins_total, sums_total, sq_total
 
 
@@ -692,22 +753,173 @@ def _engine_launch(eng, want_kw: Mapping[str, Any]):
     return launch
 
 
+ROWS_LAUNCH_BATCHES = 8      # deterministic batches per launch in rows mode (fills the GPU)
+
+
+def _checkpoint_meta(cfg: TournamentConfig, global_seed: int, profile: GameProfile | None,
+                     extra: Mapping[str, Any] | None) -> Dict[str, Any]:
+    """The reference's checkpoint ``meta`` block, key for key (run_tournament.py:1139-1171)."""
+    meta: Dict[str, Any] = {
+        "n_players": cfg.n_players, "num_shuffles": cfg.num_shuffles, "global_seed": global_seed,
+        "n_strategies": cfg.n_strategies, "rng_scheme_version": RNG_SCHEME_VERSION,
+        "outcome_schema_version": OUTCOME_SCHEMA_VERSION,
+        "tournament_method_version": TOURNAMENT_METHOD_VERSION, "rng_bit_generator": "PCG64DXSM",
+        "coordinate_contract_version": 2,
+        "shuffle_purpose_namespace": int(RandomPurpose.TOURNAMENT_SHUFFLE),
+        "shuffle_permutation_purpose_namespace": int(RandomPurpose.SHUFFLE_PERMUTATION),
+        "game_purpose_namespace": int(RandomPurpose.TOURNAMENT_GAME),
+        "player_purpose_namespace": int(RandomPurpose.TOURNAMENT_PLAYER),
+        "deterministic_batch_size": cfg.deterministic_batch_size,
+    }
+    if profile is not None:
+        meta["game_profile_sha256"] = profile.sha256
+    if extra:
+        meta.update(extra)
+    return meta
+
+
+def _save_checkpoint(path: Path, wins: OutcomeCounter, sums: MetricSums | None, sqs: MetricSums | None,
+                     meta: Mapping[str, Any]) -> None:
+    """run_tournament.py:622-651 (without the sidecar: the artifact contract is outside this path)."""
+    payload: Dict[str, Any] = {"win_totals": wins, "outcome_counts": wins.outcome_payload()}
+    if sums is not None and sqs is not None:
+        payload["metric_sums"] = {m: dict(v) for m, v in sums.items()}
+        payload["metric_square_sums"] = {m: dict(v) for m, v in sqs.items()}
+    if meta:
+        payload["meta"] = dict(meta)
+    _atomic_write(path, lambda p: p.write_bytes(pickle.dumps(payload, protocol=pickle.HIGHEST_PROTOCOL)))
+
+
+def _load_checkpoint(path: Path) -> Tuple[OutcomeCounter, MetricSums | None, MetricSums | None, set[int]]:
+    """Aggregates and completed shuffles of an earlier run (run_tournament.py:1243-1330)."""
+    payload = pickle.loads(path.read_bytes())
+    meta = payload.get("meta", {}) if isinstance(payload, Mapping) else {}
+    if "rng_scheme_version" in meta and meta["rng_scheme_version"] != RNG_SCHEME_VERSION:
+        raise ValueError("Checkpoint RNG scheme is stale or unsupported; restart from a v2 output root")
+    wins = payload["win_totals"]
+    if not isinstance(wins, OutcomeCounter):
+        wins = _restore_outcome_counter(dict(wins), payload.get("outcome_counts") or {})
+
+    def coerce(raw: Any) -> MetricSums | None:
+        if raw is None:
+            return None
+        return {m: defaultdict(float, raw.get(m, {})) for m in METRIC_LABELS}
+
+    return (wins, coerce(payload.get("metric_sums")), coerce(payload.get("metric_square_sums")),
+            {int(v) for v in meta.get("completed_shuffle_indices", [])})
+
+
+def _add_sums(total: MetricSums, part: MetricSums) -> None:
+    for label in METRIC_LABELS:
+        for key, v in part[label].items():
+            total[label][key] += v
+
+
+def _write_metric_chunk(directory: Path, state: WorkerState, root: int, tasks: Sequence[ShuffleTask],
+                        wins: OutcomeCounter, sums: MetricSums, sqs: MetricSums) -> None:
+    """One ``metrics_{chunk:06d}.parquet`` + manifest line per deterministic batch
+    (run_tournament.py:1603-1668; chunk indices are 1-based, :944-984)."""
+    import pyarrow as pa
+
+    chunk_index = tasks[0].deterministic_batch_id + 1
+    rows = []
+    for label in METRIC_LABELS:
+        for strat in sorted(set(sums[label]) | set(wins.attempted_exposures), key=str):
+            rows.append({"metric": label, "strategy": strat, "sum": sums[label].get(strat, 0.0),
+                         "square_sum": sqs[label][strat] if strat in sqs[label] else 0.0,
+                         "wins": int(wins.get(strat, 0)),
+                         "attempted_exposures": int(wins.attempted_exposures.get(strat, 0)),
+                         "completed_exposures": int(wins.completed_exposures.get(strat, 0)),
+                         "safety_limit_exposures": int(wins.safety_limit_exposures.get(strat, 0))})
+    tbl = pa.Table.from_pylist(rows)
+    out = directory / f"metrics_{chunk_index:06d}.parquet"
+    extra: Dict[str, Any] = {
+        "chunk_index": chunk_index, "process_block_index": chunk_index, "root_seed": root,
+        "n_players": state.cfg.n_players, "deterministic_batch_id": tasks[0].deterministic_batch_id,
+        "shuffle_index_start": tasks[0].shuffle_index, "shuffle_index_end": tasks[-1].shuffle_index,
+        "shuffle_count": len(tasks), "shuffle_indices": [t.shuffle_index for t in tasks],
+        "shuffle_seeds": [t.shuffle_seed for t in tasks], "rng_scheme_version": RNG_SCHEME_VERSION,
+        "rng_purpose_namespace": int(RandomPurpose.TOURNAMENT_SHUFFLE),
+        "outcome_schema_version": OUTCOME_SCHEMA_VERSION,
+        "tournament_method_version": TOURNAMENT_METHOD_VERSION}
+    if state.game_profile is not None:
+        extra["game_profile_sha256"] = state.game_profile.sha256
+    _write_shard(out, directory / "metrics_manifest.jsonl", tbl, extra)
+
+
+def _load_metric_chunk_aggregates(manifest_path: Path, k: int) -> Tuple[OutcomeCounter, MetricSums, MetricSums]:
+    """Aggregates rebuilt from the metric-chunk shards a manifest lists, in manifest order
+    (run_tournament.py:866-941).  This is what the reference's final checkpoint holds when a run
+    with a metric-chunk directory started without checkpointed sums: every strategy that was
+    seated appears, zeros included, keyed in the chunk tables' order."""
+    import pyarrow.parquet as pq
+
+    wins = OutcomeCounter()
+    sums: MetricSums = {m: defaultdict(float) for m in METRIC_LABELS}
+    sqs: MetricSums = {m: defaultdict(float) for m in METRIC_LABELS}
+    for line in manifest_path.read_text().splitlines():
+        if not line.strip():
+            continue
+        chunk = manifest_path.parent / json.loads(line)["path"]
+        if not chunk.exists():
+            raise FileNotFoundError(f"Missing metric chunk listed in manifest: {chunk}")
+        for row in pq.read_table(chunk).to_pylist():
+            label, strategy = row["metric"], row["strategy"]
+            sums[label][strategy] += float(row["sum"])
+            sqs[label][strategy] += float(row["square_sum"])
+            if label == METRIC_LABELS[0]:
+                wins[strategy] += int(row["wins"])
+                wins.attempted_exposures[strategy] += int(row["attempted_exposures"])
+                wins.completed_exposures[strategy] += int(row["completed_exposures"])
+                wins.safety_limit_exposures[strategy] += int(row["safety_limit_exposures"])
+    wins.games_completed = int(sum(wins.values()))
+    wins.games_attempted = int(sum(wins.attempted_exposures.values())) // k
+    wins.games_safety_limit = int(sum(wins.safety_limit_exposures.values())) // k
+    return wins, sums, sqs
+
+
+def _manifest_int_set(path: Path, key: str) -> set[int]:
+    out: set[int] = set()
+    if path.exists():
+        for line in path.read_text().splitlines():
+            if line.strip():
+                rec = json.loads(line)
+                if key in rec:
+                    out.add(int(rec[key]))
+    return out
+
+
 def run_tournament(*, config: TournamentConfig | None = None, global_seed: int = 0,
                    checkpoint_path: Path | str = "checkpoint.pkl", n_jobs: int | None = None,
                    collect_metrics: bool = False, row_output_directory: Path | None = None,
+                   metric_chunk_directory: Path | None = None,
                    num_shuffles: int = NUM_SHUFFLES,
                    strategies: Sequence[ThresholdStrategy] | None = None, resume: bool = True,
                    checkpoint_metadata: Mapping[str, Any] | None = None,
                    oracle_game_profile: GameProfile | None = None,
-                   write_final_metrics_artifact: bool = True, device: int | None = None) -> None:
+                   write_final_metrics_artifact: bool = True, device: int | None = None,
+                   io_threads: int | None = None) -> None:
     """Run one (root, k) tournament cell on the GPU(s) (run_tournament.py:1050-1859).
 
-    Keeps the reference's observable results: the checkpoint pickle
-    ``{"win_totals": OutcomeCounter, "outcome_counts", "metric_sums", "metric_square_sums",
-    "meta"}`` and ``{k}p_metrics.parquet``; with ``row_output_directory`` one Parquet shard +
-    manifest line per shuffle (already-listed shuffles are skipped when ``resume``).
-    ``n_jobs`` is accepted for compatibility: parallelism is the GPU's.
+    Keeps the reference's observable results: the checkpoint pickle ``{"win_totals":
+    OutcomeCounter, "outcome_counts", "metric_sums", "metric_square_sums", "meta"}`` (``meta`` key
+    for key, with ``completed_shuffle_indices`` / ``completed_process_block_indices``),
+    ``{k}p_metrics.parquet``, with ``row_output_directory`` one Parquet shard + manifest line per
+    shuffle, with ``metric_chunk_directory`` one ``metrics_{chunk}.parquet`` + manifest line per
+    deterministic batch, a checkpoint every ``config.ckpt_every_sec`` seconds, and resume: shuffles
+    listed in the checkpoint are not replayed, shuffles whose row shard is already in the manifest
+    are not rewritten (their tallies are replayed on the GPU, which costs microseconds, instead of
+    re-reading the shards as the reference does, :820-863).  Every game is played ONCE: rows and
+    tallies come out of the same launches.  ``n_jobs`` is accepted for compatibility: parallelism
+    is the GPU's (and ``io_threads`` Parquet writers on the host).
+
+    Two routes.  Plain tallies (no rows, no metric chunks, nothing to resume): one launch per rank
+    for the whole cell, one all-reduce of the tally tensor.  Otherwise the cell is walked in groups
+    of deterministic batches; ranks own contiguous blocks of batches and their partial counters are
+    joined in rank (= batch) order.
     """
+    import time
+
     import torch
     import torch.distributed as dist
 
@@ -719,6 +931,8 @@ def run_tournament(*, config: TournamentConfig | None = None, global_seed: int =
     cfg = config or TournamentConfig()
     if num_shuffles != cfg.num_shuffles:
         cfg.num_shuffles = num_shuffles
+    if cfg.deterministic_batch_size < 1:
+        raise ValueError("deterministic_batch_size must be positive")
     _init_worker(strategies, cfg, oracle_game_profile, device=device)
     state = _require_state()
     k, root = cfg.n_players, int(global_seed)
@@ -726,71 +940,152 @@ def run_tournament(*, config: TournamentConfig | None = None, global_seed: int =
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     ckpt_path = Path(checkpoint_path)
     collect_rows = row_output_directory is not None
-    if collect_rows:
-        row_dir = Path(row_output_directory)
-        manifest = row_dir / "manifest.jsonl"
-        done: set[int] = set()
-        if resume and manifest.exists():
-            for line in manifest.read_text().splitlines():
-                if line.strip():
-                    done.add(int(json.loads(line)["shuffle_index"]))
-        wins, sums, sqs = OutcomeCounter(), None, None
-        for _, s0, cnt in shard_batches(cfg.num_shuffles, cfg.deterministic_batch_size, rank, world):
-            pending = [s for s in range(s0, s0 + cnt) if s not in done]
-            tasks = make_shuffle_tasks(root, k, pending, cfg.deterministic_batch_size)
-            if tasks:
-                _run_chunk_metrics(tasks, collect_rows=True, row_dir=row_dir, manifest_path=manifest)
-        if world > 1:
-            dist.barrier()
-    eng = get_engine(state.device)
-    prof = state.game_profile
-    if prof and prof.tournament_max_rounds_overrides:
-        kw = dict(target_score=prof.default_target_score, max_rounds=prof.default_max_rounds)
+    want_sums = collect_metrics or collect_rows
+    meta = _checkpoint_meta(cfg, root, oracle_game_profile, checkpoint_metadata)
+    batch = cfg.deterministic_batch_size
+    n_batches = -(-cfg.num_shuffles // batch)
 
-        def launch(root_seed, kk, s0, n, table, tallies, totals):
-            res = eng.play_tournament(root_seed, kk, s0, n, table, tallies=tallies, totals=totals,
-                                      overrides=prof.tournament_overrides_for(root_seed, kk, s0, n),
-                                      want_first_seen=True, **kw)
-            return res.tallies, res.totals, res.first_seen
+    wins_prev, sums_prev, sqs_prev, completed = OutcomeCounter(), None, None, set()
+    if resume and ckpt_path.exists():
+        wins_prev, sums_prev, sqs_prev, completed = _load_checkpoint(ckpt_path)
+        completed &= set(range(cfg.num_shuffles))
+    row_dir = Path(row_output_directory) if collect_rows else None
+    row_manifest = row_dir / "manifest.jsonl" if row_dir else None
+    rows_done = _manifest_int_set(row_manifest, "shuffle_index") if (row_manifest and resume) else set()
+    chunk_dir = Path(metric_chunk_directory) if metric_chunk_directory is not None else None
+    chunks_done = (_manifest_int_set(chunk_dir / "metrics_manifest.jsonl", "chunk_index")
+                   if (chunk_dir and resume) else set())
+    if chunk_dir:
+        chunk_dir.mkdir(parents=True, exist_ok=True)
+
+    plain = not collect_rows and chunk_dir is None and not completed
+    if plain:
+        eng = get_engine(state.device)
+        prof = state.game_profile
+        if prof and prof.tournament_max_rounds_overrides:
+            kw = dict(target_score=prof.default_target_score, max_rounds=prof.default_max_rounds)
+
+            def launch(root_seed, kk, s0, n, table, tallies, totals):
+                res = eng.play_tournament(root_seed, kk, s0, n, table, tallies=tallies, totals=totals,
+                                          overrides=prof.tournament_overrides_for(root_seed, kk, s0, n),
+                                          want_first_seen=True, **kw)
+                return res.tallies, res.totals, res.first_seen
+        else:
+            kw = dict(target_score=prof.default_target_score, max_rounds=prof.default_max_rounds) if prof else {}
+            launch = _engine_launch(eng, kw)
+        table_dev = eng.to_device(state.table)
+        tallies, totals, seen = run_cell(root, k, cfg.num_shuffles, table_dev, batch_size=batch, launch=launch,
+                                         rank=rank, world=world, want_first_seen=True)
+        if torch.device(eng.device).type == "cuda":
+            torch.cuda.synchronize(eng.device)
+        if rank != 0:
+            return
+        tot = totals.cpu().numpy()
+        if tot[7]:
+            raise RuntimeError("a game hit ROLL_LIMIT or overflowed an int16 row counter")
+        wins, sums, sqs = tallies_to_outcome(tallies.cpu().numpy()[0], state.ids, tuple(tot[:3]),
+                                             seen.cpu().numpy())
     else:
-        kw = dict(target_score=prof.default_target_score, max_rounds=prof.default_max_rounds) if prof else {}
-        launch = _engine_launch(eng, kw)
-    table_dev = eng.to_device(state.table)
-    tallies, totals, seen = run_cell(root, k, cfg.num_shuffles, table_dev,
-                                     batch_size=cfg.deterministic_batch_size, launch=launch, rank=rank,
-                                     world=world, want_first_seen=True)
-    torch.cuda.synchronize(eng.device)
-    if rank != 0:
-        return
-    tot = totals.cpu().numpy()
-    if tot[7]:
-        raise RuntimeError("a game hit ROLL_LIMIT or overflowed an int16 row counter")
-    wins, sums, sqs = tallies_to_outcome(tallies.cpu().numpy()[0], state.ids, tuple(tot[:3]),
-                                         seen.cpu().numpy())
-    payload: Dict[str, Any] = {"win_totals": wins, "outcome_counts": wins.outcome_payload()}
-    if collect_metrics or collect_rows:
-        payload["metric_sums"] = {m: dict(v) for m, v in sums.items()}
-        payload["metric_square_sums"] = {m: dict(v) for m, v in sqs.items()}
-    if checkpoint_metadata:
-        payload["meta"] = dict(checkpoint_metadata)
-    _atomic_write(ckpt_path, lambda p: p.write_bytes(pickle.dumps(payload, protocol=pickle.HIGHEST_PROTOCOL)))
-    if write_final_metrics_artifact and (collect_metrics or collect_rows):
+        # ---- batched route: groups of whole deterministic batches, in order
+        wins, sums, sqs = OutcomeCounter(), {m: defaultdict(float) for m in METRIC_LABELS}, \
+            {m: defaultdict(float) for m in METRIC_LABELS}
+        mine = shard_batches(cfg.num_shuffles, batch, rank, world)
+        per_group = 1 if chunk_dir else ROWS_LAUNCH_BATCHES
+        newly: set[int] = set()
+        last_ckpt = time.monotonic()
+        for g0 in range(0, len(mine), per_group):
+            group = mine[g0:g0 + per_group]
+            shuffles = [s for _, s0, cnt in group for s in range(s0, s0 + cnt)]
+            count = [s for s in shuffles if s not in completed]           # tallies still owed
+            need_rows = [s for s in shuffles if collect_rows and s not in rows_done]
+            both = [s for s in count if s in set(need_rows)]
+            only_tallies = [s for s in count if s not in set(need_rows)]
+            only_rows = [s for s in need_rows if s in completed]
+            part_w, part_s, part_q = OutcomeCounter(), {m: defaultdict(float) for m in METRIC_LABELS}, \
+                {m: defaultdict(float) for m in METRIC_LABELS}
+            for todo, rows_on, counted in ((both, True, True), (only_tallies, False, True),
+                                           (only_rows, True, False)):
+                if not todo:
+                    continue
+                w, sm, sq = _run_chunk_metrics(make_shuffle_tasks(root, k, todo, batch), collect_rows=rows_on,
+                                               row_dir=row_dir, manifest_path=row_manifest, io_threads=io_threads)
+                if counted:
+                    part_w.absorb(w)
+                    _add_sums(part_s, sm)
+                    _add_sums(part_q, sq)
+            if chunk_dir and count and (group[0][0] + 1) not in chunks_done:
+                _write_metric_chunk(chunk_dir, state, root, make_shuffle_tasks(root, k, count, batch),
+                                    part_w, part_s, part_q)
+            wins.absorb(part_w)
+            _add_sums(sums, part_s)
+            _add_sums(sqs, part_q)
+            newly |= set(count)
+            if world == 1 and time.monotonic() - last_ckpt >= cfg.ckpt_every_sec:
+                done_now = completed | newly
+                w_now = OutcomeCounter()
+                w_now.absorb(wins_prev)
+                w_now.absorb(wins)
+                s_now = {m: defaultdict(float, (sums_prev or {}).get(m, {})) for m in METRIC_LABELS}
+                q_now = {m: defaultdict(float, (sqs_prev or {}).get(m, {})) for m in METRIC_LABELS}
+                _add_sums(s_now, sums)
+                _add_sums(q_now, sqs)
+                _save_checkpoint(ckpt_path, w_now, s_now if want_sums else None, q_now if want_sums else None,
+                                 {**meta, "completed_shuffle_indices": sorted(done_now),
+                                  "completed_process_block_indices": sorted({s // batch + 1 for s in done_now})})
+                last_ckpt = time.monotonic()
+        if world > 1:   # join the ranks' partial counters in rank order (= batch order)
+            parts: List[Any] = [None] * world
+            dist.all_gather_object(parts, (wins, sums, sqs, sorted(newly)))
+            wins, sums, sqs, newly = OutcomeCounter(), {m: defaultdict(float) for m in METRIC_LABELS}, \
+                {m: defaultdict(float) for m in METRIC_LABELS}, set()
+            for w, sm, sq, done in parts:
+                wins.absorb(w)
+                _add_sums(sums, sm)
+                _add_sums(sqs, sq)
+                newly |= set(done)
+        if rank != 0:
+            return
+        if chunk_dir and sums_prev is None and (chunk_dir / "metrics_manifest.jsonl").exists():
+            # no checkpointed sums to add to: the reference takes the run's aggregates from the
+            # chunk shards themselves (run_tournament.py:1770-1784)
+            wins, sums, sqs = _load_metric_chunk_aggregates(chunk_dir / "metrics_manifest.jsonl", k)
+            wins_prev = OutcomeCounter()
+        total_w = OutcomeCounter()
+        total_w.absorb(wins_prev)
+        total_w.absorb(wins)
+        wins = total_w
+        for prev, cur in ((sums_prev, sums), (sqs_prev, sqs)):
+            if prev is not None:
+                for label in METRIC_LABELS:          # earlier aggregates first: the reference's key order
+                    merged = defaultdict(float, prev[label])
+                    for key, v in cur[label].items():
+                        merged[key] += v
+                    cur[label] = merged
+        completed |= newly
+    if plain:
+        completed = set(range(cfg.num_shuffles))
+    meta["completed_shuffle_indices"] = sorted(completed)
+    meta["completed_process_block_indices"] = sorted({s // batch + 1 for s in completed})
+    del n_batches
+    _save_checkpoint(ckpt_path, wins, sums if want_sums else None, sqs if want_sums else None, meta)
+    if write_final_metrics_artifact and want_sums:
         import pyarrow as pa
         import pyarrow.parquet as pq
 
-        # label-major rows for the strategies that won at least once (run_tournament.py:1797-1826),
-        # built column-wise from the tally tensor
-        t_np = tallies.cpu().numpy()[0]
-        won = np.flatnonzero(t_np[:, T_WINS])
-        n_lab = len(METRIC_LABELS)
+        # label-major rows for the strategies that won at least once (run_tournament.py:1797-1826)
+        labels, strategies_col, sum_col, sq_col = [], [], [], []
+        for label in METRIC_LABELS:
+            for strat, value in sums[label].items():
+                labels.append(label)
+                strategies_col.append(int(strat))
+                sum_col.append(float(value))
+                sq_col.append(float(sqs[label].get(strat, 0.0)))
         schema = pa.schema([pa.field("metric", pa.string()), pa.field("strategy", pa.int32()),
                             pa.field("sum", pa.float64()), pa.field("square_sum", pa.float64())])
-        tbl = pa.Table.from_arrays([
-            pa.array(np.repeat(np.array(METRIC_LABELS, dtype=object), len(won)), type=pa.string()),
-            pa.array(np.tile(state.ids[won], n_lab).astype(np.int32)),
-            pa.array(t_np[won, T_SUMS:T_SUMS + n_lab].T.reshape(-1).astype(np.float64)),
-            pa.array(t_np[won, T_SQ_SUMS:T_SQ_SUMS + n_lab].T.reshape(-1).astype(np.float64)),
-        ], schema=schema)
+        tbl = pa.Table.from_arrays([pa.array(labels, type=pa.string()),
+                                    pa.array(np.asarray(strategies_col, dtype=np.int32)),
+                                    pa.array(np.asarray(sum_col, dtype=np.float64)),
+                                    pa.array(np.asarray(sq_col, dtype=np.float64))], schema=schema)
         _atomic_write(ckpt_path.with_name(f"{k}p_metrics.parquet"), lambda p: pq.write_table(tbl, p))
     LOGGER.info("Tournament run complete after %d attempted games", wins.games_attempted)
 

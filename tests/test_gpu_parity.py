@@ -421,7 +421,9 @@ def test_run_tournament_end_to_end(eng, golden_dir, tmp_path):
                        num_shuffles=600, strategies=strategies, checkpoint_metadata={"seed": 42})
     payload = pickle.loads(ckpt.read_bytes())
     wins = payload["win_totals"]
-    assert isinstance(wins, frt.OutcomeCounter) and payload["meta"] == {"seed": 42}
+    assert isinstance(wins, frt.OutcomeCounter) and payload["meta"]["seed"] == 42
+    assert payload["meta"]["completed_shuffle_indices"] == list(range(600))
+    assert payload["meta"]["completed_process_block_indices"] == list(range(1, 21))
     assert (wins.games_attempted, wins.games_completed, wins.games_safety_limit) == (24000, 23801, 199)
     assert [wins[i] for i in (42, 46, 51, 37, 25)] == [330, 322, 407, 386, 140]
     want = z["tallies"]

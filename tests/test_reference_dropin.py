@@ -461,3 +461,96 @@ def test_h2h_stage_with_gpu_block_runner(tmp_path, backend, runner_kind, chunk):
     assert files_a == files_b and any("h2h" in str(f) for f in files_a)
     different = [str(f) for f in files_a if (outs["cpu"] / f).read_bytes() != (outs["gpu"] / f).read_bytes()]
     assert different == [], different
+
+
+def test_standalone_driver_against_reference_driver(ref_rt, tmp_path, monkeypatch):
+    """`farkle_ii_b200.run_tournament.run_tournament` (no reference code involved) against the
+    reference's own `run_tournament` on the same cell: rows + metric chunks + checkpoint, then an
+    interrupted run resumed from its checkpoint and manifests (run_tournament.py:1243-1373).
+
+    Same checkpoint contents (win totals incl. key order, outcome counts, metric sums and squares,
+    `meta` key for key), same `{k}p_metrics.parquet`, same row shards and manifest records, same
+    metric-chunk tables and manifest records."""
+    import json
+
+    import pyarrow.parquet as pq
+    from farkle.simulation import simulation as ref_sim
+
+    from farkle_ii_b200 import run_tournament as frt
+    from farkle_ii_b200.strategies import generate_strategy_grid
+
+    rt = ref_rt
+    ref_strats = _grid(ref_sim)
+    my_strats = generate_strategy_grid(
+        score_thresholds=[250, 300, 350, 400], smart_five_opts=[True], smart_one_opts=[True],
+        consider_score_opts=[True], consider_dice_opts=[True], auto_hot_dice_opts=[True],
+        run_up_score_opts=[True])[0]
+    k, root, shuffles, batch = 4, 77, 23, 5
+
+    def run(mod, strats, out, n=shuffles, chunks=True, **kw):
+        cfg = mod.TournamentConfig(n_players=k, num_shuffles=n, deterministic_batch_size=batch)
+        mod.run_tournament(config=cfg, global_seed=root, checkpoint_path=out / f"{k}p_checkpoint.pkl",
+                           n_jobs=1, collect_metrics=True, row_output_directory=out / "rows",
+                           metric_chunk_directory=(out / "chunks") if chunks else None, num_shuffles=n,
+                           strategies=strats, checkpoint_metadata={"run": "t"}, **kw)
+
+    def payload(out):
+        p = pickle.loads((out / f"{k}p_checkpoint.pkl").read_bytes())
+        w = p["win_totals"]
+        return {"wins": list(dict(w).items()), "outcome": p["outcome_counts"],
+                "sums": {m: list(v.items()) for m, v in p["metric_sums"].items()},
+                "squares": {m: list(v.items()) for m, v in p["metric_square_sums"].items()},
+                "meta": list(p["meta"].items())}
+
+    def manifest(path, drop=("pid", "ts", "timestamp", "written_at")):
+        return [{a: b for a, b in json.loads(x).items() if a not in drop}
+                for x in path.read_text().splitlines()]
+
+    def same_outputs(a, b):
+        assert payload(a) == payload(b)
+        key = ["metric", "strategy"]
+        ta, tb = (pq.read_table(d / f"{k}p_metrics.parquet") for d in (a, b))
+        assert ta.schema == tb.schema and ta.equals(tb)
+        for sub, mname in (("rows", "manifest.jsonl"), ("chunks", "metrics_manifest.jsonl")):
+            if not (a / sub).exists():
+                assert not (b / sub).exists()
+                continue
+            ma, mb = manifest(a / sub / mname), manifest(b / sub / mname)
+            assert ma == mb and len(ma) == (shuffles if sub == "rows" else -(-shuffles // batch))
+            for rec in ma:
+                xa, xb = pq.read_table(a / sub / rec["path"]), pq.read_table(b / sub / rec["path"])
+                assert xa.schema == xb.schema and xa.equals(xb), rec["path"]
+        del key
+
+    ref_out, my_out = tmp_path / "ref", tmp_path / "mine"
+    run(rt, ref_strats, ref_out, resume=False)
+    run(frt, my_strats, my_out, resume=False)
+    same_outputs(ref_out, my_out)
+    # rows + metrics without a chunk directory: aggregates absorbed batch by batch (key order of the
+    # reference's parent loop, run_tournament.py:1596-1705)
+    run(rt, ref_strats, tmp_path / "ref2", chunks=False, resume=False)
+    run(frt, my_strats, tmp_path / "mine2", chunks=False, resume=False)
+    same_outputs(tmp_path / "ref2", tmp_path / "mine2")
+    # interrupted after 11 shuffles (a checkpoint, 11 row shards, 3 metric chunks exist), then resumed:
+    # nothing already listed is rewritten, the aggregates equal the uninterrupted run's
+    part = tmp_path / "resumed"
+    run(frt, my_strats, part, n=11, resume=False)
+    stamp = {p: p.stat().st_mtime_ns for p in (part / "rows").glob("*.parquet")}
+    assert len(stamp) == 11
+    run(frt, my_strats, part, resume=True)
+    assert all(p.stat().st_mtime_ns == t for p, t in stamp.items())
+    got, want = payload(part), payload(my_out)
+    assert got["outcome"] == want["outcome"] and dict(got["wins"]) == dict(want["wins"])
+    assert {m: dict(v) for m, v in got["sums"].items()} == {m: dict(v) for m, v in want["sums"].items()}
+    assert dict(got["meta"])["completed_shuffle_indices"] == list(range(shuffles))
+    assert len(manifest(part / "rows" / "manifest.jsonl")) == shuffles
+    # a checkpoint every group when the cadence is zero seconds
+    cfg = frt.TournamentConfig(n_players=k, num_shuffles=shuffles, deterministic_batch_size=batch, ckpt_every_sec=0)
+    seen = []
+    real = frt._save_checkpoint
+    monkeypatch.setattr(frt, "_save_checkpoint", lambda path, *a: (seen.append(len(a[3]["completed_shuffle_indices"])),
+                                                                   real(path, *a))[1])
+    frt.run_tournament(config=cfg, global_seed=root, checkpoint_path=tmp_path / "cad" / "c.pkl", collect_metrics=True,
+                       metric_chunk_directory=tmp_path / "cad" / "chunks", num_shuffles=shuffles,
+                       strategies=my_strats, resume=False)
+    assert seen == [5, 10, 15, 20, 23, 23]
