@@ -47,6 +47,7 @@ class LagRequest(C.Structure):
         ("matchup_count_dev", C.c_void_p), ("matchup_stats_dev", C.c_void_p),
         ("scratch_dev", C.c_void_p), ("scratch_bytes", C.c_size_t),
         ("n_matchups_host", C.c_void_p), ("first_seen_dev", C.c_void_p),
+        ("all_player_dev", C.c_void_p),
     ]
 
 

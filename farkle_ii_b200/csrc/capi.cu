@@ -1052,6 +1052,8 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
     LagParams L{};
     if (lag) {
         if (!tallies_dev) return fail(FB_ERR_BAD_ARG, "lag statistics / first-seen ordinals need tallies_dev");
+        if (lag->all_player_dev && shuffles_per_slot <= 0)
+            return fail(FB_ERR_BAD_ARG, "all-player statistics are per deterministic batch: shuffles_per_slot > 0");
         const bool wants_lags = lag->strategy_stats_dev || lag->strategy_edges_dev || lag->matchup_min_observations != 0;
         if (lag->n_lags < 0 || lag->n_lags > FB_MAX_LAGS || (lag->n_lags > 0 && !lag->lags) ||
             (lag->n_lags == 0 && wants_lags))
@@ -1183,6 +1185,24 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
     tally_gather_kernel<<<dim3(blocks_for((uint64_t)n_strategies, 128), (unsigned)n_chunks), 128, 0, stream>>>(G);
     rc = launch_check("tally_gather_kernel");
     if (rc || !lag) return rc;
+    if (lag->all_player_dev) {
+        AllPlayerParams A{};
+        A.seats = w.seats;
+        A.header = w.header;
+        A.inv = inv;
+        A.strategy_ids = strategy_ids_dev;
+        A.n_strategies = n_strategies;
+        A.n_tally_ids = n_tally_ids;
+        A.n_shuffles = n_shuffles;
+        A.k = k;
+        A.gps = gps;
+        A.per_slot = shuffles_per_slot;
+        A.out = reinterpret_cast<long long*>(lag->all_player_dev);
+        const int a_slots = (n_shuffles + shuffles_per_slot - 1) / shuffles_per_slot;
+        allplayer_gather_kernel<<<dim3(blocks_for((uint64_t)n_strategies, 128), (unsigned)a_slots), 128, 0, stream>>>(A);
+        rc = launch_check("allplayer_gather_kernel");
+        if (rc) return rc;
+    }
     if (lag->strategy_stats_dev) {
         L.header = w.header;
         L.inv = inv;

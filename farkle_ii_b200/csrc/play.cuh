@@ -36,6 +36,7 @@
 //               the per-strategy tallies: exposures and winner metrics by gather over the
 //               inverse permutation (few atomics).
 #pragma once
+#include <climits>
 #include <cstdint>
 
 #include "rng.cuh"
@@ -731,6 +732,113 @@ __global__ void __launch_bounds__(128) tally_gather_kernel(const GatherParams G)
             atomicAdd(&T[4 + FB_N_METRICS + m], sq[m]);
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// Unconditional all-player statistics (analysis/all_player_metrics.py:262-340)
+// ---------------------------------------------------------------------------
+// One thread per (strategy, deterministic batch): the strategy's exposures of the batch are its
+// games of the batch's shuffles, in shuffle order -- the order in which the reference's unbuffered
+// np.add.at meets them in the curated rows -- so the float64 sums of score / n_turns and
+// score / n_rounds are reproduced bit for bit by adding in that order with round-to-nearest
+// operations; everything else is integer.  Plain stores: a (slot, id) cell has one writer.
+struct AllPlayerParams {
+    const Seat* seats;
+    const uint32_t* header;  // rounds | flags << 16 | (winner seat + 1) << 24
+    const int32_t* inv;
+    const int32_t* strategy_ids;
+    int n_strategies, n_tally_ids, n_shuffles, k;
+    uint32_t gps;
+    int per_slot;  // shuffles per slot (> 0)
+    long long* out;  // [slots][n_tally_ids][FB_ALLP_WIDTH]
+};
+
+__global__ void __launch_bounds__(128) allplayer_gather_kernel(const AllPlayerParams A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_strategies) return;
+    const int c = blockIdx.y;
+    const int j0 = c * A.per_slot, j1 = min(j0 + A.per_slot, A.n_shuffles);
+    long long core[11];
+    long long beh[FB_ALLP_BEHAVIOURS][3];
+#pragma unroll
+    for (int f = 0; f < 11; f++) core[f] = 0;
+#pragma unroll
+    for (int b = 0; b < FB_ALLP_BEHAVIOURS; b++) beh[b][0] = beh[b][1] = beh[b][2] = 0;
+    double exact = 0.0, exact2 = 0.0, proxy = 0.0, proxy2 = 0.0;
+    for (int j = j0; j < j1; j++) {
+        const uint32_t pos = (uint32_t)A.inv[(size_t)j * A.n_strategies + i];
+        const uint32_t gi = pos / (uint32_t)A.k, seat = pos - gi * (uint32_t)A.k;
+        const uint32_t game = (uint32_t)j * A.gps + gi;
+        const uint32_t hdr = __ldg(&A.header[game]);
+        const bool safety = (hdr >> 16) & FB_ROW_SAFETY_LIMIT;
+        const long long rounds = hdr & 0xffffu;
+        const Seat* table = A.seats + (size_t)game * A.k;
+        const uint4 a = __ldg(&table[seat].a), b = __ldg(&table[seat].b);
+        const long long score = (int)a.y, turns = b.x & 0xffffu;
+        const bool won = !safety && ((hdr >> 24) & 15u) == seat + 1u;
+        core[0] += 1;
+        core[safety ? 2 : 1] += 1;
+        core[3] += won ? 1 : 0;
+        const long long tmr = turns - rounds;
+        core[4] += tmr != 0 ? 1 : 0;
+        core[5] += score;
+        core[6] += score * score;
+        core[7] += turns;
+        core[8] += turns * turns;
+        core[9] += tmr;
+        core[10] += tmr * tmr;
+        const double sd = (double)score;
+        const double e = turns ? __ddiv_rn(sd, (double)turns) : 0.0;
+        const double p = rounds ? __ddiv_rn(sd, (double)rounds) : 0.0;
+        exact = __dadd_rn(exact, e);
+        exact2 = __dadd_rn(exact2, __dmul_rn(e, e));
+        proxy = __dadd_rn(proxy, p);
+        proxy2 = __dadd_rn(proxy2, __dmul_rn(p, p));
+        long long v[FB_ALLP_BEHAVIOURS];
+        bool seen_rank = false;
+        v[0] = v[1] = 0;
+        if (!safety) {  // rank = place in the stable sort by (-score, seat); margin to the winner
+            int ahead = 0;
+            int best = INT_MIN;
+            for (int s = 0; s < A.k; s++) {
+                const int sc = (int)__ldg(&table[s].a).y;
+                best = max(best, sc);
+                ahead += (sc > (int)score || (sc == (int)score && (uint32_t)s < seat)) ? 1 : 0;
+            }
+            v[0] = ahead + 1;
+            v[1] = (long long)best - score;
+            seen_rank = true;
+        }
+        v[2] = a.w >> 16;           // rolls
+        v[3] = a.w & 0xffffu;       // farkles
+        v[4] = a.z & HIGH_MASK;     // highest_turn
+        v[5] = b.x >> 16;           // hot_dice
+        v[6] = b.y & 0xffffu;       // smart_five_uses
+        v[7] = b.y >> 16;           // n_smart_five_dice
+        v[8] = b.z & 0xffffu;       // smart_one_uses
+        v[9] = b.z >> 16;           // n_smart_one_dice
+#pragma unroll
+        for (int q = 0; q < FB_ALLP_BEHAVIOURS; q++) {
+            const bool present = q >= 2 || seen_rank;
+            beh[q][0] += present ? 1 : 0;
+            beh[q][1] += present ? v[q] : 0;
+            beh[q][2] += present ? v[q] * v[q] : 0;
+        }
+    }
+    const int sid = A.strategy_ids ? A.strategy_ids[i] : i;
+    long long* O = A.out + ((size_t)c * A.n_tally_ids + sid) * FB_ALLP_WIDTH;
+#pragma unroll
+    for (int f = 0; f < 11; f++) O[f] = core[f];
+#pragma unroll
+    for (int q = 0; q < FB_ALLP_BEHAVIOURS; q++) {
+        O[11 + 3 * q] = beh[q][0];
+        O[12 + 3 * q] = beh[q][1];
+        O[13 + 3 * q] = beh[q][2];
+    }
+    O[41] = __double_as_longlong(exact);
+    O[42] = __double_as_longlong(exact2);
+    O[43] = __double_as_longlong(proxy);
+    O[44] = __double_as_longlong(proxy2);
 }
 
 // ---------------------------------------------------------------------------

@@ -16,6 +16,7 @@ import torch
 
 from . import _native
 from .layout import (
+    ALLP_WIDTH,
     LAG_WIDTH,
     MATCHUP_LAG_WIDTH,
     MAX_ROUNDS,
@@ -76,6 +77,7 @@ class TournamentResult:
     matchup_count: torch.Tensor | None = None         # int32 [groups] games
     matchup_stats: torch.Tensor | None = None         # int64 [groups, n_lags, MATCHUP_LAG_WIDTH]
     first_seen: torch.Tensor | None = None    # int32 [ids, 4] first ordinal of win / seat / completed / safety
+    all_player: torch.Tensor | None = None    # int64 [slots, ids, ALLP_WIDTH] (41..44: float64 bit patterns)
 
     def rows_numpy(self) -> np.ndarray:
         assert self.rows is not None
@@ -252,7 +254,8 @@ class Engine:
                         totals: torch.Tensor | None = None, want_seat_tallies: bool = False,
                         seat_tallies: torch.Tensor | None = None,
                         lags: tuple[int, ...] = (), matchup_min_observations: int = 0,
-                        strategy_lags: bool = True, want_first_seen: bool = False) -> TournamentResult:
+                        strategy_lags: bool = True, want_first_seen: bool = False,
+                        want_all_player: bool = False) -> TournamentResult:
         """Enqueue shuffles ``shuffle0 .. shuffle0+n_shuffles-1`` of cell (root_seed, k).
 
         ``lags`` asks for the RNG lag statistics of the strategy groups (``lag_stats``
@@ -308,8 +311,16 @@ class Engine:
         ws = self.workspace(ws_bytes)
         lag_stats = lag_edges = m_part = m_count = m_stats = first_seen = None
         request = None
-        if lags or want_first_seen:
+        all_player = None
+        if lags or want_first_seen or want_all_player:
             request = _native.LagRequest()
+        if want_all_player:
+            # unconditional all-player statistics per (deterministic batch, strategy):
+            # analysis/all_player_metrics.py; see ``run_tournament.all_player_table``
+            if shuffles_per_slot <= 0:
+                raise _native.NativeError("want_all_player needs shuffles_per_slot > 0 (slot = deterministic batch)")
+            all_player = torch.zeros((n_slots, n_tally_ids, ALLP_WIDTH), dtype=torch.int64, device=self.device)
+            request.all_player_dev = all_player.data_ptr()
         if want_first_seen:
             first_seen = torch.empty((n_tally_ids, 4), dtype=torch.int32, device=self.device)
             request.first_seen_dev = first_seen.data_ptr()
@@ -347,7 +358,7 @@ class Engine:
             found = int(n_found.value)
             m_part, m_count, m_stats = m_part[:found], m_count[:found], m_stats[:found]
         return TournamentResult(tallies if want_tallies else None, totals, rows, n_games, k, seat_tallies,
-                                lag_stats, lag_edges, m_part, m_count, m_stats, first_seen)
+                                lag_stats, lag_edges, m_part, m_count, m_stats, first_seen, all_player)
 
     def play_cells(self, cells, strategies: torch.Tensor | np.ndarray, *, ahead=None,
                    strategy_ids=None, n_tally_ids: int | None = None, target_score: int = 10_000,

@@ -7,6 +7,7 @@ import numpy as np
 TALLY_WIDTH = 26
 LAG_WIDTH = 11  # pairs, win {sx, sy, sx2, sy2, sxy}, n_rounds {sx, sy, sx2, sy2, sxy}
 MATCHUP_LAG_WIDTH = 6  # pairs, n_rounds {sx, sy, sx2, sy2, sxy}
+ALLP_WIDTH = 45  # FB_ALLP_WIDTH: all-player statistics per (batch, strategy)
 SEAT_TALLY_WIDTH = 4  # raw_wins, raw_exposures, raw_completed_exposures, raw_safety_limit_exposures
 N_METRICS = 11
 MAX_PLAYERS = 12

@@ -1139,3 +1139,90 @@ def seat_counts_table(seat_tallies: np.ndarray, ids: Sequence[int], *, root_seed
         pa.array((slot_i + first_batch_id).astype(np.int32)), pa.array(sid[id_i].astype(np.int32)),
         pa.array((seat_i + 1).astype(np.int16)), pa.array(cells[:, 0]), pa.array(cells[:, 1]),
         pa.array(cells[:, 2]), pa.array(cells[:, 3])], schema=schema)
+
+
+# --------------------------------------------------------------------------- all-player statistics
+ALL_PLAYER_BEHAVIOURS = ("rank", "loss_margin", "rolls", "farkles", "highest_turn", "hot_dice",
+                         "smart_five_uses", "n_smart_five_dice", "smart_one_uses", "n_smart_one_dice")
+_ALLP_COUNTS = ("raw_player_game_exposures", "raw_completed_player_game_exposures",
+                "raw_safety_limit_player_game_exposures", "raw_wins", "raw_losses",
+                "raw_turn_round_mismatch_count", "raw_max_round_abort_exposures")
+_ALLP_SUMS = ("raw_final_score_sum", "raw_final_score_square_sum", "raw_n_turns_sum", "raw_n_turns_square_sum",
+              "raw_turn_return_game_weighted_exact_sum", "raw_turn_return_game_weighted_exact_square_sum",
+              "raw_turn_return_round_proxy_sum", "raw_turn_return_round_proxy_square_sum",
+              "raw_turn_minus_rounds_sum", "raw_turn_minus_rounds_square_sum")
+_ALLP_DERIVED = ("turn_return_turn_weighted", "turn_return_game_weighted_exact", "turn_return_round_proxy",
+                 "round_proxy_gap", "round_proxy_relative_gap", "turn_round_mismatch_prevalence",
+                 "win_rate_per_attempt", "win_rate_given_completion", "safety_limit_exposure_rate")
+
+
+def all_player_schema():
+    """The reference's ``all_player_batch_schema()`` (analysis/all_player_metrics.py:101-121)."""
+    import pyarrow as pa
+
+    behaviour = []
+    for suffix in ALL_PLAYER_BEHAVIOURS:
+        behaviour += [pa.field(f"raw_{suffix}_observations", pa.int64(), nullable=False),
+                      pa.field(f"raw_{suffix}_sum", pa.float64(), nullable=False),
+                      pa.field(f"raw_{suffix}_square_sum", pa.float64(), nullable=False)]
+    return pa.schema([
+        pa.field("root_seed", pa.int64(), nullable=False), pa.field("k", pa.int16(), nullable=False),
+        pa.field("deterministic_batch_id", pa.int32(), nullable=False),
+        pa.field("strategy", pa.int32(), nullable=False),
+        *(pa.field(name, pa.int64(), nullable=False) for name in _ALLP_COUNTS),
+        *(pa.field(name, pa.float64(), nullable=False) for name in _ALLP_SUMS),
+        *behaviour, *(pa.field(name, pa.float64()) for name in _ALLP_DERIVED)])
+
+
+def all_player_table(all_player: np.ndarray, ids: Sequence[int], *, root_seed: int, k: int,
+                     first_batch_id: int = 0):
+    """Device all-player statistics ``int64 [slots, ids, ALLP_WIDTH]`` (``Engine.play_tournament(
+    want_all_player=True, shuffles_per_slot=batch)``) -> the Arrow table the reference's metrics
+    stage builds by re-reading every curated row (analysis/all_player_metrics.py:425-520): one row
+    per (batch, strategy) in (batch, strategy) order, the raw sufficient statistics and the derived
+    ratios computed exactly as ``_finish_row`` (:384-423) computes them."""
+    import pyarrow as pa
+
+    t = np.ascontiguousarray(all_player, dtype=np.int64)
+    order = np.argsort(np.asarray(ids), kind="stable")
+    sid = np.asarray(ids)[order]
+    rows = []
+    for slot in range(t.shape[0]):
+        for pos, strategy in zip(order.tolist(), sid.tolist()):
+            v = t[slot, pos]
+            exposures, completed, safety, wins = (int(x) for x in v[:4])
+            if exposures == 0:
+                continue
+            f = v[41:45].view(np.float64)
+            exact_sum, exact_sq, proxy_sum, proxy_sq = (float(x) for x in f)
+            turns = float(v[7])
+            game_exact = exact_sum / exposures
+            round_proxy = proxy_sum / exposures
+            gap = round_proxy - game_exact
+            row: Dict[str, Any] = {
+                "root_seed": root_seed, "k": k, "deterministic_batch_id": first_batch_id + slot,
+                "strategy": int(strategy),
+                "raw_player_game_exposures": exposures, "raw_completed_player_game_exposures": completed,
+                "raw_safety_limit_player_game_exposures": safety, "raw_wins": wins,
+                "raw_losses": exposures - wins, "raw_turn_round_mismatch_count": int(v[4]),
+                "raw_max_round_abort_exposures": safety,
+                "raw_final_score_sum": float(v[5]), "raw_final_score_square_sum": float(v[6]),
+                "raw_n_turns_sum": turns, "raw_n_turns_square_sum": float(v[8]),
+                "raw_turn_return_game_weighted_exact_sum": exact_sum,
+                "raw_turn_return_game_weighted_exact_square_sum": exact_sq,
+                "raw_turn_return_round_proxy_sum": proxy_sum,
+                "raw_turn_return_round_proxy_square_sum": proxy_sq,
+                "raw_turn_minus_rounds_sum": float(v[9]), "raw_turn_minus_rounds_square_sum": float(v[10]),
+                "turn_return_turn_weighted": float(v[5]) / turns if turns else None,
+                "turn_return_game_weighted_exact": game_exact, "turn_return_round_proxy": round_proxy,
+                "round_proxy_gap": gap, "round_proxy_relative_gap": gap / game_exact if game_exact else None,
+                "turn_round_mismatch_prevalence": float(v[4]) / exposures,
+                "win_rate_per_attempt": wins / exposures,
+                "win_rate_given_completion": wins / completed if completed else None,
+                "safety_limit_exposure_rate": safety / exposures}
+            for b, suffix in enumerate(ALL_PLAYER_BEHAVIOURS):
+                row[f"raw_{suffix}_observations"] = int(v[11 + 3 * b])
+                row[f"raw_{suffix}_sum"] = float(v[12 + 3 * b])
+                row[f"raw_{suffix}_square_sum"] = float(v[13 + 3 * b])
+            rows.append(row)
+    return pa.Table.from_pylist(rows, schema=all_player_schema())

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FB_ABI_VERSION 3
+#define FB_ABI_VERSION 4
 
 /* ---- status codes ------------------------------------------------------- */
 enum fb_status {
@@ -174,7 +174,23 @@ typedef struct fb_lag_request {
      * Counter / dict keys (run_tournament.py:177-195,375-391), which a byte-identical checkpoint
      * pickle needs.                                                                           */
     uint32_t* first_seen_dev;
+    /* Unconditional all-player sufficient statistics per (deterministic batch, strategy)
+     * (src/farkle/analysis/all_player_metrics.py:31-98,262-340: what the reference's metrics stage
+     * re-derives by re-reading every curated row).  int64 [slots][n_tally_ids][FB_ALLP_WIDTH],
+     * OVERWRITTEN for the slots of this launch; needs shuffles_per_slot > 0 (slot = batch).
+     * Columns: 0 exposures  1 completed  2 safety-limit  3 wins  4 turn/round mismatches
+     *   5,6 sum / square sum of final score   7,8 of n_turns   9,10 of (n_turns - n_rounds)
+     *   11 + 3b .. 13 + 3b  observations, sum, square sum of behaviour b in the reference's order
+     *   (rank, loss_margin, rolls, farkles, highest_turn, hot_dice, smart_five_uses,
+     *   n_smart_five_dice, smart_one_uses, n_smart_one_dice; rank and loss_margin are observed in
+     *   completed games only)
+     *   41..44  IEEE-754 double BIT PATTERNS: sum and square sum of score / n_turns, then of
+     *   score / n_rounds, added in shuffle order with round-to-nearest divisions, products and
+     *   additions, i.e. the exact value of the reference's float64 accumulator.              */
+    int64_t* all_player_dev;
 } fb_lag_request_t;
+#define FB_ALLP_WIDTH 45
+#define FB_ALLP_BEHAVIOURS 10
 
 /* Per-launch totals, int64[FB_TOTALS_WIDTH]:
  *   0 games_attempted  1 games_completed  2 games_safety_limit

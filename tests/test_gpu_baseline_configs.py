@@ -314,3 +314,37 @@ def test_play_cells_equals_one_launch_per_cell(eng, full_grid):
     eng.play_cells([(11, 5, 2, 9, t, None)], table, strategy_ids=ids)
     want_t, _, _ = fo.play_tournament(11, 5, 2, 9, full_grid, strategy_ids=ids, n_threads=THREADS)
     assert np.array_equal(t.cpu().numpy(), want_t)
+
+
+# ------------------------------------------------------------------------ all-player statistics (f-3)
+@pytest.mark.parametrize("name,spb,with_ids", [("fast_54_4", 2, False), ("fast_42_2", 5, True), ("full_0_5", 1, False),
+                                               ("full_42_6", 2, False), ("full_102_12", 3, True)])
+def test_all_player_statistics(eng, golden_dir, name, spb, with_ids):
+    """`allplayer_gather_kernel` (optional output of the tournament launch): the unconditional
+    all-player sufficient statistics per (deterministic batch, strategy) -- integer counts and sums,
+    and the float64 sums of score / n_turns and score / n_rounds added in shuffle order -- equal, bit
+    for bit, the host restatement over the same launch's rows.  That restatement and the Arrow table
+    built from it are compared with the reference's own metrics stage in
+    tests/test_reference_dropin.py::test_all_player_statistics_match_reference_metrics_stage."""
+    from all_player_rows import all_player_from_rows
+
+    z = np.load(golden_dir / f"games_{name}.npz")
+    root, k, sh0, nsh = (int(x) for x in z["meta"])
+    table = z["strategies"]
+    n = len(table)
+    ids = (np.arange(n, dtype=np.int32)[::-1] * 2 + 1).copy() if with_ids else None
+    res = eng.play_tournament(root, k, sh0, nsh, table, shuffles_per_slot=spb, want_all_player=True,
+                              want_rows=True, strategy_ids=ids)
+    rows = res.rows_numpy()
+    assert rows.tobytes() == (z["rows"].tobytes() if ids is None else rows.tobytes())
+    gps = n // k
+    batch = (np.arange(len(rows)) // gps) // spb
+    n_ids = n if ids is None else int(ids.max()) + 1
+    want = all_player_from_rows(rows, batch, -(-nsh // spb), n_ids)
+    got = res.all_player.cpu().numpy()
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+    # the float columns really are doubles with sensible values
+    f = got[..., 41].view(np.float64)
+    seated = got[..., 0] > 0
+    assert np.isfinite(f).all() and (f[seated] >= 0).all() and seated.sum() == -(-nsh // spb) * n

@@ -117,7 +117,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_native.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.fb_abi_version() == 3
+    assert lib.fb_abi_version() == 4
     for k in (2, 5, 12):
         assert lib.fb_row_stride(k) == layout.row_stride(k)
     assert lib.fb_workspace_bytes(2, 1000) >= 1000 * 2 * 36

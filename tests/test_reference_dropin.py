@@ -554,3 +554,42 @@ def test_standalone_driver_against_reference_driver(ref_rt, tmp_path, monkeypatc
                        metric_chunk_directory=tmp_path / "cad" / "chunks", num_shuffles=shuffles,
                        strategies=my_strats, resume=False)
     assert seen == [5, 10, 15, 20, 23, 23]
+
+
+def test_all_player_statistics_match_reference_metrics_stage(ref_env, tmp_path):
+    """The all-player sufficient statistics (f-3): `run_tournament.all_player_table` over the
+    host restatement of the device kernel equals, column for column and bit for bit (float sums
+    included), what the reference's metrics stage derives from a curated Parquet of the same games
+    (`analysis/all_player_metrics.py::_iter_batch_tables`)."""
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from farkle.analysis import all_player_metrics as ref_apm
+    from farkle.utils.parallel import ProcessTreeMemoryGuard
+
+    from all_player_rows import all_player_from_rows
+    from farkle_ii_b200 import run_tournament as frt
+    from farkle_ii_b200 import simulation as fsim
+
+    for name, per_batch in (("games_fast_54_4", 2), ("games_full_0_5", 1), ("games_fast_42_2", 3)):
+        z = np.load(Path(__file__).parent / "golden" / f"{name}.npz")
+        root, k, sh0, nsh = (int(x) for x in z["meta"])
+        rows = z["rows"]
+        n = len(z["strategies"])
+        gps = n // k
+        shuffle = sh0 + np.arange(len(rows)) // gps
+        batch = (shuffle - sh0) // per_batch
+        tbl = fsim.compact_rows_to_table(rows, root_seed=root, k=k, shuffle_index=shuffle,
+                                         game_index=np.arange(len(rows)) % gps,
+                                         deterministic_batch_id=batch, shuffle_seed=0)
+        src = tmp_path / f"{name}.parquet"
+        pq.write_table(tbl, src)
+        guard = ProcessTreeMemoryGuard(1 << 20, rss_warning_mb=1 << 20, minimum_system_available_memory_mb=1)
+        want = pa.concat_tables(list(ref_apm._iter_batch_tables(src, k, max_batch_bytes=1 << 30,
+                                                                max_batch_rows=1 << 20, memory_guard=guard)))
+        n_slots = int(batch.max()) + 1
+        n_ids = int(rows["seats"]["strategy"].max()) + 1
+        stats = all_player_from_rows(rows, batch, n_slots, n_ids)
+        got = frt.all_player_table(stats, np.arange(n_ids), root_seed=root, k=k)
+        assert got.schema == want.schema == ref_apm.all_player_batch_schema()
+        assert got.equals(want), name
