@@ -73,16 +73,35 @@ struct Ctx {
         size_t workspace_bytes = 0;
     } ahead;
 };
-Ctx g_ctx;
-std::mutex g_mu;
+// One context per CUDA device: a process may drive several GPUs (one engine each), and every entry
+// point works on the context of the device that is CURRENT for the calling thread, the way the CUDA
+// runtime itself resolves streams and allocations.  fb_init(device) makes `device` current and
+// fills its slot.  The mutex of a context serialises only the calls that share its cached buffers
+// (fb_run_tournament_host, fb_play_tournament_cells) on that device.
+constexpr int MAX_DEVICES = 64;
+Ctx g_ctxs[MAX_DEVICES];
+std::mutex g_mus[MAX_DEVICES];
+inline int current_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEVICES) d = 0;
+    return d;
+}
+#define g_ctx (g_ctxs[current_device()])
+#define g_mu (g_mus[current_device()])
 std::atomic<uint64_t> g_launches{0};
 
 thread_local std::string t_err;
-// CUDA-event pairs around the most recent play_kernel launches of this thread (a ring)
+// CUDA-event pairs around the most recent play_kernel launches of this thread on each device (rings)
 constexpr int EV_RING = 64;
-thread_local cudaEvent_t t_ev[EV_RING][2];
-thread_local bool t_ev_made = false;
-thread_local uint64_t t_ev_count = 0;  // launches recorded so far
+struct EvRing {
+    cudaEvent_t ev[EV_RING][2];
+    bool made = false;
+    uint64_t count = 0;  // launches recorded so far
+};
+thread_local EvRing t_rings[MAX_DEVICES];
+#define t_ev (t_rings[current_device()].ev)
+#define t_ev_made (t_rings[current_device()].made)
+#define t_ev_count (t_rings[current_device()].count)
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -809,14 +828,15 @@ const char* fb_last_error(void) { return t_err.c_str(); }
 uint64_t fb_kernel_launch_count(void) { return g_launches.load(); }
 
 int fb_init(int device) {
-    std::lock_guard<std::mutex> lock(g_mu);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
         return fail(FB_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
-    if (device < 0 || device >= count) return fail(FB_ERR_BAD_ARG, "device %d out of range [0,%d)", device, count);
+    if (device < 0 || device >= count || device >= MAX_DEVICES)
+        return fail(FB_ERR_BAD_ARG, "device %d out of range [0,%d)", device, std::min(count, MAX_DEVICES));
     FB_CUDA(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lock(g_mu);  // the lock and context of `device`, now current
     if (g_ctx.device == device && g_ctx.lut_dev) return FB_OK;
     cudaDeviceProp prop;
     FB_CUDA(cudaGetDeviceProperties(&prop, device));

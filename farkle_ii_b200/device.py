@@ -39,13 +39,30 @@ def get_engine(device: int | None = None) -> "Engine":
     if device is None:
         device = torch.cuda.current_device()
     eng = _engines.get(device)
-    if eng is None:
-        if _engines:  # the C library binds ONE device per process (one process per GPU)
-            raise _native.NativeError(
-                f"this process is already bound to cuda:{next(iter(_engines))}; "
-                "run one process per GPU (torchrun) instead of switching devices")
+    if eng is None:      # one engine (and one library context) per device; several may coexist
         eng = _engines[device] = Engine(device)
     return eng
+
+
+class _OnDevice:
+    """The C library resolves its per-device context from the CUDA device that is current for the
+    calling thread (include/farkle_b200.h, fb_init): every call of an engine goes through this
+    proxy, which makes the engine's device current for the duration of the call."""
+
+    def __init__(self, lib: C.CDLL, device: torch.device):
+        self._lib, self._device = lib, device
+
+    def __getattr__(self, name: str):
+        fn = getattr(self._lib, name)
+        device = self._device
+
+        def call(*args):
+            with torch.cuda.device(device):
+                return fn(*args)
+
+        call.__name__ = name
+        setattr(self, name, call)
+        return call
 
 
 def _check_rounds(values) -> None:
@@ -88,9 +105,9 @@ class Engine:
     """One CUDA device + the loaded C-ABI library."""
 
     def __init__(self, device: int):
-        self.lib = _native.lib()
         self.device_index = device
         self.device = torch.device("cuda", device)
+        self.lib = _OnDevice(_native.lib(), self.device)
         with torch.cuda.device(self.device):
             _native.check(self.lib.fb_init(device))
         sm, khz, major, minor = C.c_int(), C.c_int(), C.c_int(), C.c_int()

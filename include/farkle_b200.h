@@ -210,7 +210,13 @@ typedef struct fb_lag_request {
 int fb_abi_version(void);
 const char* fb_last_error(void);
 
-/* Select the device, upload the score lookup table.  Idempotent per device. */
+/* Make `device` current for the calling thread (cudaSetDevice) and build its context: score
+ * lookup table, jump-ahead constants, cached streams / buffers.  Idempotent per device.  A process
+ * may initialise several devices; every other entry point works on the context of the device
+ * that is CURRENT for the calling thread when it is called (as the CUDA runtime resolves streams
+ * and allocations), so a host that drives several GPUs from one process calls cudaSetDevice(d)
+ * (or fb_init(d)) before the calls meant for device d.  Pointers and the stream passed to a call
+ * must belong to that device.  Calls on different devices do not serialise each other.        */
 int fb_init(int device);
 /* sm_count / clock_khz may be NULL. */
 int fb_device_info(int* sm_count, int* clock_khz, int* cc_major, int* cc_minor);

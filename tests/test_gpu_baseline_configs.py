@@ -348,3 +348,30 @@ def test_all_player_statistics(eng, golden_dir, name, spb, with_ids):
     f = got[..., 41].view(np.float64)
     seated = got[..., 0] > 0
     assert np.isfinite(f).all() and (f[seated] >= 0).all() and seated.sum() == -(-nsh // spb) * n
+
+
+# ------------------------------------------------------------------------ several devices, one process
+def test_two_devices_in_one_process(full_grid):
+    """Per-device library contexts ("re-entrant per (device, stream)"): two
+    engines on two GPUs of one process, launches enqueued on both before either is waited for, give
+    the two-rank result.  Needs two visible GPUs (skipped on the one-GPU box)."""
+    import torch
+
+    from farkle_ii_b200.device import get_engine
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    e0, e1 = get_engine(0), get_engine(1)
+    assert e0 is not e1 and e0.device != e1.device
+    table = full_grid[:240]
+    a = e0.play_tournament(31, 4, 0, 40, table)
+    b = e1.play_tournament(31, 4, 40, 40, table)
+    c = e0.play_tournament(32, 2, 0, 10, table, want_rows=True)          # and back on the first device
+    want_t, want_tot, _ = fo.play_tournament(31, 4, 0, 80, table, n_threads=THREADS)
+    assert np.array_equal(a.tallies.cpu().numpy() + b.tallies.cpu().numpy(), want_t)
+    assert np.array_equal(a.totals.cpu().numpy() + b.totals.cpu().numpy(), want_tot)
+    _, _, want_rows = fo.play_tournament(32, 2, 0, 10, table, want_rows=True)
+    assert c.rows_numpy().tobytes() == want_rows.tobytes()
+    out = np.zeros((1, len(table), 26), dtype=np.int64)
+    e1.run_tournament_host(31, 4, 0, 80, table, out_tallies=out)        # the host-buffer call on device 1
+    assert np.array_equal(out, want_t)

@@ -195,4 +195,15 @@ def test_lag_request_struct_layout_matches_header(tmp_path):
     out = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert out[0] == ctypes.sizeof(_native.LagRequest)
     assert out[1:] == [getattr(_native.LagRequest, f).offset for f in fields]
-    assert ctypes.sizeof(_native.LagRequest) == 96
+    assert ctypes.sizeof(_native.LagRequest) == 104          # ABI 4: + all_player_dev
+    # fb_cell_t (fb_play_tournament_cells)
+    cell_fields = [name for name, _ in _native.Cell._fields_]
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "farkle_b200.h"\nint main(void) {\n'
+        '  printf("%zu\\n", sizeof(fb_cell_t));\n'
+        + "".join(f'  printf("%zu\\n", offsetof(fb_cell_t, {f}));\n' for f in cell_fields)
+        + "  return 0;\n}\n")
+    subprocess.run([gcc, "-std=c11", f"-I{include}", str(src), "-o", str(exe)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(_native.Cell) == 40
+    assert out[1:] == [getattr(_native.Cell, f).offset for f in cell_fields]
