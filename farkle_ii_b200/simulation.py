@@ -83,6 +83,119 @@ def check_row_flags(rows: np.ndarray) -> None:
                             "(utils/schema_helpers.py:44-58); the reference's Arrow conversion raises")
 
 
+def validate_compact_rows(rows: np.ndarray) -> None:
+    """The closed outcome invariants of ``validate_simulation_row`` (simulation.py:450-563) that a
+    compact row can violate, checked for a whole launch at once: distinct seated strategies, a
+    completed game's winner is its rank-1 seat (highest score, ties to the lower seat), a
+    safety-limit game claims no winner.  Every other field the reference validates (ranks, margins,
+    seat order, null patterns) is DERIVED from these columns by ``expand_rows`` /
+    ``compact_rows_to_table``, so it cannot disagree with them."""
+    n = len(rows)
+    if n == 0:
+        return
+    seats = rows["seats"]
+    k = seats.shape[1]
+    strategies = np.sort(seats["strategy"].astype(np.int64), axis=1)
+    if k > 1 and (strategies[:, 1:] == strategies[:, :-1]).any():
+        raise ValueError("Simulation row must seat distinct strategies")
+    safety = (rows["flags"] & ROW_SAFETY_LIMIT) != 0
+    scores = seats["score"].astype(np.int64)
+    best = np.argmax(scores, axis=1)                      # first maximum = lowest seat among ties
+    winner = rows["winner_seat"].astype(np.int64)
+    if (~safety & (winner != best)).any():
+        raise ValueError("Completed simulation row must have exactly one winner matching its rank-1 seat")
+    if (safety & (winner != 0xFF)).any():
+        raise ValueError("Safety-limit simulation row cannot claim a winner: ['winner_seat']")
+
+
+def validate_simulation_row(row: Mapping[str, Any]) -> None:
+    """Validate one flattened game row: the reference's closed outcome invariants, check for check
+    and message for message (simulation/simulation.py:450-563)."""
+    try:
+        n_players = int(row["k"])
+        status = str(getattr(row["termination_status"], "value", row["termination_status"]))
+        if status not in ("completed", "safety_limit"):
+            raise ValueError(status)
+    except (KeyError, TypeError, ValueError) as exc:
+        raise ValueError("Simulation row has invalid k or termination_status") from exc
+    if n_players < 1:
+        raise ValueError("Simulation row k must be positive")
+    if row.get("outcome_schema_version") != OUTCOME_SCHEMA_VERSION:
+        raise ValueError(f"Simulation row must use outcome_schema_version={OUTCOME_SCHEMA_VERSION}")
+    seats = [f"P{index}" for index in range(1, n_players + 1)]
+    strategies: list[int] = []
+    scores: list[int] = []
+    for seat in seats:
+        if row.get(f"{seat}_strategy") is None:
+            raise ValueError(f"Simulation row missing seated strategy {seat}_strategy")
+        sid = row[f"{seat}_strategy"]
+        if isinstance(sid, bool) or not isinstance(sid, (int, np.integer)):
+            raise ValueError(f"simulation row {seat}_strategy must be a canonical integer strategy id")
+        strategies.append(int(sid))
+        score = row.get(f"{seat}_score")
+        if isinstance(score, bool) or not isinstance(score, (int, np.integer)):
+            raise ValueError(f"Simulation row {seat}_score must be an integer")
+        scores.append(int(score))
+    if len(set(strategies)) != n_players:
+        raise ValueError("Simulation row must seat distinct strategies")
+    missing_ranks = [seat for seat in seats if f"{seat}_rank" not in row]
+    if missing_ranks:
+        raise ValueError(f"Simulation row missing participant ranks for {missing_ranks}")
+    ranks = [row[f"{seat}_rank"] for seat in seats]
+    winner_seat, winner_strategy = row.get("winner_seat"), row.get("winner_strategy")
+    if status == "completed":
+        rank_one = [seat for seat, rank in zip(seats, ranks, strict=True) if rank == 1]
+        if not isinstance(winner_seat, str) or len(rank_one) != 1 or winner_seat != rank_one[0]:
+            raise ValueError("Completed simulation row must have exactly one winner matching its rank-1 seat")
+        if any(rank is None for rank in ranks) or sorted(ranks) != list(range(1, n_players + 1)):
+            raise ValueError("Completed simulation row ranks must be the permutation 1..k")
+        score_order = sorted(range(n_players), key=lambda index: (-scores[index], index))
+        expected = [0] * n_players
+        for rank, index in enumerate(score_order, start=1):
+            expected[index] = rank
+        if [int(rank) for rank in ranks] != expected:
+            raise ValueError("Completed simulation row ranks are inconsistent with final scores")
+        if winner_strategy is None or winner_strategy != row.get(f"{winner_seat}_strategy"):
+            raise ValueError("Completed simulation row must identify the winning strategy")
+        winning_score, victory_margin = row.get("winning_score"), row.get("victory_margin")
+        if winning_score is None or victory_margin is None:
+            raise ValueError("Completed simulation row must retain winner-conditioned fields")
+        if row.get("hit_safety_limit") is not False:
+            raise ValueError("Completed simulation row cannot hit the safety limit")
+        if any(row.get(f"{seat}_hit_max_rounds") is not False for seat in seats):
+            raise ValueError("Completed simulation row cannot mark a seat at the safety limit")
+        if int(winning_score) != scores[seats.index(winner_seat)] or int(winning_score) != max(scores):
+            raise ValueError("Completed simulation row has inconsistent winning_score")
+        ordered = sorted(scores, reverse=True)
+        if int(victory_margin) != int(winning_score) - (ordered[1] if n_players > 1 else 0):
+            raise ValueError("Completed simulation row has inconsistent victory_margin")
+        for seat, score in zip(seats, scores, strict=True):
+            margin = row.get(f"{seat}_loss_margin")
+            if (isinstance(margin, bool) or not isinstance(margin, (int, np.integer))
+                    or int(margin) != int(winning_score) - score):
+                raise ValueError(f"Completed simulation row has inconsistent {seat}_loss_margin")
+        seat_ranks = row.get("seat_ranks")
+        if seat_ranks is None or list(seat_ranks) != [seats[index] for index in score_order]:
+            raise ValueError("Completed simulation row has inconsistent seat_ranks")
+        return
+    if row.get("hit_safety_limit") is not True:
+        raise ValueError("Safety-limit simulation row must set hit_safety_limit=true")
+    if any(row.get(f"{seat}_hit_max_rounds") is not True for seat in seats):
+        raise ValueError("Safety-limit simulation row must mark every seat at the safety limit")
+    present = [name for name, value in (("winner_seat", winner_seat), ("winner_strategy", winner_strategy),
+                                        ("winning_score", row.get("winning_score")),
+                                        ("victory_margin", row.get("victory_margin"))) if value is not None]
+    if present:
+        raise ValueError(f"Safety-limit simulation row cannot claim a winner: {present}")
+    if any(rank is not None for rank in ranks):
+        raise ValueError("Safety-limit simulation row cannot assign participant ranks")
+    seat_ranks = row.get("seat_ranks")
+    if seat_ranks is None or list(seat_ranks) != [None] * n_players:
+        raise ValueError("Safety-limit simulation row must retain k null seat-rank entries")
+    if any(row.get(f"{seat}_loss_margin") is not None for seat in seats):
+        raise ValueError("Safety-limit simulation row cannot assign loss margins")
+
+
 def derive_ranks(rows: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
     """``(rank[n, k] (1-based, 0 = null), order[n, k])`` — stable sort by score desc, seat asc
     (game/engine.py:483), nulls for safety-limit rows."""
@@ -166,6 +279,7 @@ def expand_rows(rows: np.ndarray, provenance: Sequence[Mapping[str, Any]] | None
             flat[p + "n_smart_one_dice"] = int(seat["n_smart_one_dice"])
             flat[p + "hot_dice"] = int(seat["hot_dice"])
             flat[p + "hit_max_rounds"] = safety
+        validate_simulation_row(flat)          # as `_play_game` does before returning a row (:655)
         out.append(flat)
     return out
 
@@ -233,6 +347,7 @@ def compact_rows_to_table(rows: np.ndarray, *, root_seed: int, k: int, shuffle_i
     import pyarrow as pa
 
     check_row_flags(rows)
+    validate_compact_rows(rows)
     n = len(rows)
     schema = raw_simulation_schema_for(k)
     safety = (rows["flags"] & ROW_SAFETY_LIMIT) != 0

