@@ -258,6 +258,54 @@ def workload_config(n_gpus: int) -> dict:
     }
 
 
+def strong_scaling_leg(play_cells, table, rank: int, world: int, reps: int, timer,
+                       cells=None, n_strategies: int = N_STRATEGIES, batch: int = SHUFFLES_PER_BATCH) -> dict:
+    """Strong scaling of a FIXED workload: one mega-config root (configs/farkle_mega_config.yaml: full
+    grid, k in {2,3,4,5,6,8,10,12}, 4,300 shuffles each = 39,013,900 games).  The cells are dealt to the
+    ranks along one line by estimated cost (run_tournament.plan_cells), every rank plays its segments
+    through the pipelined cell list, ONE all-reduce merges the stacked tallies.  Rank 0 also plays
+    the whole root alone -- no collective, the other ranks wait at a barrier -- so that both times
+    come from this run, and the two tally sets are compared.  `timer(fn, reps) -> (ms, result)` times
+    on the device (CUDA events); tests pass a wall-clock one and CPU stand-ins for the launches."""
+    import torch
+    import torch.distributed as dist
+
+    from farkle_ii_b200 import run_tournament as frt
+
+    mega = cells if cells is not None else [(MEGA_ROOT, k, SHUFFLES) for k in MEGA_K]
+    multi = world > 1
+
+    def run(**kw):
+        return frt.run_cells(mega, table, batch_size=batch, play_cells=play_cells, **kw)
+
+    n_ms, (t_all, tot_all) = timer(lambda: run(rank=rank, world=world), reps)
+    if multi:
+        t = torch.tensor([n_ms], dtype=torch.float64, device=t_all.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n_ms = float(t.item())
+        dist.barrier()
+    one_ms, same = n_ms, True
+    if multi and rank == 0:
+        alone = frt.plan_cells(mega, n_strategies, 1, batch_size=batch)
+        one_ms, (t_one, tot_one) = timer(lambda: run(rank=0, world=1, plan=alone), max(1, reps - 1))
+        same = bool(torch.equal(t_one, t_all) and torch.equal(tot_one, tot_all))
+    if multi:
+        dist.barrier()
+    games = sum(s * (n_strategies // k) for _, k, s in mega)
+    out = {"workload": f"mega-config root {mega[0][0]}: full grid, k in {[k for _, k, _ in mega]}, "
+                       f"{mega[0][2]} shuffles each ({games} games), fixed total work",
+           "n_gpus": world, "n1_ms": one_ms, "nN_ms": n_ms, "speedup": one_ms / n_ms,
+           "efficiency": one_ms / n_ms / world, "games_per_s": games / (n_ms * 1e-3),
+           "identical_tallies_n1_vs_nN": same, "games_attempted": int(tot_all[:, 0].sum().item()),
+           "reps": reps,
+           "plan": [[(sg.k, sg.shuffle0, sg.n_shuffles) for sg in segs]
+                    for segs in frt.plan_cells(mega, n_strategies, world, batch_size=batch)],
+           "timing": "CUDA events on every rank around all launches + the all-reduce, max over ranks; "
+                     "n1_ms: rank 0 plays the whole root alone in the same run"}
+    assert out["games_attempted"] == games
+    return out
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def main() -> None:
     ap = argparse.ArgumentParser()
@@ -297,7 +345,11 @@ def main() -> None:
         raise SystemExit("bench.py needs a CUDA device: farkle_ii_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from datetime import timedelta
+
+        # a collective that does not complete in 90 s is a bug, not a slow run (NCCL's default of
+        # ten minutes would burn the box)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=timedelta(seconds=90))
     eng = get_engine(local)
     table_host = full_grid_table()
     table_dev = eng.to_device(table_host)
@@ -426,57 +478,25 @@ def main() -> None:
     h2d = len(CELLS_K) * table_host.nbytes
     d2h = len(CELLS_K) * (N_STRATEGIES * TALLY_WIDTH * 8 + TOTALS_WIDTH * 8)
 
-    # ---- strong scaling of a FIXED workload: one mega-config root (configs/farkle_mega_config.yaml:
-    # full grid, k in {2,3,4,5,6,8,10,12}, 4,300 shuffles each = 39,013,900 games).  The cells are dealt
-    # to the ranks along one line by estimated cost (run_tournament.plan_cells), every rank plays its
-    # segments through the pipelined cell list, ONE all-reduce merges the stacked tallies.  Rank 0
-    # also plays the whole root alone (the other GPUs idle) so that both times come from this run.
+    # ---- strong scaling of a FIXED workload (see strong_scaling_leg)
     from farkle_ii_b200 import run_tournament as frt
 
     strong = None
     if args.strong_reps > 0:
-        mega = [(MEGA_ROOT, k, SHUFFLES) for k in MEGA_K]
-
-        def play(segments, table):
-            eng.play_cells(segments, table)
-
-        def timed(reps, **kw):
-            out = frt.run_cells(mega, table_dev, batch_size=SHUFFLES_PER_BATCH, play_cells=play, **kw)  # warm-up
+        def cuda_timer(fn, reps):
+            out = fn()                                   # warm-up
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             for _ in range(reps):
-                out = frt.run_cells(mega, table_dev, batch_size=SHUFFLES_PER_BATCH, play_cells=play, **kw)
+                out = fn()
             b.record()
             torch.cuda.synchronize()
             return a.elapsed_time(b) / reps, out
 
         sync_all()
-        n_ms, (t_all, tot_all) = timed(args.strong_reps, rank=rank, world=world)
-        if world > 1:
-            t = torch.tensor([n_ms], dtype=torch.float64, device=eng.device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            n_ms = float(t.item())
-            dist.barrier()
-        one_ms, same = n_ms, True
-        if world > 1 and rank == 0:
-            one_ms, (t_one, tot_one) = timed(max(1, args.strong_reps - 1), rank=0, world=1,
-                                             plan=frt.plan_cells(mega, N_STRATEGIES, 1, batch_size=SHUFFLES_PER_BATCH))
-            same = bool(torch.equal(t_one, t_all) and torch.equal(tot_one, tot_all))
-        if world > 1:
-            dist.barrier()
-        mega_games = sum(SHUFFLES * (N_STRATEGIES // k) for k in MEGA_K)
-        strong = {"workload": f"mega-config root {MEGA_ROOT}: full grid, k in {list(MEGA_K)}, {SHUFFLES} shuffles each "
-                              f"({mega_games} games), fixed total work",
-                  "n_gpus": world, "n1_ms": one_ms, "nN_ms": n_ms, "speedup": one_ms / n_ms,
-                  "efficiency": one_ms / n_ms / world, "games_per_s": mega_games / (n_ms * 1e-3),
-                  "identical_tallies_n1_vs_nN": same, "games_attempted": int(tot_all[:, 0].sum().item()),
-                  "reps": args.strong_reps,
-                  "plan": [[(sg.k, sg.shuffle0, sg.n_shuffles) for sg in segs]
-                           for segs in frt.plan_cells(mega, N_STRATEGIES, world, batch_size=SHUFFLES_PER_BATCH)],
-                  "timing": "CUDA events on every rank around all launches + the all-reduce, max over ranks; "
-                            "n1_ms: rank 0 plays the whole root alone in the same run"}
-        assert strong["games_attempted"] == mega_games
+        strong = strong_scaling_leg(lambda segments, table: eng.play_cells(segments, table), table_dev,
+                                    rank, world, args.strong_reps, cuda_timer)
 
     # ---- rows mode all the way to disk (rank 0, N = 1 only): the Python surface's run_tournament()
     # with a row directory -- games -> compact rows -> D2H -> Arrow -> one Parquet shard + manifest

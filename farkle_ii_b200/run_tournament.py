@@ -740,7 +740,9 @@ def run_cells(cells: Sequence[Tuple[int, int, int]], table, *, batch_size: int, 
     if mine:
         play_cells([(sg.root_seed, sg.k, sg.shuffle0, sg.n_shuffles, tallies[sg.cell], totals[sg.cell])
                     for sg in mine], table)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    # `world` (not the size of the default process group) decides: a caller that plays a plan alone
+    # (world == 1) inside a multi-rank job must not enter a collective the other ranks do not join
+    if world > 1 and dist.is_available() and dist.is_initialized():
         dist.all_reduce(flat)
     return tallies, totals
 

@@ -215,3 +215,53 @@ def test_plan_cells_properties():
     assert sorted((sg.cell, sg.shuffle0, sg.n_shuffles) for segs in plan for sg in segs) == \
         [(0, 0, 4), (0, 4, 4), (0, 8, 2), (1, 0, 3)]
     assert frt.plan_cells([], 80, 3, batch_size=4) == [[], [], []]
+
+
+# ------------------------------------------------- bench.py's strong-scaling leg, two gloo ranks
+def _strong_worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from datetime import timedelta
+
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=timedelta(seconds=120))
+    try:
+        import json
+        import time
+
+        import bench
+        from farkle_ii_b200.strategies import generate_strategy_grid, pack_strategies
+
+        table = pack_strategies(generate_strategy_grid(
+            score_thresholds=[250, 300, 350, 400], smart_five_opts=[True], smart_one_opts=[True],
+            consider_score_opts=[True], consider_dice_opts=[True], auto_hot_dice_opts=[True],
+            run_up_score_opts=[True])[0])
+
+        def timer(fn, reps):
+            out = fn()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                out = fn()
+            return (time.perf_counter() - t0) * 1e3 / reps, out
+
+        res = bench.strong_scaling_leg(_oracle_play_cells([]), table, rank, world, 2, timer,
+                                       cells=[(9, 2, 12), (9, 4, 12), (9, 5, 7)], n_strategies=len(table), batch=3)
+        (Path(out_dir) / f"strong{rank}.json").write_text(json.dumps(res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bench_strong_scaling_leg_two_ranks(tmp_path):
+    """The strong-scaling leg of bench.py as the ranks run it (N-rank pass with one all-reduce, then
+    rank 0 alone WITHOUT a collective while the others wait at a barrier): completes, both passes
+    give identical tallies.  (A collective entered by rank 0 alone deadlocked the 8-GPU run once.)"""
+    import json
+
+    import oracle
+
+    oracle.build()
+    mp.spawn(_strong_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (json.loads((tmp_path / f"strong{r}.json").read_text()) for r in (0, 1))
+    games = 12 * 40 + 12 * 20 + 7 * 16
+    for r in (r0, r1):
+        assert r["n_gpus"] == 2 and r["games_attempted"] == games and r["identical_tallies_n1_vs_nN"]
+        assert sorted(x for segs in r["plan"] for x in segs) == sorted(x for segs in r0["plan"] for x in segs)
+    assert r0["n1_ms"] > 0 and r0["nN_ms"] > 0 and len(r0["plan"]) == 2
