@@ -21,9 +21,9 @@
 // The active seat lives in registers.  Generic k: a turn switch stores lines 0-2 of the outgoing
 // seat (three 16-byte st.cg) and takes the incoming seat from this lane's shared-memory staging
 // slots, which a cp.async prefetch filled during the turn that just ended; the records of the
-// games in flight stay L2 resident.  Two seats (K2): the seat that is not playing lives in the
-// lane's shared-memory slots for the whole game (a switch swaps the three mutable lines and
-// reloads the two constant ones); global memory is touched when a game starts and when it ends.
+// games in flight stay L2 resident.  Two seats (K2): each seat has a home slot in the lane's
+// shared memory for the whole game (a switch stores three mutable lines to one slot and loads
+// five lines from the other); global memory is touched when a game starts and when it ends.
 //
 // play_kernel   one game per lane, loop body = ONE ROLL, straight-line; persistent CTAs
 //               (one per SM); a lane whose game ended takes the next game from its warp's
@@ -96,10 +96,13 @@ constexpr int PLAY_THREADS = 1024;
 constexpr uint32_t STAGE_STRIDE = PLAY_THREADS * 16u;
 constexpr uint32_t QUEUE_CAP = 64;  // games per warp queue (a top-up adds <= 32 to < 32)
 // Generic kernel: 5 staging lines per lane (the prefetched record of the seat that plays next).
-// K2 kernel: 7 lines per lane -- lines 0-2 hold the mutable part of the seat that is NOT playing,
-// lines 3-4 / 5-6 the constant part (increment, strategy constants) of seat 0 / seat 1 -- so a
-// two-seat game lives in registers + shared memory from its first roll to its last.
-__host__ __device__ constexpr uint32_t stage_lines(bool k2) { return k2 ? 7u : 5u; }
+// K2 kernel: 10 lines per lane, a HOME SLOT of five lines for each seat -- lines 5*s .. 5*s+2 the
+// mutable part of seat s, lines 5*s+3, 5*s+4 its constants (increment, strategy constants) -- so a
+// two-seat game lives in registers + shared memory from its first roll to its last, and a turn
+// switch stores the outgoing seat to ITS slot before loading the incoming one from the other slot:
+// no swap through temporaries, the loads land in the registers the stores just freed.  (The compact
+// score table, scoring.cuh, is what makes 160 KB of slots fit beside the tables.)
+__host__ __device__ constexpr uint32_t stage_lines(bool k2) { return k2 ? 10u : 5u; }
 __host__ __device__ constexpr size_t play_queue_offset(bool k2) { return (size_t)((LUT_BYTES + 15) & ~15) + stage_lines(k2) * STAGE_STRIDE; }
 __host__ __device__ constexpr size_t play_smem_bytes(bool k2) { return play_queue_offset(k2) + (PLAY_THREADS / 32) * QUEUE_CAP * 4u; }
 static_assert(play_smem_bytes(true) <= 227u * 1024u, "K2 staging must fit the 227 KB of one CTA");
@@ -199,18 +202,17 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
     auto start_turn_from_l2 = [&]() {
         const uint4* sp = reinterpret_cast<const uint4*>(P.seats + (g * (uint32_t)k + (uint32_t)seat));
         if (K2) {
-            // A two-seat game starts: seat 0 goes to registers, the mutable lines of seat 1 and the
-            // constant lines of both seats go to this lane's shared-memory slots; after that the
-            // game touches global memory again only when it ends.
+            // A two-seat game starts: seat 0 goes to registers, seat 1 and the constants of seat 0 go
+            // to the home slots; after that the game touches global memory again only when it ends.
             const uint4 m0 = __ldcg(sp), m1 = __ldcg(sp + 1), m2 = __ldcg(sp + 2), i0 = __ldcg(sp + 3), i1 = __ldcg(sp + 4);
             const uint4 q0 = __ldcg(sp + 5), q1 = __ldcg(sp + 6), q2 = __ldcg(sp + 7), j0 = __ldcg(sp + 8), j1 = __ldcg(sp + 9);
-            sts128(stage, q0);
-            sts128(stage + STAGE_STRIDE, q1);
-            sts128(stage + 2u * STAGE_STRIDE, q2);
             sts128(stage + 3u * STAGE_STRIDE, i0);
             sts128(stage + 4u * STAGE_STRIDE, i1);
-            sts128(stage + 5u * STAGE_STRIDE, j0);
-            sts128(stage + 6u * STAGE_STRIDE, j1);
+            sts128(stage + 5u * STAGE_STRIDE, q0);
+            sts128(stage + 6u * STAGE_STRIDE, q1);
+            sts128(stage + 7u * STAGE_STRIDE, q2);
+            sts128(stage + 8u * STAGE_STRIDE, j0);
+            sts128(stage + 9u * STAGE_STRIDE, j1);
             start_turn(m0, m1, m2, i0, i1);
             return;
         }
@@ -437,11 +439,12 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                     stb = trig_now ? score : stb;
                     round += (closes && !capped) ? 1 : 0;
                     const bool over = fin || capped;
-                    // the other seat's mutable lines come out of the slots, this seat's go in
-                    const uint4 p0 = lds128(stage), p1 = lds128(stage + STAGE_STRIDE);
-                    const uint4 p2 = lds128(stage + 2u * STAGE_STRIDE);
+                    const uint32_t home = stage + 5u * (uint32_t)seat * STAGE_STRIDE;          // this seat's slot
+                    const uint32_t other = stage + 5u * (uint32_t)(seat ^ 1) * STAGE_STRIDE;  // the other seat's
                     if (over || (err & FB_ROW_ROLL_LIMIT)) {
                         // the game ends: both records go back to global memory for the finish pass
+                        const uint4 p0 = lds128(other), p1 = lds128(other + STAGE_STRIDE);
+                        const uint4 p2 = lds128(other + 2u * STAGE_STRIDE);
                         __stcg(sp, l0);
                         __stcg(sp + 1, l1);
                         __stcg(sp + 2, l2);
@@ -453,12 +456,13 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                                       (((trigger < 0 ? FB_ROW_SAFETY_LIMIT : 0u) | (err & 0xffu)) << 16);
                         status = ST_NEED;
                     } else {
-                        sts128(stage, l0);
-                        sts128(stage + STAGE_STRIDE, l1);
-                        sts128(stage + 2u * STAGE_STRIDE, l2);
+                        // park this seat in its home slot, then seat the other one from its own
+                        sts128(home, l0);
+                        sts128(home + STAGE_STRIDE, l1);
+                        sts128(home + 2u * STAGE_STRIDE, l2);
                         seat ^= 1;
-                        const uint32_t cs = stage + (3u + 2u * (uint32_t)seat) * STAGE_STRIDE;
-                        start_turn(p0, p1, p2, lds128(cs), lds128(cs + STAGE_STRIDE));
+                        start_turn(lds128(other), lds128(other + STAGE_STRIDE), lds128(other + 2u * STAGE_STRIDE),
+                                   lds128(other + 3u * STAGE_STRIDE), lds128(other + 4u * STAGE_STRIDE));
                     }
                 } else {
                     // Who plays next.  Without a trigger event it is the seat predicted (and

@@ -6,16 +6,23 @@
 //   apply_discards                 src/farkle/game/scoring.py:548-578
 //   _decide_continue               src/farkle/simulation/strategies.py:125-162
 //
-// Layout of the lookup in shared memory (99,520 bytes per CTA):
-//   idxA[512] u8      packed 3-bit counts of faces 1,2,3 -> combo index 0..83
-//   idxB[512] u8      packed 3-bit counts of faces 4,5,6 -> combo index 0..83
-//   tab[3][84*84] u32 one copy per smart-discard variant of the strategy (0 none, 1 smart five,
+// Layout of the lookup in shared memory (26,448 bytes per CTA):
+//   rowA[512] u16     packed 3-bit counts of faces 1,2,3 -> offset of that combination's ROW in tab
+//   colB[512] u8      packed 3-bit counts of faces 4,5,6 -> column inside the row
+//   tab[3][924] u32   one copy per smart-discard variant of the strategy (0 none, 1 smart five,
 //                     2 smart five + one): score/50 (7 bits) | used (3) | single_fives (2) |
 //                     single_ones (2) | bits 16..25 the roll-dependent part of the discard-table
 //                     index, premultiplied (see disc_index)
 //   disc[16*864] u8   smart-discard decision
 // A roll's histogram h = sum 1 << 3*(face-1) indexes it as
-//   tab[variant][idxA[h & 511] * 84 + idxB[h >> 9]].
+//   tab[variant][rowA[h & 511] + colB[h >> 9]].
+// Only the 924 multisets of at most six dice exist, so the table is triangular: the 84 (c4,c5,c6)
+// combinations are numbered by ascending dice count, a (c1,c2,c3) combination that uses s dice owns
+// a row of C(9-s,3) entries (the combinations that fit in the remaining 6-s dice are exactly a
+// prefix of that numbering), and the rows are laid end to end: 84+3*56+6*35+10*20+15*10+21*4+28 =
+// 924 entries instead of 84*84.  Same two index loads and one table load as the square table, and
+// the row offset replaces the multiply by 84; what it buys is 73 KB of shared memory per CTA
+// (used by the two-seat kernel for per-seat home slots, play.cuh).
 #pragma once
 #include <cstdint>
 
@@ -25,17 +32,20 @@ namespace fb {
 
 constexpr int LUT_COMBOS = 84;  // multisets of <= 6 dice over 3 faces = C(9,3)
 constexpr int LUT_IDX = 512;
-constexpr int LUT_TAB = LUT_COMBOS * LUT_COMBOS;
+constexpr int LUT_TAB = 924;    // multisets of <= 6 dice over 6 faces = C(12,6)
 constexpr int LUT_VARIANTS = 3;
 // discard table: [consider_score 2][consider_dice 2][favor_score 2][require_both 2] x
 //                [all_singles 2][sf 3][bm 3][xs 8][yd 6]
 constexpr int DISC_INNER = 2 * 3 * 3 * 8 * 6;  // entries per strategy class = 864
 constexpr int LUT_DISC = 16 * DISC_INNER;      // 13,824
-constexpr int LUT_BYTES = 2 * LUT_IDX + 4 * LUT_VARIANTS * LUT_TAB + LUT_DISC;  // 99,520
+constexpr int LUT_BYTES = 3 * LUT_IDX + 4 * LUT_VARIANTS * LUT_TAB + LUT_DISC;  // 26,448
+constexpr int LUT_OFF_COLB = 2 * LUT_IDX;
+constexpr int LUT_OFF_TAB = 3 * LUT_IDX;
+constexpr int LUT_OFF_DISC = LUT_OFF_TAB + 4 * LUT_VARIANTS * LUT_TAB;
 
 struct ScoreLut {
-    uint8_t idxA[LUT_IDX];
-    uint8_t idxB[LUT_IDX];
+    uint16_t rowA[LUT_IDX];
+    uint8_t colB[LUT_IDX];
     uint32_t tab[LUT_VARIANTS * LUT_TAB];
     uint8_t disc[LUT_DISC];
 };
@@ -113,24 +123,44 @@ inline RollScore host_evaluate_counts(const int cin[6]) {
 }
 
 inline void host_build_lut(ScoreLut& lut) {
-    int combo[LUT_COMBOS][3];
+    // the 84 three-face combinations, numbered by ascending dice count (then lexicographically)
+    int combo[LUT_COMBOS][3], csum[LUT_COMBOS];
     int n = 0;
-    for (int i = 0; i < LUT_IDX; i++) lut.idxA[i] = lut.idxB[i] = 0xFF;
-    for (int a = 0; a <= 6; a++)
-        for (int b = 0; a + b <= 6; b++)
-            for (int c = 0; a + b + c <= 6; c++) {
-                combo[n][0] = a; combo[n][1] = b; combo[n][2] = c;
-                lut.idxA[a | (b << 3) | (c << 6)] = (uint8_t)n;
-                lut.idxB[a | (b << 3) | (c << 6)] = (uint8_t)n;
+    for (int s = 0; s <= 6; s++)
+        for (int a = 0; a <= s; a++)
+            for (int b = 0; a + b <= s; b++) {
+                combo[n][0] = a; combo[n][1] = b; combo[n][2] = s - a - b;
+                csum[n] = s;
                 n++;
             }
+    // rows: combination i of faces 1-3 (using csum[i] dice) owns the columns j with csum[j] <= 6 - csum[i]
+    int row_len[7], row_off[LUT_COMBOS];
+    for (int s = 0; s <= 6; s++) {
+        row_len[s] = 0;
+        for (int j = 0; j < LUT_COMBOS; j++) row_len[s] += csum[j] <= 6 - s;
+    }
+    int total = 0;
+    for (int i = 0; i < LUT_COMBOS; i++) {
+        row_off[i] = total;
+        total += row_len[csum[i]];
+    }
+    // (total == LUT_TAB: 924)
+    for (int i = 0; i < LUT_IDX; i++) {
+        lut.rowA[i] = 0;
+        lut.colB[i] = 0;
+    }
+    for (int i = 0; i < LUT_COMBOS; i++) {
+        const int key = combo[i][0] | (combo[i][1] << 3) | (combo[i][2] << 6);
+        lut.rowA[key] = (uint16_t)row_off[i];
+        lut.colB[key] = (uint8_t)i;
+    }
     for (int v = 0; v < LUT_VARIANTS; v++)
         for (int i = 0; i < LUT_COMBOS; i++)
-            for (int j = 0; j < LUT_COMBOS; j++) {
+            for (int j = 0; j < row_len[csum[i]]; j++) {
                 int c[6] = {combo[i][0], combo[i][1], combo[i][2], combo[j][0], combo[j][1], combo[j][2]};
                 const int nd = c[0] + c[1] + c[2] + c[3] + c[4] + c[5];
                 uint32_t e = 0;
-                if (nd <= 6) {
+                {
                     RollScore r = host_evaluate_counts(c);
                     e = (uint32_t)((r.score / 50) | (r.used << 7) | (r.sf << 10) | (r.so << 12));
                     // decide_smart_discards (scoring.py:369-467): candidates exist only with
@@ -140,7 +170,7 @@ inline void host_build_lut(ScoreLut& lut) {
                     const int excl = r.score == 50 * sfi + 100 * bm ? 1 : 0;  // all-discard scores 0
                     e |= (uint32_t)(((excl * 3 + sfi) * 3 + bm) * 48) << 16;
                 }
-                lut.tab[v * LUT_TAB + i * LUT_COMBOS + j] = e;
+                lut.tab[v * LUT_TAB + row_off[i] + j] = e;
             }
     // Smart-discard table.  A candidate "drop a lone fives and b lone ones" loses
     // u = a + 2b units of 50 points and frees D = a + b dice; whether it must bank depends
@@ -193,9 +223,9 @@ bool never_banks(int dice_threshold, uint32_t flags) {
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t lut_lookup(const ScoreLut* lut, uint32_t tab_off, uint32_t hist) {
-    const uint32_t a = lut->idxA[hist & 511u];
-    const uint32_t b = lut->idxB[hist >> 9];
-    return lut->tab[tab_off + a * LUT_COMBOS + b];
+    const uint32_t a = lut->rowA[hist & 511u];
+    const uint32_t b = lut->colB[hist >> 9];
+    return lut->tab[tab_off + a + b];
 }
 
 // decide_smart_discards (scoring.py:369-467) as ONE table lookup, branch free.
@@ -230,10 +260,15 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint32_t lut_lookup_s(uint32_t lut_s, uint32_t tab_off, uint32_t hist) {
-    const uint32_t a = lds_u8(lut_s + (hist & 511u));
-    const uint32_t b = lds_u8(lut_s + LUT_IDX + (hist >> 9));
-    return lds_u32(lut_s + 2 * LUT_IDX + 4u * (tab_off + a * LUT_COMBOS + b));
+    const uint32_t a = lds_u16(lut_s + 2u * (hist & 511u));
+    const uint32_t b = lds_u8(lut_s + LUT_OFF_COLB + (hist >> 9));
+    return lds_u32(lut_s + LUT_OFF_TAB + 4u * (tab_off + a + b));
 }
 __device__ __forceinline__ uint32_t smart_discards_s(uint32_t lut_s, uint32_t dbase, uint32_t e, int n, int ts,
                                                      int st_d, int dt_d) {
@@ -241,7 +276,7 @@ __device__ __forceinline__ uint32_t smart_discards_s(uint32_t lut_s, uint32_t db
     int xs = min(max(ts + score - st_d + 50, 0), 399);
     xs = (xs * 1311) >> 16;  // floor(xs / 50) for 0 <= xs <= 399
     const int yd = min(max(dt_d - (n - used) + 1, 0), 5);
-    return lds_u8(lut_s + (2 * LUT_IDX + 4 * LUT_VARIANTS * LUT_TAB) + dbase + (e >> 16) + (uint32_t)(xs * 6 + yd));
+    return lds_u8(lut_s + LUT_OFF_DISC + dbase + (e >> 16) + (uint32_t)(xs * 6 + yd));
 }
 
 // _decide_continue (strategies.py:125-162), branch free on the seat constants: a threshold

@@ -467,7 +467,7 @@ def _run_chunk_metrics(shuffle_tasks: Sequence[ShuffleTask | int], *, collect_ro
     manifest_file = Path(manifest_path or (Path(row_dir) / "manifest.jsonl")) if want_rows else None
     threads = io_threads if io_threads is not None else min(32, os.cpu_count() or 1)
     pool = None
-    pending: List[Tuple[Any, Path, Mapping[str, Any]]] = []       # (future, shard path, manifest record)
+    pending: List[Tuple[Any, Sequence[Path], Sequence[Mapping[str, Any]]]] = []  # (future, shard paths, manifest records)
 
     def shard_table(shard: np.ndarray, task: ShuffleTask):
         return compact_rows_to_table(
@@ -475,25 +475,40 @@ def _run_chunk_metrics(shuffle_tasks: Sequence[ShuffleTask | int], *, collect_ro
             game_index=np.arange(gps), deterministic_batch_id=task.deterministic_batch_id,
             shuffle_seed=task.shuffle_seed)
 
-    def build_and_write(shard: np.ndarray, task: ShuffleTask, out: Path) -> int:
+    def build_and_write(block: np.ndarray, group: Sequence[ShuffleTask], outs: Sequence[Path]) -> List[int]:
+        """One writer task = a run of consecutive shuffles (up to a deterministic batch): ONE Arrow
+        build for all their rows (numpy and Arrow release the GIL on arrays this size; per-shuffle
+        builds spend their time in interpreter overhead and serialise on it), then one zero-copy
+        slice and one Parquet file per shuffle."""
         import time
 
         import pyarrow.parquet as pq
 
         t0 = time.perf_counter()
-        tbl = shard_table(shard, task)
+        per = np.repeat(np.arange(len(group)), gps)
+        tbl = compact_rows_to_table(
+            block, root_seed=group[0].root_seed, k=group[0].k,
+            shuffle_index=np.array([t.shuffle_index for t in group], dtype=np.int64)[per],
+            game_index=np.tile(np.arange(gps, dtype=np.int32), len(group)),
+            deterministic_batch_id=np.array([t.deterministic_batch_id for t in group], dtype=np.int32)[per],
+            shuffle_seed=np.array([t.shuffle_seed for t in group], dtype=np.int64)[per])
         t1 = time.perf_counter()
-        _atomic_write(out, lambda p: pq.write_table(tbl, p))
+        counts = []
+        for i, out in enumerate(outs):
+            part = tbl.slice(i * gps, gps)
+            _atomic_write(out, lambda p, part=part: pq.write_table(part, p))
+            counts.append(part.num_rows)
         t2 = time.perf_counter()
         with _IO_LOCK:
             IO_STATS["arrow_build_cpu_s"] += t1 - t0
             IO_STATS["parquet_write_cpu_s"] += t2 - t1
-            IO_STATS["shards"] += 1
-        return tbl.num_rows
+            IO_STATS["shards"] += len(outs)
+        return counts
 
     def drain() -> None:
-        for fut, out, extra in pending:
-            _append_manifest(manifest_file, {"path": out.name, "rows": fut.result(), **extra})
+        for fut, outs, extras in pending:
+            for out, extra, n_rows in zip(outs, extras, fut.result()):
+                _append_manifest(manifest_file, {"path": out.name, "rows": n_rows, **extra})
         pending.clear()
 
     try:
@@ -511,21 +526,29 @@ def _run_chunk_metrics(shuffle_tasks: Sequence[ShuffleTask | int], *, collect_ro
             rows = rows.copy()
             rows["seats"]["strategy"] = state.ids[rows["seats"]["strategy"]]
             drain()                 # the previous launch's shards (written while this one played)
-            for i, task in enumerate(run):
-                shard = rows[i * gps:(i + 1) * gps]
-                out = Path(row_dir) / f"rows_{task.root_seed}_{task.k}p_{task.shuffle_index:012d}.parquet"
-                extra = shard_manifest_extra(state, task, out.name)
-                if shard_writer is not None:
-                    shard_writer(out, manifest_file, shard_table(shard, task), extra)
-                elif threads <= 1:
-                    _append_manifest(manifest_file, {"path": out.name, "rows": build_and_write(shard, task, out),
-                                                     **extra})
-                else:
-                    if pool is None:
-                        from concurrent.futures import ThreadPoolExecutor
+            outs = [Path(row_dir) / f"rows_{t.root_seed}_{t.k}p_{t.shuffle_index:012d}.parquet" for t in run]
+            extras = [shard_manifest_extra(state, t, o.name) for t, o in zip(run, outs)]
+            if shard_writer is not None:
+                for i, task in enumerate(run):
+                    shard_writer(outs[i], manifest_file, shard_table(rows[i * gps:(i + 1) * gps], task), extras[i])
+                continue
+            # writer tasks: runs of consecutive shuffles of one deterministic batch, at most 64 each
+            cuts = [0]
+            for i in range(1, len(run)):
+                if run[i].deterministic_batch_id != run[cuts[-1]].deterministic_batch_id or i - cuts[-1] >= 64:
+                    cuts.append(i)
+            cuts.append(len(run))
+            if pool is None and threads > 1:
+                from concurrent.futures import ThreadPoolExecutor
 
-                        pool = ThreadPoolExecutor(max_workers=threads, thread_name_prefix="fb-shard")
-                    pending.append((pool.submit(build_and_write, shard, task, out), out, extra))
+                pool = ThreadPoolExecutor(max_workers=threads, thread_name_prefix="fb-shard")
+            for i0, i1 in zip(cuts[:-1], cuts[1:]):
+                args = (rows[i0 * gps:i1 * gps], run[i0:i1], outs[i0:i1])
+                if pool is None:
+                    for out, extra, n_rows in zip(outs[i0:i1], extras[i0:i1], build_and_write(*args)):
+                        _append_manifest(manifest_file, {"path": out.name, "rows": n_rows, **extra})
+                else:
+                    pending.append((pool.submit(build_and_write, *args), outs[i0:i1], extras[i0:i1]))
         drain()
     finally:
         if pool is not None:

@@ -201,9 +201,16 @@ def derive_ranks(rows: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
     (game/engine.py:483), nulls for safety-limit rows."""
     scores = rows["seats"]["score"].astype(np.int64)
     n, k = scores.shape
-    order = np.argsort(-scores, axis=1, kind="stable")
-    rank = np.empty((n, k), dtype=np.int8)
-    np.put_along_axis(rank, order, np.arange(1, k + 1, dtype=np.int8)[None, :], axis=1)
+    # rank of seat s = 1 + seats ahead of it (higher score, or equal score and lower seat): k*k
+    # vector comparisons instead of n small sorts; order = the inverse permutation of rank
+    rank = np.ones((n, k), dtype=np.int8)
+    for s in range(k):
+        for o in range(k):
+            if o != s:
+                ahead = scores[:, o] > scores[:, s] if o > s else scores[:, o] >= scores[:, s]
+                rank[:, s] += ahead
+    order = np.empty((n, k), dtype=np.intp)
+    np.put_along_axis(order, rank.astype(np.intp) - 1, np.arange(k, dtype=np.intp)[None, :], axis=1)
     safety = (rows["flags"] & ROW_SAFETY_LIMIT) != 0
     rank[safety] = 0
     return rank, order
@@ -357,15 +364,16 @@ def compact_rows_to_table(rows: np.ndarray, *, root_seed: int, k: int, shuffle_i
     w = np.where(safety, 0, rows["winner_seat"]).astype(np.int64)
     ar = np.arange(n)
     win_score = scores[ar, w]
-    sorted_scores = np.sort(scores, axis=1)[:, ::-1]
-    margin = sorted_scores[:, 0] - (sorted_scores[:, 1] if k > 1 else 0)
-    names = np.array([f"P{i + 1}" for i in range(k)], dtype=object)
+    margin = scores[ar, order[:, 0]] - (scores[ar, order[:, 1]] if k > 1 else 0)   # winner minus runner-up
+    # string columns by `take` from tiny dictionaries (no Python string objects per row: at ingest
+    # rate this build, not the GPU, is the bottleneck of rows mode)
+    names = pa.array([f"P{i + 1}" for i in range(k)], type=pa.string())
+    status_names = pa.array(["completed", "safety_limit"], type=pa.string())
 
     def full(v, dtype):
         return np.broadcast_to(np.asarray(v, dtype=dtype), (n,))
 
-    seat_rank_values = pa.array(names[order].reshape(-1), type=pa.string(),
-                                mask=np.repeat(safety, k))
+    seat_rank_values = names.take(pa.array(order.reshape(-1).astype(np.int32), mask=np.repeat(safety, k)))
     seat_ranks = pa.ListArray.from_arrays(pa.array(np.arange(0, n * k + 1, k, dtype=np.int32)),
                                           seat_rank_values, type=schema.field("seat_ranks").type)
     cols: dict[str, Any] = {
@@ -375,11 +383,10 @@ def compact_rows_to_table(rows: np.ndarray, *, root_seed: int, k: int, shuffle_i
         "game_index": pa.array(full(game_index, np.int32)),
         "deterministic_batch_id": pa.array(full(deterministic_batch_id, np.int32)),
         "shuffle_seed": pa.array(full(shuffle_seed, np.int64)),
-        "termination_status": pa.array(np.where(safety, "safety_limit", "completed").astype(object),
-                                       type=pa.string()),
+        "termination_status": status_names.take(pa.array(safety.astype(np.int8))),
         "hit_safety_limit": pa.array(safety),
         "outcome_schema_version": pa.array(full(OUTCOME_SCHEMA_VERSION, np.int16)),
-        "winner_seat": pa.array(names[w], type=pa.string(), mask=safety),
+        "winner_seat": names.take(pa.array(w.astype(np.int32), mask=safety)),
         "winner_strategy": pa.array(seats["strategy"][ar, w].astype(np.int32), mask=safety),
         "game_seed": pa.array(rows["game_seed"].astype(np.int64)),
         "rng_scheme_version": pa.array(full(RNG_SCHEME_VERSION, np.int16)),

@@ -44,9 +44,9 @@ cfg.screening.practical_delta_by_k = {2: 0.03, 4: 0.03}
 cfg.screening.delta_across_k = 0.03
 cfg.head2head.total_game_cap = None
 cfg.head2head.n_jobs = 0 if kind == "reference" else 1
-cfg.resources.scheduler_memory_budget_mb = 1 << 16
-cfg.resources.process_tree_warning_threshold_mb = 1 << 17
-cfg.resources.aggregate_memory_hard_limit_mb = 1 << 18
+cfg.resources.scheduler_memory_budget_mb = 8192
+cfg.resources.process_tree_warning_threshold_mb = 24576
+cfg.resources.aggregate_memory_hard_limit_mb = 32768
 cfg.resources.minimum_system_available_memory_mb = 256
 cfg.resources.logical_cpu_budget = os.cpu_count() or 1
 step = 5160 // n_cand

@@ -207,3 +207,20 @@ def test_lag_request_struct_layout_matches_header(tmp_path):
     out = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert out[0] == ctypes.sizeof(_native.Cell) == 40
     assert out[1:] == [getattr(_native.Cell, f).offset for f in cell_fields]
+
+
+def test_score_lookup_table_layout(tmp_path):
+    """The triangular score table of csrc/scoring.cuh (924 entries per variant instead of 84 x 84):
+    rowA/colB address every multiset of at most six dice exactly once and every entry carries the
+    fields of `host_evaluate_counts` (scoring_lookup.py:123-172) -- checked on the host, no GPU."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    exe = tmp_path / "lut_check"
+    subprocess.run([gxx, "-std=c++17", "-O1", "-o", str(exe), str(Path(__file__).parent / "lut_check.cpp")],
+                   check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(x) for x in out] == [924, 0, 924, 26448]
