@@ -43,7 +43,7 @@ cfg = AppConfig(io=IOConfig(results_dir_prefix=Path(out) / "results"),
 cfg.screening.practical_delta_by_k = {2: 0.03, 4: 0.03}
 cfg.screening.delta_across_k = 0.03
 cfg.head2head.total_game_cap = None
-cfg.head2head.n_jobs = 0 if kind == "reference" else 1
+cfg.head2head.n_jobs = 1       # identical configuration (it is hashed into every sidecar) in both runs
 cfg.resources.scheduler_memory_budget_mb = 8192
 cfg.resources.process_tree_warning_threshold_mb = 24576
 cfg.resources.aggregate_memory_hard_limit_mb = 32768
@@ -70,7 +70,7 @@ sm = cfg.strategy_manifest_root_path()
 sm.parent.mkdir(parents=True, exist_ok=True)
 build_strategy_manifest(generate_strategy_grid()[0]).to_parquet(sm)
 schedule = pq.read_table(cfg.h2h_block_manifest_path()).to_pandas()
-kw = {}
+kw = dict(n_jobs=os.cpu_count() or 1)        # the reference's pool: all host cores
 if kind == "batched":
     sys.path.insert(0, repo)
     from farkle_ii_b200 import h2h

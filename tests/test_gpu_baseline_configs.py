@@ -336,8 +336,6 @@ def test_all_player_statistics(eng, golden_dir, name, spb, with_ids):
     res = eng.play_tournament(root, k, sh0, nsh, table, shuffles_per_slot=spb, want_all_player=True,
                               want_rows=True, want_game_seeds=True, strategy_ids=ids)
     rows = res.rows_numpy()
-    if ids is None:
-        assert rows.tobytes() == z["rows"].tobytes()
     gps = n // k
     batch = (np.arange(len(rows)) // gps) // spb
     n_ids = n if ids is None else int(ids.max()) + 1
