@@ -45,8 +45,23 @@ SHUFFLES_PER_BATCH = 43
 CELLS_K = (2, 4)
 ROOTS = (42, 43)
 MEGA_K, MEGA_ROOT = (2, 3, 4, 5, 6, 8, 10, 12), 102   # configs/farkle_mega_config.yaml:10-14
-# algorithmic lane-instruction model of SURVEY.md §8d (play kernel: words, dice, rolls)
-W_OPS, D_OPS, R_OPS, S_OPS = 28, 8, 90, 1000
+# Lane-instruction model of SURVEY.md §8d (play kernel): W per PCG64-DXSM word, D per die, R per roll.
+# SURVEY's estimates were 28 / 8 / 90; the constants used are SASS-exact, from the ncu captures of the
+# two play_kernel variants (scripts/sass_model.py -> profiles/sass_model.json; these defaults are the
+# round-2 values): 3 W + 6 D + R is what the kernel EXECUTES per roll (three words and six die slots
+# are computed for every roll), W words + D dice + R rolls with the words and dice actually consumed
+# is the algorithmic work.
+SASS_MODEL_DEFAULT = {"k2": {"W": 26.0, "D": 7.2, "R": 142.5}, "generic": {"W": 26.0, "D": 7.2, "R": 149.8}}
+SURVEY_MODEL = {"W": 28.0, "D": 8.0, "R": 90.0}
+
+
+def sass_model() -> dict:
+    try:
+        got = json.loads((ROOT / "profiles" / "sass_model.json").read_text())
+        return {kind: {c: float(got[kind][c]) for c in "WDR"} | {"source": got[kind].get("source")}
+                for kind in ("k2", "generic")}
+    except Exception:
+        return SASS_MODEL_DEFAULT
 METRIC = "simulated games/sec at 1/2/4/8 B200 (bit-exact tallies) vs reference CPU n_jobs"
 
 
@@ -136,9 +151,11 @@ class ClockSampler:
                 "reasons": [n for i, n in enumerate(self.NAMES) if seen >> i & 1], "source": self.source}
 
 
-def algorithmic_ops(totals: np.ndarray, k_seats: int) -> float:
-    """SURVEY.md §8d model: W*words + D*dice + R*rolls (+ S per seat for the seed kernel)."""
-    return float(W_OPS * totals[5] + D_OPS * totals[4] + R_OPS * totals[3] + S_OPS * k_seats)
+def lane_ops(totals: np.ndarray, c: dict) -> tuple[float, float]:
+    """(algorithmic, executed) lane instructions of one play_kernel launch from its work counters
+    (totals: 3 rolls, 4 dice, 5 rng words) and the model constants `c`."""
+    rolls, dice, words = float(totals[3]), float(totals[4]), float(totals[5])
+    return c["W"] * words + c["D"] * dice + c["R"] * rolls, (3 * c["W"] + 6 * c["D"] + c["R"]) * rolls
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -419,7 +436,10 @@ def main() -> None:
         eng.play_tournament(ROOTS[(args.steps - 1) % 2], k, shuffle0, n_sh, table_dev, tallies=tallies[k],
                             totals=totals[k])
         tot = totals[k].cpu().numpy()
-        kern[k].update({"totals": tot, "games": int(tot[0]), "ops": algorithmic_ops(tot, 0)})
+        model_k = sass_model()["k2" if k == 2 else "generic"]
+        alg, exe = lane_ops(tot, model_k)
+        kern[k].update({"totals": tot, "games": int(tot[0]), "ops": alg, "ops_executed": exe,
+                        "ops_survey": lane_ops(tot, SURVEY_MODEL)[0], "model": model_k})
     # e2e through the host-buffer C-ABI call
     out_t = {k: np.empty((1, N_STRATEGIES, TALLY_WIDTH), dtype=np.int64) for k in CELLS_K}
     pin = torch.from_numpy(table_host.view(np.uint8).copy()).pin_memory()
@@ -578,13 +598,23 @@ def main() -> None:
         "bound": "issue", "kernel": f"play_kernel (k={dom} cell, {kern[dom]['games']} games/launch)",
         "achieved": achieved / 1e12, "peak": peak_measured / 1e12, "unit": "Tlaneop/s",
         "frac": achieved / peak_measured,
+        "frac_model": achieved / peak_measured,
+        "frac_executed": kern[dom]["ops_executed"] / (kern[dom]["ms"] * 1e-3) / peak_measured,
+        "frac_survey_constants": kern[dom]["ops_survey"] / (kern[dom]["ms"] * 1e-3) / peak_measured,
+        "frac_by_k": {str(k_): {"model": kern[k_]["ops"] / (kern[k_]["ms"] * 1e-3) / peak_measured,
+                                "executed": kern[k_]["ops_executed"] / (kern[k_]["ms"] * 1e-3) / peak_measured}
+                      for k_ in CELLS_K},
         "peak_source": ("measured: fb_measure_issue_peak = best of four register-only integer-chain "
                         "probes at 1,024 threads/SM (the LOP3 + IMAD.IADD one issues at ~0.98 IPC: "
                         "profiles/r02_issue_peak.md); MEASURED_PEAKS.json holds no integer peak"),
         "peak_variants": {str(v): eng.measure_issue_peak_variant(v) / 1e12 for v in range(5)},
         "peak_nominal": nominal_peak / 1e12,
-        "model": (f"algorithmic lane-instructions = {W_OPS}*rng_words + {D_OPS}*dice + "
-                  f"{R_OPS}*rolls (SURVEY.md §8d), counts returned by the kernel"),
+        "model": (f"algorithmic lane-instructions = {kern[dom]['model']['W']}*rng_words + "
+                  f"{kern[dom]['model']['D']}*dice + {kern[dom]['model']['R']}*rolls: SURVEY.md §8d's formula "
+                  "with SASS-exact constants of this kernel (scripts/sass_model.py on the ncu capture under "
+                  "profiles/; SURVEY's estimates were 28/8/90 -> frac_survey_constants); words, dice and rolls "
+                  "are returned by the kernel.  frac_executed charges the three words and six die slots "
+                  "the kernel computes for every roll = issue-active x lane efficiency"),
         "per_game": {"rolls": float(tot[3] / tot[0]), "dice": float(tot[4] / tot[0]),
                      "rng_words": float(tot[5] / tot[0]),
                      "lane_ops": float(kern[dom]["ops"] / tot[0])},
