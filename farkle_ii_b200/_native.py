@@ -32,7 +32,7 @@ SYMBOLS = (
     "fb_play_tournament_cells", "fb_matchup_scratch_bytes",
     "fb_play_h2h", "fb_h2h_resolve", "fb_play_games", "fb_run_tournament_host",
     "fb_measure_issue_peak", "fb_measure_issue_peak_variant", "fb_last_play_kernel_ms", "fb_play_kernel_ms_history",
-    "fb_kernel_launch_count",
+    "fb_kernel_launch_count", "fb_timeline", "fb_timeline_dump",
 )
 
 
@@ -137,6 +137,8 @@ def _declare(L: C.CDLL) -> None:
     L.fb_last_play_kernel_ms.restype = C.c_float
     L.fb_play_kernel_ms_history.argtypes = [C.POINTER(C.c_float), _int]
     L.fb_kernel_launch_count.restype = _u64
+    L.fb_timeline.argtypes = [_int]
+    L.fb_timeline_dump.argtypes = [C.c_char_p, _sz]
 
 
 def lib() -> C.CDLL:

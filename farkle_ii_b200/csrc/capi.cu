@@ -62,7 +62,10 @@ struct Ctx {
     // cell a previous call prepared ahead of time
     cudaStream_t s_prep = nullptr;
     cudaEvent_t ev_cells_entry = nullptr, ev_cell_prepared[2] = {nullptr, nullptr},
-                ev_cell_played[2] = {nullptr, nullptr};
+                ev_play_kernel_done[2] = {nullptr, nullptr};
+    // set by fb_play_tournament_cells around a PLAY phase: launch_play records it right behind
+    // play_kernel (before the finish pass) and clears it
+    cudaEvent_t after_play_kernel = nullptr;
     struct Ahead {
         bool valid = false;
         uint64_t root_seed = 0, shuffle0 = 0;
@@ -126,6 +129,27 @@ int fail(int code, const char* fmt, ...) {
         if (g_ctx.device < 0)                                                    \
             return fail(FB_ERR_NO_DEVICE, "fb_init has not succeeded: no CUDA device bound"); \
     } while (0)
+
+// Timeline hook (fb_timeline): when enabled, a timing event is recorded on the launching stream
+// behind every kernel of the tournament path; fb_timeline_dump reports them relative to the first
+// mark.  Off by default (no events, no cost).
+struct TlMark {
+    const char* name;
+    int lane;  // 0 = caller's stream, 1 = preparation stream
+    cudaEvent_t ev;
+};
+std::mutex g_tl_mu;
+std::vector<TlMark> g_tl;
+std::atomic<bool> g_tl_on{false};
+inline void tl_mark(const char* name, cudaStream_t s, int lane = 0) {
+    if (!g_tl_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lock(g_tl_mu);
+    if (g_tl.size() >= 4096) return;
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, s);
+    g_tl.push_back({name, lane, ev});
+}
 
 inline int launch_check(const char* what) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -385,27 +409,40 @@ __global__ void check_ids_kernel(const int32_t* ids, int n, int n_tally_ids, uns
 
 // Generator.permutation(n) per shuffle: Fisher-Yates from the top with masked
 // rejection on buffered 32-bit draws (run_tournament.py:312-318).  The swap chain is
-// sequential per shuffle but the draws are not: ONE WARP walks one shuffle.  Per batch,
-// lane j jumps the LCG ahead by j steps (S_j = A^j S + (A^j-1)/(A-1) inc, constants in
-// JumpTable) and emits the j-th 64-bit output, i.e. 64 buffered 32-bit draws per batch;
-// then every lane replays the same accept/reject walk over them (warp-uniform, broadcast
-// shared-memory reads) and swaps in the shuffle's uint16 array in shared memory.
+// sequential per shuffle but the draws are not.  Per batch, lane j of a lane group jumps the LCG
+// ahead by j steps (S_j = A^j S + (A^j-1)/(A-1) inc, constants in JumpTable) and emits the j-th
+// 64-bit output, i.e. 2 * PERM_LANES buffered 32-bit draws per batch; then every lane of the group
+// replays the same accept/reject walk over them and one lane swaps in the shuffle's uint16 array in
+// shared memory.
 __device__ __forceinline__ void mul128(uint64_t ahi, uint64_t alo, uint64_t bhi, uint64_t blo, uint64_t& rhi,
                                        uint64_t& rlo) {
     rlo = alo * blo;
     rhi = __umul64hi(alo, blo) + alo * bhi + ahi * blo;
 }
 
-// Sub-warp layout: PERM_LANES lanes share one shuffle (they execute the identical walk on the same
-// array, which is what keeps the array consistent without locks), so a warp carries
-// PERM_SHUFFLES different shuffles through the same instruction stream.  The swap chain is
-// latency bound; running four chains per warp cuts the issue slots per shuffle by four.
+// Sub-warp layout: PERM_LANES lanes share one shuffle, so a warp carries PERM_SHUFFLES different
+// shuffles through the same instruction stream.  The kernel is LATENCY bound (one warp per CTA, a
+// few warps per SM, bounded by the shared memory of the arrays: 4,300 shuffles of a 5,160-entry
+// grid need two waves), so what counts is the length of the dependent chain per draw:
+//   * the draws of batch b+1 are generated (four 128-bit multiplies and the output function per
+//     lane, no dependence on the walk) in the same straight-line code as the walk over batch b,
+//     into the other half of a double-buffered ring: the arithmetic fills the shared-memory
+//     latency of the swaps instead of preceding them (a further split of the walk into a
+//     register-only accept pass one batch ahead of the swaps gained nothing: with one warp per
+//     scheduler the loop is bound by the ALU pipe's one warp instruction per two cycles, ~320
+//     instructions per batch of 16 draws);
+//   * the walk's own chain is v = h & mask -> accept = v <= i -> i -= accept -> mask halves when
+//     i drops to mask >> 1 (compare + select, no count-leading-zeros per draw);
+//   * a rejected draw costs no swap (the swap is predicated on accept), an accepted one is two
+//     loads and two stores by ONE lane of the group (a swap is not idempotent).
+// After the last swap (i == 0) further draws only "swap" a[0] with itself, so finished and unused
+// groups ride along without a live flag in the chain.
 constexpr int PERM_LANES = 8;
 constexpr int PERM_SHUFFLES = 32 / PERM_LANES;  // per warp (= per CTA: one warp per CTA)
 constexpr int PERM_RING = 2 * PERM_LANES;       // 32-bit draws per batch and shuffle
 
 __host__ __device__ inline size_t perm_bytes_per_shuffle(int n) {
-    return (((size_t)n * 2 + 15) & ~(size_t)15) + PERM_RING * 4;
+    return (((size_t)n * 2 + 15) & ~(size_t)15) + 2 * PERM_RING * 4;  // array + double-buffered ring
 }
 
 __global__ void __launch_bounds__(32) permute_warp_kernel(uint64_t root, int k, uint64_t shuffle0,
@@ -419,7 +456,7 @@ __global__ void __launch_bounds__(32) permute_warp_kernel(uint64_t root, int k, 
     const bool valid = j < n_shuffles;
     const size_t per = perm_bytes_per_shuffle(n);
     uint16_t* a = reinterpret_cast<uint16_t*>(perm_smem + sub * per);
-    uint32_t* ring = reinterpret_cast<uint32_t*>(perm_smem + sub * per + (per - PERM_RING * 4));
+    uint32_t* ring = reinterpret_cast<uint32_t*>(perm_smem + sub * per + (per - 2 * PERM_RING * 4));
     for (int i = sl; i < n; i += PERM_LANES) a[i] = (uint16_t)i;
     Coord c{FB_PURPOSE_SHUFFLE_PERMUTATION, root, (uint64_t)k, shuffle0 + (uint64_t)j, 0, 0, 0, 0, 0};
     Pcg g;
@@ -427,49 +464,53 @@ __global__ void __launch_bounds__(32) permute_warp_kernel(uint64_t root, int k, 
     const uint64_t ahi = jt->a_hi[sl], alo = jt->a_lo[sl], ghi = jt->g_hi[sl], glo = jt->g_lo[sl];
     const uint64_t nahi = jt->a_hi[PERM_LANES], nalo = jt->a_lo[PERM_LANES];
     const uint64_t nghi = jt->g_hi[PERM_LANES], nglo = jt->g_lo[PERM_LANES];
-    constexpr int GROUPS = PERM_RING / 4;  // ring = GROUPS groups of four 32-bit draws
-    int grp = GROUPS;
+    // batch: the lane's state S_sl, its output -> halves 2*sl, 2*sl+1 of ring buffer b; then S
+    // advances by PERM_LANES steps
+    auto generate = [&](int b) {
+        uint64_t thi, tlo, uhi, ulo;
+        mul128(ahi, alo, g.hi, g.lo, thi, tlo);
+        mul128(ghi, glo, g.ihi, g.ilo, uhi, ulo);
+        const uint64_t slo = tlo + ulo;
+        const uint64_t shi = thi + uhi + (slo < tlo ? 1u : 0u);
+        const uint64_t o = pcg_output(shi, slo);
+        reinterpret_cast<uint2*>(ring + b * PERM_RING)[sl] = make_uint2((uint32_t)o, (uint32_t)(o >> 32));
+        mul128(nahi, nalo, g.hi, g.lo, thi, tlo);
+        mul128(nghi, nglo, g.ihi, g.ilo, uhi, ulo);
+        g.lo = tlo + ulo;
+        g.hi = thi + uhi + (g.lo < tlo ? 1u : 0u);
+    };
     int i = valid ? n - 1 : 0;
     uint32_t mask = 0xffffffffu >> __clz(i | 1);
+    int cur = 0;
+    generate(0);
     __syncwarp();
     while (__any_sync(0xffffffffu, i >= 1)) {
-        if (grp == GROUPS) {
-            // batch: the lane's state S_sl, its output -> halves 2*sl, 2*sl+1; then S += PERM_LANES steps
-            uint64_t thi, tlo, uhi, ulo;
-            mul128(ahi, alo, g.hi, g.lo, thi, tlo);
-            mul128(ghi, glo, g.ihi, g.ilo, uhi, ulo);
-            uint64_t slo = tlo + ulo;
-            uint64_t shi = thi + uhi + (slo < tlo ? 1u : 0u);
-            const uint64_t o = pcg_output(shi, slo);
-            __syncwarp();
-            reinterpret_cast<uint2*>(ring)[sl] = make_uint2((uint32_t)o, (uint32_t)(o >> 32));
-            mul128(nahi, nalo, g.hi, g.lo, thi, tlo);
-            mul128(nghi, nglo, g.ihi, g.ilo, uhi, ulo);
-            g.lo = tlo + ulo;
-            g.hi = thi + uhi + (g.lo < tlo ? 1u : 0u);
-            grp = 0;
-            __syncwarp();
-        }
-        // Every lane of a group performs the identical walk (i, mask and the accept decisions
-        // depend on the draws only, never on the array), but ONE lane of the group does the
-        // swaps: a swap is not idempotent, so identical swaps by several lanes are only correct
-        // under warp-lockstep execution, which CUDA does not promise.  Branch free: a rejected
-        // draw swaps a[i] with itself.
-        const uint4 h = reinterpret_cast<const uint4*>(ring)[grp++];
-        const uint32_t hs[4] = {h.x, h.y, h.z, h.w};
+        generate(cur ^ 1);  // the other buffer: its readers passed the __syncwarp below one trip ago
+        const uint4* rp = reinterpret_cast<const uint4*>(ring + cur * PERM_RING);
+        uint32_t hs[PERM_RING];
 #pragma unroll
-        for (int d = 0; d < 4; d++) {
-            const uint32_t v = hs[d] & mask;
-            const bool accept = v <= (uint32_t)i && i >= 1;
-            const int iv = accept ? (int)v : i;
-            if (sl == 0) {
-                const uint16_t x = a[i], y = a[iv];
-                a[i] = y;
-                a[iv] = x;
-            }
-            i -= accept ? 1 : 0;
-            mask = 0xffffffffu >> __clz(i | 1);
+        for (int q = 0; q < PERM_RING / 4; q++) {
+            const uint4 h = rp[q];
+            hs[4 * q] = h.x;
+            hs[4 * q + 1] = h.y;
+            hs[4 * q + 2] = h.z;
+            hs[4 * q + 3] = h.w;
         }
+#pragma unroll
+        for (int d = 0; d < PERM_RING; d++) {
+            const uint32_t v = hs[d] & mask;
+            const bool accept = v <= (uint32_t)i;
+            if (sl == 0 && accept) {
+                const uint16_t x = a[i], y = a[v];
+                a[i] = y;
+                a[v] = x;
+            }
+            i = max(i - (accept ? 1 : 0), 0);
+            const uint32_t half = mask >> 1;
+            mask = (uint32_t)i <= half ? half : mask;  // smallest 2^b - 1 that is >= i
+        }
+        __syncwarp();
+        cur ^= 1;
     }
     __syncwarp();
     if (!valid) return;
@@ -792,6 +833,7 @@ int launch_play(const PlayParams& P_in, const FinishParams& F, cudaStream_t stre
         t_ev_made = true;
     }
     cudaEvent_t* ev = t_ev[t_ev_count % EV_RING];
+    tl_mark("play_begin", stream);
     FB_CUDA(cudaEventRecord(ev[0], stream));
     const dim3 block((unsigned)warps * 32u);
     if (P.k == 2) {
@@ -805,13 +847,20 @@ int launch_play(const PlayParams& P_in, const FinishParams& F, cudaStream_t stre
     if (rc) return rc;
     FB_CUDA(cudaEventRecord(ev[1], stream));
     t_ev_count++;
+    tl_mark("play_kernel", stream);
+    if (g_ctx.after_play_kernel) {
+        FB_CUDA(cudaEventRecord(g_ctx.after_play_kernel, stream));
+        g_ctx.after_play_kernel = nullptr;
+    }
     const size_t tile = F.rows ? (size_t)256 * F.row_words * 4 : 0;  // <= 88 KB at k = 12
     if (tile > 40 * 1024 && !g_ctx.finish_opted) {
         FB_CUDA(cudaFuncSetAttribute(finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 352));
         g_ctx.finish_opted = true;
     }
     finish_kernel<<<(unsigned)((F.n_games + 255) / 256), 256, tile, stream>>>(F);
-    return launch_check("finish_kernel");
+    rc = launch_check("finish_kernel");
+    tl_mark("finish", stream);
+    return rc;
 }
 
 inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -1130,9 +1179,12 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
     uint4* prefix = reinterpret_cast<uint4*>(w.prefix);
     int rc = FB_OK;
     int32_t* limits = n_overrides > 0 ? w.limits : nullptr;
+    const int tl_lane = (g_ctx.s_prep && stream == g_ctx.s_prep) ? 1 : 0;
     if (phase & PHASE_PREPARE) {
+    tl_mark("prepare_begin", stream, tl_lane);
     rc = permute_shuffles(root_seed, k, shuffle0, n_shuffles, n_strategies, perm, inv, prefix, stream);
     if (rc) return rc;
+    tl_mark("permute", stream, tl_lane);
     FB_CUDA(cudaMemsetAsync(w.counter, 0, 4 * sizeof(unsigned int), stream));
     if (tallies_dev && strategy_ids_dev && !ids_trusted) {
         // explicit ids address the tally buffers: one pass over the table, one flag back
@@ -1151,6 +1203,7 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
         strategies_dev, w.seats, w.game_seed, limits, w.header, w.long_list, w.counter, prefix);
     rc = launch_check("seed_tournament_kernel");
     if (rc) return rc;
+    tl_mark("seed", stream, tl_lane);
     }  // PHASE_PREPARE
     if (!(phase & PHASE_PLAY)) return FB_OK;
     PlayParams P{};
@@ -1204,6 +1257,7 @@ static int play_tournament_impl(uint64_t root_seed, int k, uint64_t shuffle0, in
     const int n_chunks = (n_shuffles + G.chunk - 1) / G.chunk;
     tally_gather_kernel<<<dim3(blocks_for((uint64_t)n_strategies, 128), (unsigned)n_chunks), 128, 0, stream>>>(G);
     rc = launch_check("tally_gather_kernel");
+    tl_mark("gather", stream, tl_lane);
     if (rc || !lag) return rc;
     if (lag->all_player_dev) {
         AllPlayerParams A{};
@@ -1317,13 +1371,20 @@ int fb_play_tournament_cells(const fb_cell_t* cells, int n_cells, int n_ahead,
     cudaStream_t stream = (cudaStream_t)stream_v;
     std::lock_guard<std::mutex> lock(g_mu);
     if (!g_ctx.s_prep) {
-        int lo = 0, hi = 0;
-        FB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = least urgent
-        FB_CUDA(cudaStreamCreateWithPriority(&g_ctx.s_prep, cudaStreamNonBlocking, lo));
+        // Default priority, the same as the caller's stream.  Measured (scripts/timeline_step.py,
+        // profiles/r02_timeline.md): the block scheduler places a kernel's CTAs only when no CTA
+        // of a more urgent kernel is pending, so an urgent preparation stream holds the finish
+        // pass back until the permutation kernel's second wave is placed (window 2.24 ms), a less
+        // urgent one is held back by finish and gather (window 2.38 ms); at equal priority the
+        // finish pass goes first and the permutation kernel runs beside the tally pass (2.03 ms).
+        // FB_PREP_PRIO overrides (tuning knob).
+        int prio = 0;
+        if (const char* env = getenv("FB_PREP_PRIO")) prio = atoi(env);
+        FB_CUDA(cudaStreamCreateWithPriority(&g_ctx.s_prep, cudaStreamNonBlocking, prio));
         FB_CUDA(cudaEventCreateWithFlags(&g_ctx.ev_cells_entry, cudaEventDisableTiming));
         for (int i = 0; i < 2; i++) {
             FB_CUDA(cudaEventCreateWithFlags(&g_ctx.ev_cell_prepared[i], cudaEventDisableTiming));
-            FB_CUDA(cudaEventCreateWithFlags(&g_ctx.ev_cell_played[i], cudaEventDisableTiming));
+            FB_CUDA(cudaEventCreateWithFlags(&g_ctx.ev_play_kernel_done[i], cudaEventDisableTiming));
         }
     }
     // two workspace slots: cell i is prepared in one while cell i-1 is played out of the other
@@ -1376,20 +1437,33 @@ int fb_play_tournament_cells(const fb_cell_t* cells, int n_cells, int n_ahead,
         if (rc) return rc;
         FB_CUDA(cudaEventRecord(g_ctx.ev_cell_prepared[slot0], g_ctx.s_prep));
     }
-    for (int i = 0; i < n_all; i++) {
+    // play_kernel is persistent and fills every SM (all registers, all shared memory): nothing runs
+    // beside it, and a small kernel that gets onto the SMs first keeps its CTAs out.  So the
+    // preparation of cell i+1 is released by the END of cell i's play_kernel: it then runs beside
+    // cell i's finish and tally passes (which only read slot i), and the window between two play
+    // kernels is max(prepare, finish + gather) instead of their sum.  (Slot reuse: the passes of
+    // cell i-1, which read the slot cell i+1 is prepared in, precede play_kernel(i) on `stream`.)
+    for (int i = 0; i < n_cells; i++) {
         const int slot = (slot0 + i) & 1;
-        if (i + 1 < n_all) {  // prepare the next cell while this one is being played
+        FB_CUDA(cudaStreamWaitEvent(stream, g_ctx.ev_cell_prepared[slot], 0));
+        const bool more = i + 1 < n_all;
+        if (more) g_ctx.after_play_kernel = g_ctx.ev_play_kernel_done[slot];
+        rc = run(i, slot, PHASE_PLAY, stream);
+        const bool recorded = more && g_ctx.after_play_kernel == nullptr;
+        g_ctx.after_play_kernel = nullptr;
+        if (rc) return rc;
+        if (more) {
             const int nslot = slot ^ 1;
-            if (i >= 1) FB_CUDA(cudaStreamWaitEvent(g_ctx.s_prep, g_ctx.ev_cell_played[nslot], 0));
+            if (recorded) {
+                FB_CUDA(cudaStreamWaitEvent(g_ctx.s_prep, g_ctx.ev_play_kernel_done[slot], 0));
+            } else {  // nothing was played (empty cell): order behind whatever the stream holds
+                FB_CUDA(cudaEventRecord(g_ctx.ev_play_kernel_done[slot], stream));
+                FB_CUDA(cudaStreamWaitEvent(g_ctx.s_prep, g_ctx.ev_play_kernel_done[slot], 0));
+            }
             rc = run(i + 1, nslot, PHASE_PREPARE, g_ctx.s_prep);
             if (rc) return rc;
             FB_CUDA(cudaEventRecord(g_ctx.ev_cell_prepared[nslot], g_ctx.s_prep));
         }
-        if (i >= n_cells) break;  // the look-ahead cell is only prepared
-        FB_CUDA(cudaStreamWaitEvent(stream, g_ctx.ev_cell_prepared[slot], 0));
-        rc = run(i, slot, PHASE_PLAY, stream);
-        if (rc) return rc;
-        FB_CUDA(cudaEventRecord(g_ctx.ev_cell_played[slot], stream));
     }
     if (n_ahead == 1) {
         const fb_cell_t& c = cells[n_cells];
@@ -1713,6 +1787,32 @@ int fb_play_kernel_ms_history(float* out_ms, int max_entries) {
         FB_CUDA(cudaEventElapsedTime(&out_ms[i], ev[0], ev[1]));
     }
     return n;
+}
+
+int fb_timeline(int enable) {
+    std::lock_guard<std::mutex> lock(g_tl_mu);
+    for (TlMark& m : g_tl) cudaEventDestroy(m.ev);
+    g_tl.clear();
+    g_tl_on.store(enable != 0);
+    return FB_OK;
+}
+
+int fb_timeline_dump(char* out, size_t capacity) {
+    if (!out || capacity == 0) return fail(FB_ERR_BAD_ARG, "bad timeline buffer");
+    std::lock_guard<std::mutex> lock(g_tl_mu);
+    size_t used = 0;
+    out[0] = 0;
+    int written = 0;
+    for (const TlMark& m : g_tl) {
+        float ms = 0.0f;
+        FB_CUDA(cudaEventSynchronize(m.ev));
+        FB_CUDA(cudaEventElapsedTime(&ms, g_tl.front().ev, m.ev));
+        const int n = snprintf(out + used, capacity - used, "%d %s %.4f\n", m.lane, m.name, ms);
+        if (n < 0 || (size_t)n >= capacity - used) break;
+        used += (size_t)n;
+        written++;
+    }
+    return written;
 }
 
 float fb_last_play_kernel_ms(void) {

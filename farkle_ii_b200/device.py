@@ -202,6 +202,23 @@ class Engine:
     def kernel_launch_count(self) -> int:
         return int(self.lib.fb_kernel_launch_count())
 
+    def timeline(self, enable: bool) -> None:
+        """Start (and clear) or stop the per-kernel timeline log (``fb_timeline``)."""
+        _native.check(self.lib.fb_timeline(int(enable)))
+
+    def timeline_marks(self) -> list[tuple[int, str, float]]:
+        """``(lane, mark, ms since the first mark)`` per recorded kernel; lane 1 is the preparation
+        stream of ``play_cells``.  Waits for the recorded work."""
+        buf = C.create_string_buffer(1 << 18)
+        rc = self.lib.fb_timeline_dump(buf, len(buf))
+        if rc < 0:
+            _native.check(rc)
+        out = []
+        for line in buf.value.decode().splitlines():
+            lane, name, ms = line.split()
+            out.append((int(lane), name, float(ms)))
+        return out
+
     # ----------------------------------------------------------- building blocks
     def seedseq_generate(self, entropy: np.ndarray, n_words: int) -> np.ndarray:
         e = np.ascontiguousarray(entropy, dtype=np.uint32)

@@ -349,8 +349,9 @@ typedef struct fb_cell {
 size_t fb_cells_workspace_bytes(const fb_cell_t* cells, int n_cells, int n_strategies);
 /* Plays cells[0 .. n_cells) in order on `stream` with the results of fb_play_tournament called
  * once per cell, but pipelined: the permutations and seat seeding of cell i+1 run on an internal
- * low-priority stream, in the other workspace slot, under the end-of-launch tail and the finish /
- * tally passes of cell i (they only touch the workspace).  n_ahead = 1 additionally PREPARES
+ * stream, in the other workspace slot, released by the end of cell i's play_kernel, so that they
+ * run beside the finish / tally passes of cell i (they only touch the workspace; nothing can run
+ * beside the persistent play_kernel itself).  n_ahead = 1 additionally PREPARES
  * cells[n_cells] without playing it; the next call on the same workspace whose first cell equals
  * it (same strategies, limits) starts playing at once.  A runner that knows its cell list passes
  * it whole; one that is driven cell by cell passes the next cell as look-ahead.  No rows, seat
@@ -425,6 +426,14 @@ float fb_last_play_kernel_ms(void);
  * to max_entries durations (the library keeps the last 64) and returns how many were
  * written (negative fb_status on error).  Blocks until those kernels have finished.      */
 int fb_play_kernel_ms_history(float* out_ms, int max_entries);
+/* Timeline hook.  fb_timeline(1) clears the log and starts recording a CUDA timing event on the
+ * launching stream behind every kernel of the tournament path (permute, seed, play_kernel, finish,
+ * gather); fb_timeline(0) stops and clears.  fb_timeline_dump waits for the recorded events and
+ * writes one line per mark, "<lane> <name> <ms since the first mark>\n" (lane 0 = the caller's
+ * stream, 1 = the preparation stream of fb_play_tournament_cells), returning the number of lines
+ * written (negative fb_status on error).  Off by default: no events, no cost.  Process-wide.   */
+int fb_timeline(int enable);
+int fb_timeline_dump(char* out, size_t capacity);
 /* Roofline probe: register-only kernels of independent 32-bit integer chains on every SM
  * (1,024 threads per SM, no memory), returning measured lane-instructions per second.
  * Synchronous.  fb_measure_issue_peak reports the best of the mixed-pipe variants
