@@ -442,14 +442,13 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                     const uint32_t home = stage + 5u * (uint32_t)seat * STAGE_STRIDE;          // this seat's slot
                     const uint32_t other = stage + 5u * (uint32_t)(seat ^ 1) * STAGE_STRIDE;  // the other seat's
                     if (over || (err & FB_ROW_ROLL_LIMIT)) {
-                        // the game ends: both records go back to global memory for the finish pass
-                        const uint4 p0 = lds128(other), p1 = lds128(other + STAGE_STRIDE);
+                        // the game ends: the counters of both seats (lines 1-2; nobody reads a
+                        // finished game's generator state) go back to global memory for the finish pass
+                        const uint4 p1 = lds128(other + STAGE_STRIDE);
                         const uint4 p2 = lds128(other + 2u * STAGE_STRIDE);
-                        __stcg(sp, l0);
                         __stcg(sp + 1, l1);
                         __stcg(sp + 2, l2);
                         uint4* op = reinterpret_cast<uint4*>(P.seats + (g * 2u + (uint32_t)(seat ^ 1)));
-                        __stcg(op, p0);
                         __stcg(op + 1, p1);
                         __stcg(op + 2, p2);
                         P.header[g] = (uint32_t)round | (err & HDR_LONG) |
@@ -644,7 +643,13 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
             if (v[4]) atomicAdd(&s_tot[6], v[4]);
             if (v[5]) atomicAdd(&s_tot[7], v[5]);
         }
-        if (winner >= 0) atomicAdd(&s_tot[8 + winner], 1ull);
+        // wins by seat, warp-aggregated: a 64-bit shared-memory add is a compare-and-swap loop, and
+        // 256 threads adding 1 to the same two or three counters made those loops the kernel's top
+        // stall (short scoreboard 18.6 warps per issue cycle, profiles/r01_finish_kernel.md)
+        for (int s = 0; s < k; s++) {
+            const uint32_t won = __ballot_sync(FULL, winner == s);
+            if (lane == 0 && won) atomicAdd(&s_tot[8 + s], (unsigned long long)__popc(won));
+        }
         __syncthreads();
         if (threadIdx.x < FB_TOTALS_WIDTH && s_tot[threadIdx.x])
             atomicAdd(&F.totals[threadIdx.x], s_tot[threadIdx.x]);
