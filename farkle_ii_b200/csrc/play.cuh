@@ -11,8 +11,10 @@
 //
 // Data layout in HBM: one 80-byte Seat record per (game, seat), written by the seed kernels
 //   line 0  PCG state (16 B)
-//   line 1  saved half | score | highest_turn|has32<<30|has_scored<<31 | farkles|rolls<<16
-//   line 2  turns|hot<<16 | smart-five uses|dice<<16 | smart-one uses|dice<<16 | pad
+//   line 1  face queue lo | score | highest_turn|queue holds a rejected half<<30|has_scored<<31 |
+//           farkles|rolls<<16
+//   line 2  turns|hot<<16 | smart-five uses|dice<<16 | smart-one uses|dice<<16 |
+//           face queue hi (25 bits) | queue length in bits<<25
 //   line 3  PCG increment (16 B)
 //   line 4  st_d | kf|dt_d<<16 | dbase|tab_off<<16 | strategy table index   (seat_consts())
 //   game header 4 B  n_rounds | flags << 16 | HDR_LONG, written when the game ends; the seed
@@ -46,15 +48,26 @@ namespace fb {
 
 constexpr int ROLL_LIMIT = 1000;  // src/farkle/game/engine.py:36
 constexpr uint32_t HIGH_MASK = 0x3fffffffu;
-constexpr uint32_t HW_HAS32 = 1u << 30;
+constexpr uint32_t HW_REJ = 1u << 30;  // the seat's face queue holds a rejected half (code 6)
+// Face queue (the dice of a seat's stream that are already drawn): 3-bit codes, next die in the low
+// bits, 0..5 a face, 6 a half NumPy's Lemire test rejects (it is skipped, but it was read).
+// The queue length is kept in BITS (3 per code): it is the shift count of an insert as it stands.
+#ifndef FB_FQ_WORDS
+#define FB_FQ_WORDS 3
+#endif
+constexpr int FQ_WORDS = FB_FQ_WORDS;            // 64-bit outputs per top-up
+constexpr int FQ_CAP_BITS = 57;                  // 19 codes; bits 25..30 of the high word carry the length
+constexpr int FQ_GEN_BITS = 6 * FQ_WORDS;        // two codes per output
+constexpr uint32_t FQ_LEN_SHIFT = 25;
+constexpr uint32_t FQ_HI_MASK = (1u << FQ_LEN_SHIFT) - 1u;
 constexpr uint32_t HW_SCORED = 1u << 31;
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr uint32_t HDR_LONG = 1u << 31;
 
 struct __align__(16) Seat {
     uint4 state;  // PCG state lo0, lo1, hi0, hi1
-    uint4 a;      // saved | score | hw | farkles|rolls<<16
-    uint4 b;      // turns|hot<<16 | sf uses|dice<<16 | so uses|dice<<16 | pad
+    uint4 a;      // face queue lo | score | hw | farkles|rolls<<16
+    uint4 b;      // turns|hot<<16 | sf uses|dice<<16 | so uses|dice<<16 | face queue hi | length in bits<<25
     uint4 inc;    // PCG increment
     uint4 cst;    // st_d | kf|dt_d<<16 | dbase|tab_off<<16 | strategy table index
 };
@@ -151,7 +164,9 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
     int target = P.target_score, max_rounds = P.max_rounds;
     // active seat in registers
     Pcg rng{0, 0, 0, 0};
-    uint32_t saved = 0, hw = 0;
+    uint32_t hw = 0;
+    uint64_t fq = 0;  // face queue of the active seat
+    int fq_bits = 0;  // 3 x the number of queued codes
     int score = 0, st_d = 0, dt_d = 0;
     uint32_t c_fr = 0, c_th = 0, c_sf = 0, c_so = 0, kf = 0, dbase = 0, tab_off = 0;
     // active turn
@@ -169,7 +184,8 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
         rng.hi = (uint64_t)m0.z | ((uint64_t)m0.w << 32);
         rng.ilo = (uint64_t)i0.x | ((uint64_t)i0.y << 32);
         rng.ihi = (uint64_t)i0.z | ((uint64_t)i0.w << 32);
-        saved = m1.x;
+        fq = (uint64_t)m1.x | ((uint64_t)(m2.w & FQ_HI_MASK) << 32);
+        fq_bits = (int)(m2.w >> FQ_LEN_SHIFT);
         score = (int)m1.y;
         hw = m1.z;
         c_fr = m1.w;
@@ -305,79 +321,94 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
             if (__all_sync(FULL, status == ST_DEAD)) return true;
         }
 
+        // ================= G: top up the face queues ===========================
+        // A seat's dice are a pure function of its own stream of 32-bit halves, read in order
+        // (engine.py:85-101: Generator.integers(1, 7, size=n) draws n Lemire-bounded values from
+        // the buffered halves, re-drawing a half whose low product word is < 4), and nothing else
+        // reads that stream.  So the halves can be turned into faces AHEAD of the rolls that use
+        // them: every seat keeps a queue of 3-bit face codes, and the warp tops all its queues up by
+        // two 64-bit outputs (four codes) whenever some lane's queue is shorter than its next roll.
+        // That is 2.3-2.4 outputs computed per roll instead of three (2.13 are consumed), no
+        // per-word state selects, and no per-die window arithmetic: a roll takes its n codes off
+        // the queue with two shifts.
+        const bool playing = status == ST_PLAY;
+        const int need_bits = 3 * dice;
+        while (__any_sync(FULL, playing && fq_bits < need_bits)) {
+            if (playing && fq_bits <= FQ_CAP_BITS - FQ_GEN_BITS) {
+                uint64_t shi = rng.hi, slo = rng.lo;
+                // Lemire per half: face = high word of half * 6, rejected when the low word is < 4
+                // (4 in 2^32); codes packed two per output, first-read half lowest
+                uint32_t packed = 0, minl = 0xffffffffu;
+#pragma unroll
+                for (int w = 0; w < FQ_WORDS; w++) {
+                    const uint64_t o = pcg_output(shi, slo);
+                    pcg_step(shi, slo, rng.ihi, rng.ilo);
+                    const uint64_t m0 = (uint64_t)(uint32_t)o * 6u, m1 = (o >> 32) * 6u;
+                    minl = min(minl, min((uint32_t)m0, (uint32_t)m1));
+                    packed |= ((uint32_t)(m0 >> 32) + 8u * (uint32_t)(m1 >> 32)) << (6 * w);
+                }
+                if (minl < 4u) {  // redo the batch half by half, code 6 for a rejected half
+                    shi = rng.hi;
+                    slo = rng.lo;
+                    packed = 0;
+                    for (int w = 0; w < FQ_WORDS; w++) {
+                        const uint64_t o = pcg_output(shi, slo);
+                        pcg_step(shi, slo, rng.ihi, rng.ilo);
+                        const uint32_t u0 = (uint32_t)o, u1 = (uint32_t)(o >> 32);
+                        const uint32_t c0 = u0 * 6u < 4u ? 6u : __umulhi(u0, 6u);
+                        const uint32_t c1 = u1 * 6u < 4u ? 6u : __umulhi(u1, 6u);
+                        packed |= (c0 | (c1 << 3)) << (6 * w);
+                    }
+                    hw |= HW_REJ;
+                }
+                rng.hi = shi;
+                rng.lo = slo;
+                fq |= (uint64_t)packed << (uint32_t)fq_bits;
+                fq_bits += FQ_GEN_BITS;
+                a_words += (uint32_t)FQ_WORDS;
+            }
+        }
+
         // ================= P: one roll (straight-line, no divergent branches) =====
-        if (status == ST_PLAY) {
+        if (playing) {
             const int n = dice;
-            // -- dice: n consecutive 32-bit halves of the seat's stream (engine.py:101).
-            // Halves H0..H6 = [buffered half, lo/hi of up to three fresh 64-bit outputs];
-            // die i reads H[i + p].  All three outputs are always computed; the state only
-            // advances past the nw words this roll really consumes.
-            const uint32_t p = (hw & HW_HAS32) ? 0u : 1u;
-            const int nw = (n + (int)p) >> 1;
-            const bool c1 = nw > 0, c2 = nw > 1, c3 = nw > 2;
-            uint64_t shi = rng.hi, slo = rng.lo;
-            const uint64_t o1 = pcg_output(shi, slo);
-            {
-                uint64_t th = shi, tl = slo;
-                pcg_step(th, tl, rng.ihi, rng.ilo);
-                shi = c1 ? th : shi;
-                slo = c1 ? tl : slo;
-            }
-            const uint64_t o2 = pcg_output(shi, slo);
-            {
-                uint64_t th = shi, tl = slo;
-                pcg_step(th, tl, rng.ihi, rng.ilo);
-                shi = c2 ? th : shi;
-                slo = c2 ? tl : slo;
-            }
-            const uint64_t o3 = pcg_output(shi, slo);
-            {
-                uint64_t th = shi, tl = slo;
-                pcg_step(th, tl, rng.ihi, rng.ilo);
-                shi = c3 ? th : shi;
-                slo = c3 ? tl : slo;
-            }
-            const uint32_t H1 = (uint32_t)o1, H2 = (uint32_t)(o1 >> 32);
-            const uint32_t H3 = (uint32_t)o2, H4 = (uint32_t)(o2 >> 32);
-            const uint32_t H5 = (uint32_t)o3, H6 = (uint32_t)(o3 >> 32);
-            uint32_t hist = 0;
-            uint32_t minlo = 0xffffffffu;  // Lemire leftover; < 4 means NumPy redraws
-#define FB_DIE(i_, Ha_, Hb_)                                               \
-    {                                                                      \
-        const uint32_t u_ = p ? (Hb_) : (Ha_);                             \
-        minlo = min(minlo, u_ * 6u);                                       \
-        if ((i_) < n) hist += 1u << (3u * __umulhi(u_, 6u));               \
-    }
-            FB_DIE(0, saved, H1)
-            FB_DIE(1, H1, H2)
-            FB_DIE(2, H2, H3)
-            FB_DIE(3, H3, H4)
-            FB_DIE(4, H4, H5)
-            FB_DIE(5, H5, H6)
-#undef FB_DIE
-            // The buffered half afterwards is the high half of the last word consumed (only
-            // meaningful when an odd number of halves remains unread); has32 flips with odd n.
-            uint32_t nsaved = c3 ? H6 : (c2 ? H4 : H2);
-            uint32_t nhw = hw ^ (((uint32_t)n << 30) & HW_HAS32);
-            uint32_t words = (uint32_t)nw;
-            if (minlo < 4u) {
-                // A draw with leftover < 4 somewhere in the window (4 in 2^32 per die; unused
-                // slots can only add false alarms): replay this roll draw by draw.
-                PcgStream s{rng, saved, (hw & HW_HAS32) != 0u};
+            uint32_t hist;
+            if (!(hw & HW_REJ)) {
+                // the next n codes; the slots beyond them read as code 7, which counts nothing
+                const uint32_t bits = (uint32_t)fq | (0xffffffffu << (uint32_t)need_bits);
+                hist = lds_u32(lut_s + LUT_OFF_HIST3 + 4u * (bits & 511u)) +
+                       lds_u32(lut_s + LUT_OFF_HIST3 + 4u * ((bits >> 9) & 511u));
+                fq >>= (uint32_t)need_bits;
+                fq_bits -= need_bits;
+            } else {
+                // A rejected half somewhere in the queue: take the dice one code at a time,
+                // skipping it (and drawing more when the queue runs dry).
                 hist = 0;
-                words = 0;
-                for (int i = 0; i < n; i++) hist += 1u << (3u * s.die0(words));
-                shi = s.g.hi;
-                slo = s.g.lo;
-                nhw = s.has32 ? (hw | HW_HAS32) : (hw & ~HW_HAS32);
-                nsaved = s.saved;
+                for (int taken = 0; taken < n;) {
+                    if (fq_bits == 0) {
+                        const uint64_t o = pcg_output(rng.hi, rng.lo);
+                        pcg_step(rng.hi, rng.lo, rng.ihi, rng.ilo);
+                        const uint32_t u0 = (uint32_t)o, u1 = (uint32_t)(o >> 32);
+                        const uint32_t c0 = u0 * 6u < 4u ? 6u : __umulhi(u0, 6u);
+                        const uint32_t c1 = u1 * 6u < 4u ? 6u : __umulhi(u1, 6u);
+                        fq = c0 | (c1 << 3);
+                        fq_bits = 6;
+                        a_words += 1u;
+                    }
+                    const uint32_t code = (uint32_t)fq & 7u;
+                    fq >>= 3;
+                    fq_bits -= 3;
+                    if (code < 6u) {
+                        hist += 1u << (3u * code);
+                        taken++;
+                    }
+                }
+                bool rej = false;
+                uint64_t t = fq;
+                for (int i = 0; i < fq_bits; i += 3, t >>= 3) rej = rej || ((uint32_t)t & 7u) == 6u;
+                hw = rej ? hw : (hw & ~HW_REJ);
             }
-            rng.hi = shi;
-            rng.lo = slo;
-            hw = nhw;
-            saved = nsaved;
             a_dice += (uint32_t)n;
-            a_words += words;
 
             // -- score the roll (engine.py:103-147), discards, counters
             const uint32_t e = lut_lookup_s(lut_s, tab_off, hist);
@@ -420,8 +451,8 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                 hw = (hw & ~HIGH_MASK) | max(hw & HIGH_MASK, (uint32_t)banked);
                 const uint4 l0 = make_uint4((uint32_t)rng.lo, (uint32_t)(rng.lo >> 32), (uint32_t)rng.hi,
                                             (uint32_t)(rng.hi >> 32));
-                const uint4 l1 = make_uint4(saved, (uint32_t)score, hw, c_fr);
-                const uint4 l2 = make_uint4(c_th, c_sf, c_so, 0u);
+                const uint4 l1 = make_uint4((uint32_t)fq, (uint32_t)score, hw, c_fr);
+                const uint4 l2 = make_uint4(c_th, c_sf, c_so, (uint32_t)(fq >> 32) | ((uint32_t)fq_bits << FQ_LEN_SHIFT));
                 uint4* sp = reinterpret_cast<uint4*>(P.seats + (g * (uint32_t)k + (uint32_t)seat));
                 if (!K2) {
                     __stcg(sp, l0);
@@ -558,7 +589,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = F.k;
     unsigned long long t_rolls = 0, t_turns = 0;
-    uint32_t t_done = 0, t_safe = 0, t_err = 0;
+    uint32_t t_done = 0, t_safe = 0, t_err = 0, t_ahead = 0;
     int winner = -1;
     if (g < F.n_games) {
         const uint32_t hdr = F.header[g];
@@ -579,6 +610,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
             }
             t_rolls += a.w >> 16;
             t_turns += b.x & 0xffffu;
+            t_ahead += (b.w >> FQ_LEN_SHIFT) / 6u;  // whole outputs (two 3-bit codes) drawn ahead and never read
             if ((a.w >> 16) > 32767u || (a.z & HIGH_MASK) > 32767u || (b.y >> 16) > 32767u ||
                 (b.z >> 16) > 32767u || (b.x & 0xffffu) > 32767u || (b.x >> 16) > 32767u)
                 flags |= FB_ROW_I16_OVERFLOW;
@@ -629,9 +661,9 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
     // ---- totals: warp shuffle -> shared memory -> one global RED per CTA ----
     if (F.totals) {
         const int lane = threadIdx.x & 31;
-        unsigned long long v[6] = {t_done, (unsigned long long)t_done - t_safe, t_safe, t_rolls, t_turns, t_err};
+        unsigned long long v[7] = {t_done, (unsigned long long)t_done - t_safe, t_safe, t_rolls, t_turns, t_err, t_ahead};
 #pragma unroll
-        for (int i = 0; i < 6; i++) {
+        for (int i = 0; i < 7; i++) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(FULL, v[i], o);
         }
@@ -642,6 +674,9 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
             if (v[3]) atomicAdd(&s_tot[3], v[3]);
             if (v[4]) atomicAdd(&s_tot[6], v[4]);
             if (v[5]) atomicAdd(&s_tot[7], v[5]);
+            // totals[5] counts the 64-bit outputs the reference's generators would have PRODUCED:
+            // play_kernel adds the ones it computed, this takes back the ones still queued
+            if (v[6]) atomicAdd(&s_tot[5], 0ull - v[6]);
         }
         // wins by seat, warp-aggregated: a 64-bit shared-memory add is a compare-and-swap loop, and
         // 256 threads adding 1 to the same two or three counters made those loops the kernel's top

@@ -6,7 +6,7 @@
 //   apply_discards                 src/farkle/game/scoring.py:548-578
 //   _decide_continue               src/farkle/simulation/strategies.py:125-162
 //
-// Layout of the lookup in shared memory (26,448 bytes per CTA):
+// Layout of the lookup in shared memory (28,496 bytes per CTA):
 //   rowA[512] u16     packed 3-bit counts of faces 1,2,3 -> offset of that combination's ROW in tab
 //   colB[512] u8      packed 3-bit counts of faces 4,5,6 -> column inside the row
 //   tab[3][924] u32   one copy per smart-discard variant of the strategy (0 none, 1 smart five,
@@ -14,6 +14,7 @@
 //                     single_ones (2) | bits 16..25 the roll-dependent part of the discard-table
 //                     index, premultiplied (see disc_index)
 //   disc[16*864] u8   smart-discard decision
+//   hist3[512] u32    three queued face codes -> packed face counts (play.cuh, face queue)
 // A roll's histogram h = sum 1 << 3*(face-1) indexes it as
 //   tab[variant][rowA[h & 511] + colB[h >> 9]].
 // Only the 924 multisets of at most six dice exist, so the table is triangular: the 84 (c4,c5,c6)
@@ -38,16 +39,18 @@ constexpr int LUT_VARIANTS = 3;
 //                [all_singles 2][sf 3][bm 3][xs 8][yd 6]
 constexpr int DISC_INNER = 2 * 3 * 3 * 8 * 6;  // entries per strategy class = 864
 constexpr int LUT_DISC = 16 * DISC_INNER;      // 13,824
-constexpr int LUT_BYTES = 3 * LUT_IDX + 4 * LUT_VARIANTS * LUT_TAB + LUT_DISC;  // 26,448
+constexpr int LUT_BYTES = 3 * LUT_IDX + 4 * LUT_VARIANTS * LUT_TAB + LUT_DISC + 4 * LUT_IDX;  // 28,496
 constexpr int LUT_OFF_COLB = 2 * LUT_IDX;
 constexpr int LUT_OFF_TAB = 3 * LUT_IDX;
 constexpr int LUT_OFF_DISC = LUT_OFF_TAB + 4 * LUT_VARIANTS * LUT_TAB;
+constexpr int LUT_OFF_HIST3 = LUT_OFF_DISC + LUT_DISC;
 
 struct ScoreLut {
     uint16_t rowA[LUT_IDX];
     uint8_t colB[LUT_IDX];
     uint32_t tab[LUT_VARIANTS * LUT_TAB];
     uint8_t disc[LUT_DISC];
+    uint32_t hist3[LUT_IDX];  // three 3-bit face codes (6, 7 = no die) -> their packed face counts
 };
 static_assert(sizeof(ScoreLut) == LUT_BYTES, "lut layout");
 
@@ -148,6 +151,12 @@ inline void host_build_lut(ScoreLut& lut) {
     for (int i = 0; i < LUT_IDX; i++) {
         lut.rowA[i] = 0;
         lut.colB[i] = 0;
+        uint32_t h = 0;
+        for (int d = 0; d < 3; d++) {
+            const int code = (i >> (3 * d)) & 7;
+            if (code < 6) h += 1u << (3 * code);
+        }
+        lut.hist3[i] = h;
     }
     for (int i = 0; i < LUT_COMBOS; i++) {
         const int key = combo[i][0] | (combo[i][1] << 3) | (combo[i][2] << 6);

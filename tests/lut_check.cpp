@@ -36,6 +36,16 @@ int main() {
         }
         checked++;
     }
+    // hist3: three queued 3-bit face codes (6, 7 = no die) -> their packed face counts; two lookups
+    // give the histogram of a roll of up to six dice (play.cuh, face queue)
+    for (unsigned i = 0; i < 512; i++) {
+        unsigned want = 0;
+        for (int d = 0; d < 3; d++) {
+            const unsigned code = (i >> (3 * d)) & 7u;
+            if (code < 6u) want += 1u << (3 * code);
+        }
+        bad += lut.hist3[i] != want;
+    }
     printf("%d %d %zu %d\n", checked, bad, slots.size(), (int)sizeof(fb::ScoreLut));
     return bad != 0;
 }

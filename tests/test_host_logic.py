@@ -223,4 +223,4 @@ def test_score_lookup_table_layout(tmp_path):
     subprocess.run([gxx, "-std=c++17", "-O1", "-o", str(exe), str(Path(__file__).parent / "lut_check.cpp")],
                    check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
-    assert [int(x) for x in out] == [924, 0, 924, 26448]
+    assert [int(x) for x in out] == [924, 0, 924, 28496]
