@@ -11,10 +11,9 @@
 //
 // Data layout in HBM: one 80-byte Seat record per (game, seat), written by the seed kernels
 //   line 0  PCG state (16 B)
-//   line 1  face queue lo | score | highest_turn|queue holds a rejected half<<30|has_scored<<31 |
-//           farkles|rolls<<16
-//   line 2  turns|hot<<16 | smart-five uses|dice<<16 | smart-one uses|dice<<16 |
-//           face queue hi (25 bits) | queue length in bits<<25
+//   line 1  face queue lo | score | highest_turn|queue length in bits<<24|queue holds a rejected
+//           half<<30|has_scored<<31 | farkles|rolls<<16
+//   line 2  turns|hot<<16 | smart-five uses|dice<<16 | smart-one uses|dice<<16 | face queue hi
 //   line 3  PCG increment (16 B)
 //   line 4  st_d | kf|dt_d<<16 | dbase|tab_off<<16 | strategy table index   (seat_consts())
 //   game header 4 B  n_rounds | flags << 16 | HDR_LONG, written when the game ends; the seed
@@ -47,7 +46,7 @@
 namespace fb {
 
 constexpr int ROLL_LIMIT = 1000;  // src/farkle/game/engine.py:36
-constexpr uint32_t HIGH_MASK = 0x3fffffffu;
+constexpr uint32_t HIGH_MASK = 0x00ffffffu;  // highest_turn (< 3,000 points x 1,000 rolls)
 constexpr uint32_t HW_REJ = 1u << 30;  // the seat's face queue holds a rejected half (code 6)
 // Face queue (the dice of a seat's stream that are already drawn): 3-bit codes, next die in the low
 // bits, 0..5 a face, 6 a half NumPy's Lemire test rejects (it is skipped, but it was read).
@@ -56,10 +55,12 @@ constexpr uint32_t HW_REJ = 1u << 30;  // the seat's face queue holds a rejected
 #define FB_FQ_WORDS 3
 #endif
 constexpr int FQ_WORDS = FB_FQ_WORDS;            // 64-bit outputs per top-up
-constexpr int FQ_CAP_BITS = 57;                  // 19 codes; bits 25..30 of the high word carry the length
+constexpr int FQ_CAP_BITS = 63;                  // 21 codes in one 64-bit word
 constexpr int FQ_GEN_BITS = 6 * FQ_WORDS;        // two codes per output
-constexpr uint32_t FQ_LEN_SHIFT = 25;
-constexpr uint32_t FQ_HI_MASK = (1u << FQ_LEN_SHIFT) - 1u;
+constexpr uint32_t HW_LEN_SHIFT = 24;            // the record keeps the length in bits 24..29 of line 1 word 2
+constexpr uint32_t HW_LEN_MASK = 63u << HW_LEN_SHIFT;
+constexpr int FQ_IDLE = 63;  // queue length of a lane that is not playing: never short, never topped up
+static_assert(FQ_WORDS == 3, "one top-up must cover the longest roll (6 codes) for every lane it serves");
 constexpr uint32_t HW_SCORED = 1u << 31;
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr uint32_t HDR_LONG = 1u << 31;
@@ -67,7 +68,7 @@ constexpr uint32_t HDR_LONG = 1u << 31;
 struct __align__(16) Seat {
     uint4 state;  // PCG state lo0, lo1, hi0, hi1
     uint4 a;      // face queue lo | score | hw | farkles|rolls<<16
-    uint4 b;      // turns|hot<<16 | sf uses|dice<<16 | so uses|dice<<16 | face queue hi | length in bits<<25
+    uint4 b;      // turns|hot<<16 | sf uses|dice<<16 | so uses|dice<<16 | face queue hi
     uint4 inc;    // PCG increment
     uint4 cst;    // st_d | kf|dt_d<<16 | dbase|tab_off<<16 | strategy table index
 };
@@ -123,6 +124,10 @@ __device__ __forceinline__ void sts128(uint32_t smem_addr, const uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(smem_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
 }
+// u * 6 as its two 32-bit words (one IMAD.WIDE)
+__device__ __forceinline__ void mul_wide6(uint32_t u, uint32_t& lo, uint32_t& hi) {
+    asm("{ .reg .b64 t; mul.wide.u32 t, %2, 6; mov.b64 {%0, %1}, t; }" : "=r"(lo), "=r"(hi) : "r"(u));
+}
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -166,7 +171,7 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
     Pcg rng{0, 0, 0, 0};
     uint32_t hw = 0;
     uint64_t fq = 0;  // face queue of the active seat
-    int fq_bits = 0;  // 3 x the number of queued codes
+    int fq_bits = FQ_IDLE;  // 3 x the number of queued codes (FQ_IDLE while the lane has no game)
     int score = 0, st_d = 0, dt_d = 0;
     uint32_t c_fr = 0, c_th = 0, c_sf = 0, c_so = 0, kf = 0, dbase = 0, tab_off = 0;
     // active turn
@@ -184,10 +189,10 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
         rng.hi = (uint64_t)m0.z | ((uint64_t)m0.w << 32);
         rng.ilo = (uint64_t)i0.x | ((uint64_t)i0.y << 32);
         rng.ihi = (uint64_t)i0.z | ((uint64_t)i0.w << 32);
-        fq = (uint64_t)m1.x | ((uint64_t)(m2.w & FQ_HI_MASK) << 32);
-        fq_bits = (int)(m2.w >> FQ_LEN_SHIFT);
+        fq = (uint64_t)m1.x | ((uint64_t)m2.w << 32);
+        fq_bits = (int)((m1.z & HW_LEN_MASK) >> HW_LEN_SHIFT);
         score = (int)m1.y;
-        hw = m1.z;
+        hw = m1.z & ~HW_LEN_MASK;  // (the field stays clear in the register: the store ORs the length in)
         c_fr = m1.w;
         c_th = m2.x + 1u;  // n_turns += 1 (engine.py:237)
         c_sf = m2.y;
@@ -331,10 +336,12 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
         // That is 2.3-2.4 outputs computed per roll instead of three (2.13 are consumed), no
         // per-word state selects, and no per-die window arithmetic: a roll takes its n codes off
         // the queue with two shifts.
-        const bool playing = status == ST_PLAY;
+        // A top-up adds six codes, the longest roll, to every lane it serves, and a lane it does
+        // not serve holds more than that: one top-up per iteration at most.  Lanes without a game
+        // carry the length FQ_IDLE and are neither short nor served.
         const int need_bits = 3 * dice;
-        while (__any_sync(FULL, playing && fq_bits < need_bits)) {
-            if (playing && fq_bits <= FQ_CAP_BITS - FQ_GEN_BITS) {
+        if (__any_sync(FULL, fq_bits < need_bits)) {
+            if (fq_bits <= FQ_CAP_BITS - FQ_GEN_BITS) {
                 uint64_t shi = rng.hi, slo = rng.lo;
                 // Lemire per half: face = high word of half * 6, rejected when the low word is < 4
                 // (4 in 2^32); codes packed two per output, first-read half lowest
@@ -343,9 +350,11 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                 for (int w = 0; w < FQ_WORDS; w++) {
                     const uint64_t o = pcg_output(shi, slo);
                     pcg_step(shi, slo, rng.ihi, rng.ilo);
-                    const uint64_t m0 = (uint64_t)(uint32_t)o * 6u, m1 = (o >> 32) * 6u;
-                    minl = min(minl, min((uint32_t)m0, (uint32_t)m1));
-                    packed |= ((uint32_t)(m0 >> 32) + 8u * (uint32_t)(m1 >> 32)) << (6 * w);
+                    uint32_t l0, f0, l1, f1;
+                    mul_wide6((uint32_t)o, l0, f0);
+                    mul_wide6((uint32_t)(o >> 32), l1, f1);
+                    minl = min(minl, min(l0, l1));
+                    packed += (f0 + (f1 << 3)) << (6 * w);
                 }
                 if (minl < 4u) {  // redo the batch half by half, code 6 for a rejected half
                     shi = rng.hi;
@@ -370,7 +379,7 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
         }
 
         // ================= P: one roll (straight-line, no divergent branches) =====
-        if (playing) {
+        if (status == ST_PLAY) {
             const int n = dice;
             uint32_t hist;
             if (!(hw & HW_REJ)) {
@@ -451,8 +460,8 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                 hw = (hw & ~HIGH_MASK) | max(hw & HIGH_MASK, (uint32_t)banked);
                 const uint4 l0 = make_uint4((uint32_t)rng.lo, (uint32_t)(rng.lo >> 32), (uint32_t)rng.hi,
                                             (uint32_t)(rng.hi >> 32));
-                const uint4 l1 = make_uint4((uint32_t)fq, (uint32_t)score, hw, c_fr);
-                const uint4 l2 = make_uint4(c_th, c_sf, c_so, (uint32_t)(fq >> 32) | ((uint32_t)fq_bits << FQ_LEN_SHIFT));
+                const uint4 l1 = make_uint4((uint32_t)fq, (uint32_t)score, hw | ((uint32_t)fq_bits << HW_LEN_SHIFT), c_fr);
+                const uint4 l2 = make_uint4(c_th, c_sf, c_so, (uint32_t)(fq >> 32));
                 uint4* sp = reinterpret_cast<uint4*>(P.seats + (g * (uint32_t)k + (uint32_t)seat));
                 if (!K2) {
                     __stcg(sp, l0);
@@ -485,6 +494,7 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                         P.header[g] = (uint32_t)round | (err & HDR_LONG) |
                                       (((trigger < 0 ? FB_ROW_SAFETY_LIMIT : 0u) | (err & 0xffu)) << 16);
                         status = ST_NEED;
+                        fq_bits = FQ_IDLE;
                     } else {
                         // park this seat in its home slot, then seat the other one from its own
                         sts128(home, l0);
@@ -513,6 +523,7 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                         P.header[g] = (uint32_t)round | (err & HDR_LONG) |
                                       (((trigger < 0 ? FB_ROW_SAFETY_LIMIT : 0u) | (err & 0xffu)) << 16);
                         status = ST_NEED;
+                        fq_bits = FQ_IDLE;
                     } else {
                         // A trigger event (or k == 1) makes the prediction miss: restage the right
                         // record (the outstanding copies into the same slots must land first) and
@@ -610,7 +621,7 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishParams F) {
             }
             t_rolls += a.w >> 16;
             t_turns += b.x & 0xffffu;
-            t_ahead += (b.w >> FQ_LEN_SHIFT) / 6u;  // whole outputs (two 3-bit codes) drawn ahead and never read
+            t_ahead += ((a.z & HW_LEN_MASK) >> HW_LEN_SHIFT) / 6u;  // whole outputs (two codes) drawn ahead, never read
             if ((a.w >> 16) > 32767u || (a.z & HIGH_MASK) > 32767u || (b.y >> 16) > 32767u ||
                 (b.z >> 16) > 32767u || (b.x & 0xffffu) > 32767u || (b.x >> 16) > 32767u)
                 flags |= FB_ROW_I16_OVERFLOW;
