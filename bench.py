@@ -48,17 +48,19 @@ MEGA_K, MEGA_ROOT = (2, 3, 4, 5, 6, 8, 10, 12), 102   # configs/farkle_mega_conf
 # Lane-instruction model of SURVEY.md §8d (play kernel): W per PCG64-DXSM word, D per die, R per roll.
 # SURVEY's estimates were 28 / 8 / 90; the constants used are SASS-exact, from the ncu captures of the
 # two play_kernel variants (scripts/sass_model.py -> profiles/sass_model.json; these defaults are the
-# round-2 values): 3 W + 6 D + R is what the kernel EXECUTES per roll (three words and six die slots
-# are computed for every roll), W words + D dice + R rolls with the words and dice actually consumed
-# is the algorithmic work.
-SASS_MODEL_DEFAULT = {"k2": {"W": 26.0, "D": 7.2, "R": 142.5}, "generic": {"W": 26.0, "D": 7.2, "R": 149.8}}
+# round-2 values).  With the face queue a die costs nothing beyond its share of a word and of the roll
+# (D = 0): W words + R rolls, with the words the reference's generators would have produced, is the
+# algorithmic work; E rolls is what the kernel executes (the top-up computes ~10 % more words than
+# are consumed, and everything runs at the lane occupancy the kernel achieves).
+SASS_MODEL_DEFAULT = {"k2": {"W": 34.34, "D": 0.0, "R": 139.69, "E": 215.7},
+                      "generic": {"W": 34.74, "D": 0.0, "R": 148.58, "E": 227.68}}
 SURVEY_MODEL = {"W": 28.0, "D": 8.0, "R": 90.0}
 
 
 def sass_model() -> dict:
     try:
         got = json.loads((ROOT / "profiles" / "sass_model.json").read_text())
-        return {kind: {c: float(got[kind][c]) for c in "WDR"} | {"source": got[kind].get("source")}
+        return {kind: {c: float(got[kind][c]) for c in "WDRE"} | {"source": got[kind].get("source")}
                 for kind in ("k2", "generic")}
     except Exception:
         return SASS_MODEL_DEFAULT
@@ -155,7 +157,8 @@ def lane_ops(totals: np.ndarray, c: dict) -> tuple[float, float]:
     """(algorithmic, executed) lane instructions of one play_kernel launch from its work counters
     (totals: 3 rolls, 4 dice, 5 rng words) and the model constants `c`."""
     rolls, dice, words = float(totals[3]), float(totals[4]), float(totals[5])
-    return c["W"] * words + c["D"] * dice + c["R"] * rolls, (3 * c["W"] + 6 * c["D"] + c["R"]) * rolls
+    executed = c["E"] * rolls if "E" in c else (3 * c["W"] + 6 * c["D"] + c["R"]) * rolls
+    return c["W"] * words + c["D"] * dice + c["R"] * rolls, executed
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -578,8 +581,8 @@ def main() -> None:
     achieved = kern[dom]["ops"] / (kern[dom]["ms"] * 1e-3)
     tot = kern[dom]["totals"]
     # algorithmic HBM bytes of play_kernel per game: every 80-byte seat record is read once and
-    # its 48 mutable bytes written back once, plus the 4-byte game header
-    row_bytes_alg = kern[dom]["games"] * (dom * (80 + 48) + 4)
+    # its 32 bytes of counters written back once, plus the 4-byte game header
+    row_bytes_alg = kern[dom]["games"] * (dom * (80 + 32) + 4)
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -613,8 +616,9 @@ def main() -> None:
                   f"{kern[dom]['model']['D']}*dice + {kern[dom]['model']['R']}*rolls: SURVEY.md §8d's formula "
                   "with SASS-exact constants of this kernel (scripts/sass_model.py on the ncu capture under "
                   "profiles/; SURVEY's estimates were 28/8/90 -> frac_survey_constants); words, dice and rolls "
-                  "are returned by the kernel.  frac_executed charges the three words and six die slots "
-                  "the kernel computes for every roll = issue-active x lane efficiency"),
+                  "are returned by the kernel.  frac_executed charges everything the kernel executes per roll "
+                  f"({kern[dom]['model'].get('E')} lane-instructions: the surplus words of the face-queue top-up "
+                  "included) = issue-active x lane efficiency"),
         "per_game": {"rolls": float(tot[3] / tot[0]), "dice": float(tot[4] / tot[0]),
                      "rng_words": float(tot[5] / tot[0]),
                      "lane_ops": float(kern[dom]["ops"] / tot[0])},

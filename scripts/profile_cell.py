@@ -20,5 +20,6 @@ for rep in range(reps):
     ms = eng.last_play_kernel_ms()
     tot = res.totals.cpu().numpy()
     print(f"k={k} shuffles={shuffles} games={tot[0]} play_kernel {ms:.3f} ms "
-          f"{tot[0] / ms / 1e3:.1f} Mgames/s rolls/game {tot[3] / tot[0]:.1f}")
+          f"{tot[0] / ms / 1e3:.1f} Mgames/s rolls/game {tot[3] / tot[0]:.1f} "
+          f"rolls={tot[3]} dice={tot[4]} rng_words={tot[5]}")
 torch.cuda.synchronize()
