@@ -678,11 +678,12 @@ class CellSegment:
     n_shuffles: int
 
 
-# Measured on one B200 (profiles/r01_other_configs.json, the eight cells of one mega-config root):
-# a full-grid 4,300-shuffle cell takes 13.9 + 18.2 / k ms within 2 % for every k of the config
-# (2 -> 23.0, 4 -> 18.5, 6 -> 17.0, 12 -> 15.5): seat-exposures are constant per cell, a seat's
-# turns cost the same at every table size, and the per-game part shrinks with the game count.
-CELL_MS_CONST, CELL_MS_PER_K = 13.9, 18.2
+# Measured on one B200 (profiles/r02_cells.log + the 1.4-1.7 ms of permutation, seeding, finish and
+# tally passes per cell, profiles/r02_timeline.md): a full-grid 4,300-shuffle cell takes
+# 13.6 + 12.4 / k ms within 3 % for k = 2, 4, 6, 12 (19.6, 17.3, 15.5, 14.4): seat-exposures are
+# constant per cell, a seat's turns cost the same at every table size, and the per-game part shrinks
+# with the game count.  (Round 1's kernels: 13.9 + 18.2 / k.)
+CELL_MS_CONST, CELL_MS_PER_K = 13.6, 12.4
 CELL_MS_REFERENCE_EXPOSURES = 5160 * 4300
 SEGMENT_OVERHEAD_MS = 0.5       # kernel start-up and drain tail of one more launch
 
