@@ -25,6 +25,9 @@
 // games in flight stay L2 resident.  Two seats (K2): each seat has a home slot in the lane's
 // shared memory for the whole game (a switch stores three mutable lines to one slot and loads
 // five lines from the other); global memory is touched when a game starts and when it ends.
+// The generator state of line 0 runs AHEAD of the reference's by the halves already turned into
+// the face codes of the seat's queue (lines 1-2): only that seat's rolls read the stream, in
+// order, so every die is the reference's die (the G block of play_kernel).
 //
 // play_kernel   one game per lane, loop body = ONE ROLL, straight-line; persistent CTAs
 //               (one per SM); a lane whose game ended takes the next game from its warp's

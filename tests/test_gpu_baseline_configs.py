@@ -316,6 +316,44 @@ def test_play_cells_equals_one_launch_per_cell(eng, full_grid):
     assert np.array_equal(t.cpu().numpy(), want_t)
 
 
+def test_timeline_of_a_pipelined_cell_list(eng, full_grid):
+    """`fb_timeline`: one mark per kernel of the tournament path, in stream order, the preparation of
+    the next cell on its own lane and released by the end of the play kernel before it; nothing is
+    recorded when the hook is off."""
+    import torch
+
+    from farkle_ii_b200.layout import TALLY_WIDTH, TOTALS_WIDTH
+
+    n = len(full_grid)
+    table = eng.to_device(full_grid)
+    t = torch.zeros((1, n, TALLY_WIDTH), dtype=torch.int64, device=eng.device)
+    tot = torch.zeros(TOTALS_WIDTH, dtype=torch.int64, device=eng.device)
+    cells = [(3, 2, 0, 43, t, tot), (3, 4, 0, 43, t, tot), (3, 6, 0, 43, t, tot)]
+    eng.play_cells(cells, table)  # streams and events exist afterwards
+    torch.cuda.synchronize()
+    eng.timeline(False)
+    eng.play_cells(cells, table)
+    assert eng.timeline_marks() == []
+    eng.timeline(True)
+    eng.play_cells(cells, table)
+    marks = eng.timeline_marks()
+    eng.timeline(False)
+    main = [name for lane, name, _ in marks if lane == 0]
+    prep = [name for lane, name, _ in marks if lane == 1]
+    assert main == ["play_begin", "play_kernel", "finish", "gather"] * 3
+    assert prep == ["prepare_begin", "permute", "seed"] * 3          # (the first cell is prepared on lane 1 too)
+    at = {}
+    for lane, name, ms in marks:
+        at.setdefault((lane, name), []).append(ms)
+    for lane in (0, 1):  # marks of one stream are in stream order
+        times = [ms for ln, _name, ms in marks if ln == lane]
+        assert times == sorted(times)
+    # cell i+1 is prepared after cell i's play kernel has finished and before its own play kernel starts
+    for i in (1, 2):
+        assert at[(1, "prepare_begin")][i] >= at[(0, "play_kernel")][i - 1]
+        assert at[(1, "seed")][i] <= at[(0, "play_kernel")][i]
+
+
 # ------------------------------------------------------------------------ all-player statistics (f-3)
 @pytest.mark.parametrize("name,spb,with_ids", [("fast_54_4", 2, False), ("fast_42_2", 5, True), ("full_0_5", 1, False),
                                                ("full_42_6", 2, False), ("full_102_12", 3, True)])
