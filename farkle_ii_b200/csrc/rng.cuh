@@ -190,12 +190,37 @@ __host__ __device__ __forceinline__ void pcg_seed_coord(Pcg& g, const Coord& c) 
 
 // DXSM output of the current state (pcg_cm_random_r computes it from the
 // pre-step state).
+// Low 64 bits of a 64 x 64 product as three multiply-adds (one wide, two accumulating into its
+// high word); the compiler's own expansion is four instructions (two independent cross products,
+// the wide one and an add): one fewer issue slot per multiply matters more here than the shorter
+// chain (FB_MUL64_PLAIN keeps the plain product).
+__host__ __device__ __forceinline__ uint64_t mul64lo(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__) && !defined(FB_MUL64_PLAIN)
+    uint64_t r;
+    asm("{\n\t"
+        ".reg .u32 a0, a1, b0, b1, lo, hi;\n\t"
+        ".reg .u64 t;\n\t"
+        "mov.b64 {a0, a1}, %1;\n\t"
+        "mov.b64 {b0, b1}, %2;\n\t"
+        "mul.wide.u32 t, a0, b0;\n\t"
+        "mov.b64 {lo, hi}, t;\n\t"
+        "mad.lo.u32 hi, a0, b1, hi;\n\t"
+        "mad.lo.u32 hi, a1, b0, hi;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t"
+        "}"
+        : "=l"(r)
+        : "l"(a), "l"(b));
+    return r;
+#else
+    return a * b;
+#endif
+}
 __host__ __device__ __forceinline__ uint64_t pcg_output(uint64_t hi, uint64_t lo) {
     uint64_t h = hi;
     h ^= h >> 32;
-    h *= PCG_CHEAP_MULT;
+    h = mul64lo(h, PCG_CHEAP_MULT);
     h ^= h >> 48;
-    h *= (lo | 1u);
+    h = mul64lo(h, lo | 1u);
     return h;
 }
 // state = state * CHEAP_MULT + inc (mod 2^128)
