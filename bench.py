@@ -52,8 +52,8 @@ MEGA_K, MEGA_ROOT = (2, 3, 4, 5, 6, 8, 10, 12), 102   # configs/farkle_mega_conf
 # (D = 0): W words + R rolls, with the words the reference's generators would have produced, is the
 # algorithmic work; E rolls is what the kernel executes (the top-up computes ~10 % more words than
 # are consumed, and everything runs at the lane occupancy the kernel achieves).
-SASS_MODEL_DEFAULT = {"k2": {"W": 34.34, "D": 0.0, "R": 139.69, "E": 215.7},
-                      "generic": {"W": 34.74, "D": 0.0, "R": 148.58, "E": 227.68}}
+SASS_MODEL_DEFAULT = {"k2": {"W": 32.17, "D": 0.0, "R": 139.71, "E": 210.92},
+                      "generic": {"W": 32.4, "D": 0.0, "R": 148.86, "E": 222.65}}
 SURVEY_MODEL = {"W": 28.0, "D": 8.0, "R": 90.0}
 
 
