@@ -229,3 +229,19 @@ def play_h2h_block(root_seed, pair_id, order, seat1, seat2, *, n_completed_requi
                             C.c_int32(chunk_games), C.c_int32(target_score),
                             C.c_int32(max_rounds), _p(pr), _p(oc))
     return pr, oc[: int(pr[0]) - start]
+
+
+def scan_rejected_halves(root_seed, k, shuffle0, n_shuffles, strategies, *, target_score=10_000,
+                         max_rounds=200, cap=256) -> np.ndarray:
+    """Games of the cell that meet a rejected Lemire half: rows ``(shuffle_index, game_index, rejected
+    halves)`` (fixture helper for the rejection paths of the CUDA kernel; single-threaded)."""
+    st = np.ascontiguousarray(strategies, dtype=STRATEGY_DTYPE)
+    out = np.zeros((cap, 3), dtype=np.uint64)
+    fn = lib().fo_scan_rejected_halves
+    fn.restype = C.c_int64
+    n = fn(C.c_uint64(root_seed), C.c_int(k), C.c_uint64(shuffle0), C.c_int(n_shuffles), _p(st),
+           C.c_int(len(st)), C.c_int32(target_score), C.c_int32(max_rounds), _p(out), C.c_int64(cap))
+    if n < 0:
+        raise ValueError(f"fo_scan_rejected_halves failed: {n}")
+    return out[: min(int(n), cap)]
+

@@ -130,6 +130,7 @@ typedef struct {
     int has32;
     uint32_t saved;
     uint64_t words, dice; /* work counters: fresh 64-bit outputs / dice drawn */
+    uint64_t rejects;     /* halves the Lemire test threw away (fo_scan_rejected_halves) */
 } pcg_t;
 
 static void pcg_seed_words(pcg_t* g, const uint64_t w[4]) {
@@ -183,6 +184,7 @@ static inline int pcg_die(pcg_t* g) {
     if (left < rng_excl) {
         const uint32_t thr = (0xffffffffu - 5u) % rng_excl;
         while (left < thr) {
+            g->rejects++;
             if (!g->has32) g->words++;
             m = (uint64_t)pcg_next32(g) * rng_excl;
             left = (uint32_t)m;
@@ -472,7 +474,7 @@ static int take_turn(player_t* p, int final_round, int score_to_beat, uint64_t* 
 }
 
 typedef struct {
-    uint64_t rolls, dice, words, turns;
+    uint64_t rolls, dice, words, turns, rejects;
 } work_t;
 
 /* FarkleGame.play + _run_final_round — game/engine.py:436-550, flattened into
@@ -549,6 +551,7 @@ static void play_game(const fo_coord_t* seat_coord_base, int k, const fb_strateg
         for (int s = 0; s < k; s++) {
             work->dice += pl[s].rng.dice;
             work->words += pl[s].rng.words;
+            work->rejects += pl[s].rng.rejects;
         }
         work->turns += turns;
     }
@@ -627,7 +630,7 @@ static void* tour_worker(void* arg) {
     const size_t stride = row_stride(k);
     int32_t* perm = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
     uint8_t* rowbuf = (uint8_t*)calloc(1, stride);
-    work_t work = {0, 0, 0, 0};
+    work_t work = {0, 0, 0, 0, 0};
     for (int si = j->thread; si < j->n_shuffles; si += j->n_threads) {
         uint64_t shuffle = j->shuffle0 + (uint64_t)si;
         fo_permutation(j->root_seed, (uint64_t)k, shuffle, n, perm);
@@ -730,7 +733,7 @@ int fo_play_games(const uint64_t* coords /*[n][7]*/, uint64_t n_games, int k,
     if (k < 1 || k > FB_MAX_PLAYERS) return -2;
     const size_t stride = row_stride(k);
     uint8_t* rowbuf = (uint8_t*)calloc(1, stride);
-    work_t work = {0, 0, 0, 0};
+    work_t work = {0, 0, 0, 0, 0};
     for (uint64_t i = 0; i < n_games; i++) {
         const uint64_t* cc = coords + i * 7;
         fo_coord_t c = {cc[0], cc[1], cc[2], cc[3], cc[4], cc[5], cc[6], 0, 0};
@@ -785,3 +788,47 @@ int fo_play_h2h_block(uint64_t root_seed, uint64_t pair_id, int order, const fb_
     progress[3] = w1; progress[4] = w2;
     return 0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Test-fixture helper: which games of a tournament cell meet a REJECTED half   */
+/* (Lemire leftover < 4: four 32-bit values in 2^32, about seven games of an    */
+/* 11 M-game cell)?  tests/golden/make_golden_rejects.py uses it to pick the     */
+/* games that exercise the rejection paths of the CUDA kernel.  out[i] =         */
+/* {shuffle_index, game_index, rejected halves}; returns the number found        */
+/* (at most cap are stored).  Single-threaded per call: callers split the        */
+/* shuffle range.                                                                 */
+/* ------------------------------------------------------------------------- */
+int64_t fo_scan_rejected_halves(uint64_t root_seed, int k, uint64_t shuffle0, int n_shuffles,
+                                const fb_strategy_t* strategies, int n_strategies,
+                                int32_t target_score, int32_t max_rounds, uint64_t* out, int64_t cap) {
+    refresh_roll_limit();
+    if (k < 1 || k > FB_MAX_PLAYERS || n_strategies % k != 0 || n_shuffles < 0) return -2;
+    const int gps = n_strategies / k;
+    int32_t* perm = (int32_t*)malloc(sizeof(int32_t) * (size_t)n_strategies);
+    uint8_t row[16 + 32 * FB_MAX_PLAYERS];
+    int64_t found = 0;
+    for (int si = 0; si < n_shuffles; si++) {
+        const uint64_t shuffle = shuffle0 + (uint64_t)si;
+        fo_permutation(root_seed, (uint64_t)k, shuffle, n_strategies, perm);
+        for (int g = 0; g < gps; g++) {
+            fb_strategy_t st[FB_MAX_PLAYERS];
+            for (int s = 0; s < k; s++) st[s] = strategies[perm[g * k + s]];
+            fo_coord_t c = {FB_PURPOSE_TOURNAMENT_PLAYER, root_seed, (uint64_t)k, shuffle, 0, 0,
+                            (uint64_t)g, 0, 0};
+            work_t work = {0, 0, 0, 0, 0};
+            memset(row, 0, sizeof row);
+            play_game(&c, k, st, NULL, target_score, max_rounds, 0, 0, row, &work);
+            if (work.rejects) {
+                if (found < cap) {
+                    out[3 * found] = shuffle;
+                    out[3 * found + 1] = (uint64_t)g;
+                    out[3 * found + 2] = work.rejects;
+                }
+                found++;
+            }
+        }
+    }
+    free(perm);
+    return found;
+}
+

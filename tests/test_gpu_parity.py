@@ -93,6 +93,38 @@ def test_lemire_rejection_branch(eng, golden_dir):
             assert faces[r, :n].tolist() == case["dice"][r]
 
 
+def test_games_with_rejected_halves(eng, golden_dir):
+    """The face queue of play_kernel keeps a half that NumPy's Lemire test rejects as a skip code
+    (csrc/play.cuh).  tests/golden/rejects.json lists 18 tournament games of the full grid whose dice
+    meet such a half (found with the oracle, four 32-bit values in 2^32): each is played alone at its
+    explicit coordinates, and its whole shuffle through the tournament launch, rows / tallies / totals
+    (incl. the count of 64-bit outputs the reference's generators would have produced) against the
+    oracle."""
+    from farkle_ii_b200.strategies import generate_strategy_grid, pack_strategies
+
+    table = pack_strategies(generate_strategy_grid()[0])
+    games = json.loads((golden_dir / "rejects.json").read_text())["games"]
+    assert len(games) >= 10
+    by_k: dict[int, list] = {}
+    for g in games:
+        by_k.setdefault(g["k"], []).append(g)
+    for k, gs in by_k.items():
+        coords = np.array([[P_TPLAYER, g["root"], k, g["shuffle"], 0, 0, g["game"]] for g in gs], dtype=np.uint64)
+        ids = np.stack([fo.permutation(g["root"], k, g["shuffle"], len(table))[g["game"] * k:(g["game"] + 1) * k]
+                        for g in gs]).astype(np.int32)
+        rows, totals = eng.play_games(coords, k, table[ids], seat_strategy_ids=ids)
+        want_rows, want_tot = fo.play_games(coords, k, table[ids], seat_strategy_ids=ids)
+        assert rows.tobytes() == want_rows.tobytes(), k
+        assert np.array_equal(totals, want_tot), (k, totals[:8], want_tot[:8])
+    for g in games[::3]:  # the whole shuffle of every third game through the tournament launch
+        root, k, sh = g["root"], g["k"], g["shuffle"]
+        tallies, totals, rows = _play(eng, root, k, sh, 1, table)
+        want_t, want_tot, want_rows = fo.play_tournament(root, k, sh, 1, table, want_rows=True,
+                                                         want_game_seeds=True, n_threads=1)
+        assert rows.tobytes() == want_rows.tobytes(), g
+        assert np.array_equal(tallies, want_t) and np.array_equal(totals, want_tot), g
+
+
 def test_permutations(eng, golden_dir):
     perms = np.load(golden_dir / "perm.npz")
     for key in perms.files:

@@ -272,3 +272,22 @@ def test_fast_grid_seed42_full_cell(golden_dir):
     assert int(tallies[0][:, 4].sum()) == 252_520_900   # sum winning_score
     assert int(tallies[0][:, 5].sum()) == 474_671       # sum n_rounds
     assert int(tallies[0][:, 7].sum()) == 1_180_523     # sum winner_rolls
+
+
+def test_rejected_half_fixture(golden_dir):
+    """tests/golden/rejects.json (games whose dice meet a half the Lemire test rejects; the GPU suite
+    plays exactly these): the oracle finds the rejected halves where the fixture says, and nowhere
+    else in those shuffles."""
+    import json
+
+    from farkle_ii_b200.strategies import generate_strategy_grid, pack_strategies
+
+    table = pack_strategies(generate_strategy_grid()[0])
+    games = json.loads((golden_dir / "rejects.json").read_text())["games"]
+    assert len(games) == 18 and {g["k"] for g in games} == {2, 3, 4}
+    for g in games[::4]:
+        hits = fo.scan_rejected_halves(g["root"], g["k"], g["shuffle"], 1, table)
+        assert hits.tolist() == [[g["shuffle"], g["game"], g["rejects"]]]
+    # and a shuffle without one
+    assert len(fo.scan_rejected_halves(42, 2, 0, 1, table)) == 0
+
