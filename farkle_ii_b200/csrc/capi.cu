@@ -1439,9 +1439,11 @@ int fb_play_tournament_cells(const fb_cell_t* cells, int n_cells, int n_ahead,
     }
     // play_kernel is persistent and fills every SM (all registers, all shared memory): nothing runs
     // beside it, and a small kernel that gets onto the SMs first keeps its CTAs out.  So the
-    // preparation of cell i+1 is released by the END of cell i's play_kernel: it then runs beside
-    // cell i's finish and tally passes (which only read slot i), and the window between two play
-    // kernels is max(prepare, finish + gather) instead of their sum.  (Slot reuse: the passes of
+    // preparation of cell i+1 is released by the END of cell i's play_kernel and runs beside cell
+    // i's finish and tally passes (which only read slot i).  Measured gain: small -- sharing SMs,
+    // the permutation kernel (209 KB of shared memory per SM) and the gathers (which want the L1)
+    // each take about as long as both in sequence; what the second stream buys is the seed pass
+    // under the tail of the tally pass (profiles/r02_timeline.md).  (Slot reuse: the passes of
     // cell i-1, which read the slot cell i+1 is prepared in, precede play_kernel(i) on `stream`.)
     for (int i = 0; i < n_cells; i++) {
         const int slot = (slot0 + i) & 1;
