@@ -334,14 +334,14 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
         // (engine.py:85-101: Generator.integers(1, 7, size=n) draws n Lemire-bounded values from
         // the buffered halves, re-drawing a half whose low product word is < 4), and nothing else
         // reads that stream.  So the halves can be turned into faces AHEAD of the rolls that use
-        // them: every seat keeps a queue of 3-bit face codes, and the warp tops all its queues up by
-        // two 64-bit outputs (four codes) whenever some lane's queue is shorter than its next roll.
-        // That is 2.3-2.4 outputs computed per roll instead of three (2.13 are consumed), no
-        // per-word state selects, and no per-die window arithmetic: a roll takes its n codes off
-        // the queue with two shifts.
-        // A top-up adds six codes, the longest roll, to every lane it serves, and a lane it does
-        // not serve holds more than that: one top-up per iteration at most.  Lanes without a game
-        // carry the length FQ_IDLE and are neither short nor served.
+        // them: every seat keeps a queue of 3-bit face codes, and the warp tops its queues up by
+        // three 64-bit outputs (six codes) whenever some lane's queue is shorter than its next roll.
+        // That is 2.2 outputs computed per roll instead of three (2.13 are consumed), no per-word
+        // state selects, and no per-die window arithmetic: a roll takes its n codes off the queue
+        // with two shifts.
+        // A top-up adds six codes, the longest roll, to every lane it serves (the lanes with room
+        // for them), and a lane it does not serve holds more than that: one top-up per iteration
+        // at most.  Lanes without a game carry the length FQ_IDLE and are neither short nor served.
         const int need_bits = 3 * dice;
         if (__any_sync(FULL, fq_bits < need_bits)) {
             if (fq_bits <= FQ_CAP_BITS - FQ_GEN_BITS) {
