@@ -92,6 +92,32 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+# Test builds of the same sources (never loaded by the product path; FARKLE_B200_LIB selects one):
+#   rejects  Lemire threshold 2^30 instead of 4: one half in four is rejected, so the face queue's
+#            handling of rejected halves runs all the time (tests/rejects_variant_check.py; the oracle
+#            has the matching run-time knob FB_TEST_LEMIRE_THR)
+TEST_VARIANTS = {"rejects": ["-DFB_LEMIRE_THR=0x40000000u"]}
+
+
+def variant_path(name: str) -> Path:
+    return PKG_DIR / f"libfarkle_b200_{name}.so"
+
+
+def build_variant(name: str, defines: list[str] | None = None, force: bool = False) -> Path:
+    """Compile ``csrc/capi.cu`` with extra ``-D`` defines into ``libfarkle_b200_<name>.so`` (in-tree,
+    git-ignored, travels with ``gpurun``).  Up-to-date files are kept."""
+    out = variant_path(name)
+    defines = list(TEST_VARIANTS[name] if defines is None else defines)
+    if not force and out.exists() and all(src.stat().st_mtime <= out.stat().st_mtime for src in sources()):
+        return out
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    proc = subprocess.run([nvcc, *NVCC_FLAGS, *defines, "-o", str(out), str(CSRC / "capi.cu")],
+                          capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{proc.stdout}\n{proc.stderr}")
+    return out
+
+
 _lib: C.CDLL | None = None
 
 _u64, _u32, _i32, _int, _vp, _sz = (C.c_uint64, C.c_uint32, C.c_int32, C.c_int, C.c_void_p,

@@ -51,6 +51,13 @@ namespace fb {
 constexpr int ROLL_LIMIT = 1000;  // src/farkle/game/engine.py:36
 constexpr uint32_t HIGH_MASK = 0x00ffffffu;  // highest_turn (< 3,000 points x 1,000 rolls)
 constexpr uint32_t HW_REJ = 1u << 30;  // the seat's face queue holds a rejected half (code 6)
+// Lemire threshold of Generator.integers(1, 7): a half whose low product word is below it is
+// re-drawn; NumPy's value is (2^32 - 6) % 6 = 4.  Test builds raise it (scripts/build_variant.py,
+// -DFB_LEMIRE_THR=0x40000000u: one half in four rejected) so that the rejection paths of the face
+// queue run all the time; the oracle has the matching run-time knob FB_TEST_LEMIRE_THR.
+#ifndef FB_LEMIRE_THR
+#define FB_LEMIRE_THR 4u
+#endif
 // Face queue (the dice of a seat's stream that are already drawn): 3-bit codes, next die in the low
 // bits, 0..5 a face, 6 a half NumPy's Lemire test rejects (it is skipped, but it was read).
 // The queue length is kept in BITS (3 per code): it is the shift count of an insert as it stands.
@@ -359,7 +366,7 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                     minl = min(minl, min(l0, l1));
                     packed += (f0 + (f1 << 3)) << (6 * w);
                 }
-                if (minl < 4u) {  // redo the batch half by half, code 6 for a rejected half
+                if (minl < FB_LEMIRE_THR) {  // redo the batch half by half, code 6 for a rejected half
                     shi = rng.hi;
                     slo = rng.lo;
                     packed = 0;
@@ -367,8 +374,8 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                         const uint64_t o = pcg_output(shi, slo);
                         pcg_step(shi, slo, rng.ihi, rng.ilo);
                         const uint32_t u0 = (uint32_t)o, u1 = (uint32_t)(o >> 32);
-                        const uint32_t c0 = u0 * 6u < 4u ? 6u : __umulhi(u0, 6u);
-                        const uint32_t c1 = u1 * 6u < 4u ? 6u : __umulhi(u1, 6u);
+                        const uint32_t c0 = u0 * 6u < FB_LEMIRE_THR ? 6u : __umulhi(u0, 6u);
+                        const uint32_t c1 = u1 * 6u < FB_LEMIRE_THR ? 6u : __umulhi(u1, 6u);
                         packed |= (c0 | (c1 << 3)) << (6 * w);
                     }
                     hw |= HW_REJ;
@@ -401,8 +408,8 @@ __global__ void __launch_bounds__(PLAY_THREADS, 1) play_kernel(const PlayParams 
                         const uint64_t o = pcg_output(rng.hi, rng.lo);
                         pcg_step(rng.hi, rng.lo, rng.ihi, rng.ilo);
                         const uint32_t u0 = (uint32_t)o, u1 = (uint32_t)(o >> 32);
-                        const uint32_t c0 = u0 * 6u < 4u ? 6u : __umulhi(u0, 6u);
-                        const uint32_t c1 = u1 * 6u < 4u ? 6u : __umulhi(u1, 6u);
+                        const uint32_t c0 = u0 * 6u < FB_LEMIRE_THR ? 6u : __umulhi(u0, 6u);
+                        const uint32_t c1 = u1 * 6u < FB_LEMIRE_THR ? 6u : __umulhi(u1, 6u);
                         fq = c0 | (c1 << 3);
                         fq_bits = 6;
                         a_words += 1u;

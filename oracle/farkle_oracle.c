@@ -176,13 +176,19 @@ static inline uint32_t pcg_next32(pcg_t* g) {
 }
 
 /* Generator.integers(1, 7) — Lemire 32-bit path; game/engine.py:101. */
+/* Test knob shared with the CUDA library (FB_TEST_LEMIRE_THR=t, 4 <= t <= 2^31): a half whose low
+ * product word is below t is re-drawn.  NumPy's threshold is 4 (four 32-bit values in 2^32); the
+ * knob makes rejected halves frequent so that the tests can exercise the kernel's handling of
+ * them.  Refreshed at every exported play call (refresh_roll_limit). */
+static uint32_t g_lemire_thr = 4u;
+static void refresh_roll_limit(void);
 static inline int pcg_die(pcg_t* g) {
     const uint32_t rng_excl = 6;
     if (!g->has32) g->words++;
     uint64_t m = (uint64_t)pcg_next32(g) * rng_excl;
     uint32_t left = (uint32_t)m;
-    if (left < rng_excl) {
-        const uint32_t thr = (0xffffffffu - 5u) % rng_excl;
+    const uint32_t thr = g_lemire_thr; /* (0xffffffff - 5) % 6 == 4 without the knob */
+    if (left < (thr > rng_excl ? thr : rng_excl)) {
         while (left < thr) {
             g->rejects++;
             if (!g->has32) g->words++;
@@ -214,7 +220,8 @@ void fo_roll_dice_state(const uint64_t state_inc[4], int has32, uint32_t saved,
     g.inc = ((u128)state_inc[2] << 64) | state_inc[3];
     g.has32 = has32;
     g.saved = saved;
-    g.words = g.dice = 0;
+    g.words = g.dice = g.rejects = 0;
+    refresh_roll_limit();
     for (int r = 0; r < n_rolls; r++)
         for (int i = 0; i < 6; i++) faces_out[r * 6 + i] = i < n_dice[r] ? (uint8_t)pcg_die(&g) : 0;
 }
@@ -397,6 +404,9 @@ static void refresh_roll_limit(void) {
     const char* e = getenv("FB_TEST_ROLL_LIMIT");
     const int v = e ? atoi(e) : ROLL_LIMIT;
     g_roll_limit = (v >= 1 && v <= ROLL_LIMIT) ? v : ROLL_LIMIT;
+    const char* t = getenv("FB_TEST_LEMIRE_THR");
+    const unsigned long thr = t ? strtoul(t, NULL, 0) : 4ul;
+    g_lemire_thr = (thr >= 4ul && thr <= 0x80000000ul) ? (uint32_t)thr : 4u;
 }
 
 typedef struct {

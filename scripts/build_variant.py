@@ -1,10 +1,10 @@
 #!/usr/bin/env python
-"""Build a variant of the library with extra -D defines: python scripts/build_variant.py NAME -DFOO=1 ...
+"""Build a variant of the library with extra -D defines: python scripts/build_variant.py NAME [-DFOO=1 ...]
 
 Writes farkle_ii_b200/libfarkle_b200_NAME.so (git-ignored, travels with gpurun); run with
-FARKLE_B200_LIB=farkle_ii_b200/libfarkle_b200_NAME.so.
+FARKLE_B200_LIB=farkle_ii_b200/libfarkle_b200_NAME.so.  Without defines NAME must be one of
+`_native.TEST_VARIANTS` (e.g. `rejects`).
 """
-import subprocess
 import sys
 from pathlib import Path
 
@@ -13,7 +13,4 @@ sys.path.insert(0, str(ROOT))
 from farkle_ii_b200 import _native  # noqa: E402
 
 name, defines = sys.argv[1], sys.argv[2:]
-out = _native.PKG_DIR / f"libfarkle_b200_{name}.so"
-cmd = ["nvcc", *_native.NVCC_FLAGS, *defines, "-o", str(out), str(_native.CSRC / "capi.cu")]
-subprocess.run(cmd, check=True)
-print(out)
+print(_native.build_variant(name, defines or None, force=True))

@@ -125,6 +125,26 @@ def test_games_with_rejected_halves(eng, golden_dir):
         assert np.array_equal(tallies, want_t) and np.array_equal(totals, want_tot), g
 
 
+def test_frequent_rejected_halves_variant():
+    """The rejection paths of the face queue under load: a TEST BUILD of the same sources with the
+    Lemire threshold raised to 2^30 (one half in four rejected; `_native.TEST_VARIANTS`), loaded by a
+    subprocess through FARKLE_B200_LIB, against the oracle with the matching knob
+    (tests/rejects_variant_check.py): rows, tallies, totals of k = 2, 3, 4, 5, 12 cells."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    from farkle_ii_b200 import _native
+
+    lib = _native.build_variant("rejects")  # built by __graft_entry__.build(); kept when up to date
+    env = dict(os.environ, FARKLE_B200_LIB=str(lib), FB_TEST_LEMIRE_THR="0x40000000")
+    proc = subprocess.run([sys.executable, str(Path(__file__).parent / "rejects_variant_check.py")], env=env,
+                          capture_output=True, text=True, timeout=900)
+    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+    assert proc.stdout.count(": ok;") == 6, proc.stdout
+
+
 def test_permutations(eng, golden_dir):
     perms = np.load(golden_dir / "perm.npz")
     for key in perms.files:
