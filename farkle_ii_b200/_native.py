@@ -9,14 +9,13 @@ raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import shutil
 import subprocess
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
-import os
-
 # FARKLE_B200_LIB: load another build of the same sources (kernel experiments: scripts/build_variant.py)
 LIB_PATH = Path(os.environ.get("FARKLE_B200_LIB") or PKG_DIR / "libfarkle_b200.so")
 HEADER = PKG_DIR.parent / "include" / "farkle_b200.h"
