@@ -17,7 +17,8 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 # FARKLE_B200_LIB: load another build of the same sources (kernel experiments: scripts/build_variant.py)
-LIB_PATH = Path(os.environ.get("FARKLE_B200_LIB") or PKG_DIR / "libfarkle_b200.so")
+DEFAULT_LIB_PATH = PKG_DIR / "libfarkle_b200.so"  # what build() writes
+LIB_PATH = Path(os.environ.get("FARKLE_B200_LIB") or DEFAULT_LIB_PATH)  # what lib() loads
 HEADER = PKG_DIR.parent / "include" / "farkle_b200.h"
 
 NVCC_FLAGS = [
@@ -69,18 +70,18 @@ def sources() -> list[Path]:
 
 
 def is_stale() -> bool:
-    if not LIB_PATH.exists():
+    if not DEFAULT_LIB_PATH.exists():
         return True
-    built = LIB_PATH.stat().st_mtime
+    built = DEFAULT_LIB_PATH.stat().st_mtime
     return any(src.stat().st_mtime > built for src in sources())
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile ``csrc/capi.cu`` for sm_100a with nvcc (cross-compiles without a GPU)."""
     if not force and not is_stale():
-        return LIB_PATH
+        return DEFAULT_LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), str(CSRC / "capi.cu")]
+    cmd = [nvcc, *NVCC_FLAGS, "-o", str(DEFAULT_LIB_PATH), str(CSRC / "capi.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     proc = subprocess.run(cmd, capture_output=True, text=True)
@@ -88,7 +89,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError(f"nvcc failed:\n{proc.stdout}\n{proc.stderr}")
     if verbose:
         print(proc.stderr)
-    return LIB_PATH
+    return DEFAULT_LIB_PATH
 
 
 # Test builds of the same sources (never loaded by the product path; FARKLE_B200_LIB selects one):
